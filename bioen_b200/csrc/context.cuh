@@ -1,0 +1,403 @@
+// context.cuh -- device-resident BioEn problem: yTilde in HBM + everything one evaluation needs.
+//
+// HBM layout (all fp64):
+//   Y        M x ld   row-major copy of yTilde, ld = N rounded up to 16 (rows start 128-byte aligned);
+//                     described to the TMA unit by one 2-D tensor map {N, M} with 32 x 128 boxes
+//   N-vectors         w (or E) padded with zeros to a multiple of 128 (1-D bulk copies never run off the end)
+//   M-vectors         Yobs, avg, msum (+3 tail scalars), ab = interleaved {a_i, b_i}; padded to 32
+//   partialA/B        [slots][Mpad] / [slots][Npad] partial sums of the two passes (slots <= 2 for the column
+//                     pass on any N >= 19 k, a handful for the row pass)
+//   sc[64]            the device scalar file (vector_kernels.cuh)
+//
+// One evaluation = 2 passes over Y (logw) or 4 (forces, unfused) + a few O(N)/O(M) kernels, all enqueued
+// on one stream with no host synchronisation; the caller fetches sc[] when it needs numbers.
+#pragma once
+#include <vector>
+
+#include "comm.cuh"
+#include "stream_pass.cuh"
+#include "vector_kernels.cuh"
+
+namespace bioen {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) {
+            CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+            CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+        }
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess)
+            throw CudaError("bioen_b200: driver does not provide cuTensorMapEncodeTiled");
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+inline int round_up(long long a, long long b) { return (int)(((a + b - 1) / b) * b); }
+
+class Context {
+   public:
+    int M, N;            // local matrix shape (N = this rank's columns)
+    long long N_total;   // all columns over all ranks
+    long long ld = 0;    // row stride of Y in doubles
+    int Mpad, Npad, nRT, nCB;
+    int device, num_sms;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    Comm* comm = nullptr;  // not owned
+    int nranks = 1;
+
+    // pass geometry (shared by both passes)
+    long long T, chunk;
+    int grid, slotsA, slotsB;
+    int evict_first;
+    int vec_blocks_n, vec_blocks_m;
+
+    double* Y = nullptr;
+    DevBuf<double> Yown;
+    CUtensorMap tmap;
+
+    DevBuf<double> partialA, partialB, ab, avg, msum, Yobs, w, aux_n, aux_n2, Gv, sc, red_partials, lse_all;
+    DevBuf<unsigned int> ticket;
+    double* h_sc = nullptr;  // pinned
+    double theta = 0.0;
+    bool have_logw = false, have_forces = false;
+    long long passes_launched = 0, kernels_launched = 0;
+
+    Context(int m, int n, int dev, cudaStream_t user_stream = nullptr) : M(m), N(n), N_total(n), device(dev) {
+        if (m <= 0 || n <= 0) throw std::invalid_argument("bioen_b200: matrix dimensions must be positive");
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            throw CudaError("bioen_b200: this library is built for sm_100a (Blackwell B200) only");
+        num_sms = prop.multiProcessorCount;
+        if (user_stream) {
+            stream = user_stream;
+            own_stream = false;
+        } else {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        }
+        nRT = (M + kTileR - 1) / kTileR;
+        nCB = (N + kTileC - 1) / kTileC;
+        Mpad = nRT * kTileR;
+        Npad = nCB * kTileC;
+        T = (long long)nRT * nCB;
+        const long long ncta = T < num_sms ? T : num_sms;
+        chunk = (T + ncta - 1) / ncta;
+        grid = (int)((T + chunk - 1) / chunk);
+        auto slots = [&](long long L) {
+            long long s = (L - 1) / chunk + 2;
+            return (int)(s < grid ? s : grid);
+        };
+        slotsA = slots(nCB);
+        slotsB = slots(nRT);
+        vec_blocks_n = std::min((N + kVecThreads - 1) / kVecThreads, num_sms * 4);
+        vec_blocks_m = std::min((M + kVecThreads - 1) / kVecThreads, num_sms * 4);
+
+        partialA.alloc((size_t)slotsA * Mpad);
+        partialB.alloc((size_t)slotsB * Npad);
+        ab.alloc((size_t)2 * Mpad);
+        avg.alloc(Mpad);
+        msum.alloc(Mpad + 8);
+        Yobs.alloc(Mpad);
+        w.alloc(Npad);
+        sc.alloc(SC_COUNT);
+        red_partials.alloc((size_t)std::max(vec_blocks_n, vec_blocks_m) * 4 + 16);
+        ticket.alloc(4);
+        lse_all.alloc(2 * 64);
+        CUDA_CHECK(cudaHostAlloc(&h_sc, SC_COUNT * sizeof(double), cudaHostAllocDefault));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kRowPass, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kRowPass, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
+    }
+
+    ~Context() {
+        if (h_sc) cudaFreeHost(h_sc);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    void set_comm(Comm* c) {
+        comm = c;
+        nranks = c ? c->nranks : 1;
+        if (nranks > 64) throw std::invalid_argument("bioen_b200: at most 64 ranks");
+    }
+
+    // ---- matrix -------------------------------------------------------------------------------
+    void upload_matrix(const double* host, size_t ld_host) {
+        ld = round_up(N, 16);
+        Yown.release();
+        CUDA_CHECK(cudaMalloc(&Yown.p, (size_t)M * ld * sizeof(double)));
+        Yown.n = (size_t)M * ld;
+        Y = Yown.p;
+        if (ld != N) CUDA_CHECK(cudaMemsetAsync(Y, 0, (size_t)M * ld * sizeof(double), stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(Y, ld * sizeof(double), host, ld_host * sizeof(double), (size_t)N * sizeof(double),
+                                     M, cudaMemcpyHostToDevice, stream));
+        make_tensor_map();
+    }
+    // use a matrix that already lives in HBM (row stride `ld_dev` doubles, must be even; base 16-byte aligned)
+    void adopt_matrix(double* dev, size_t ld_dev) {
+        if ((ld_dev & 1) || (reinterpret_cast<uintptr_t>(dev) & 15))
+            throw std::invalid_argument("bioen_b200: adopted yTilde needs an even row stride and a 16-byte aligned base");
+        if (ld_dev < (size_t)N) throw std::invalid_argument("bioen_b200: row stride smaller than N");
+        Yown.release();
+        Y = dev;
+        ld = (long long)ld_dev;
+        make_tensor_map();
+    }
+    void make_tensor_map() {
+        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)kTileC, (cuuint32_t)kTileR};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, Y, gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char buf[128];
+            snprintf(buf, sizeof buf, "bioen_b200: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+            throw CudaError(buf);
+        }
+        // a matrix that fits in L2 with room to spare is kept there between the two passes
+        evict_first = ((double)M * (double)ld * 8.0 > 80.0e6) ? 1 : 0;
+    }
+
+    // ---- per-method constant data ------------------------------------------------------------------
+    void h2d(double* dst, const double* src, size_t n) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    void d2h(double* dst, const double* src, size_t n) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    void d2d(double* dst, const double* src, size_t n) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    }
+    void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+
+    void set_observations(const double* Y_host) { h2d(Yobs.p, Y_host, M); }
+    void set_theta(double th) { theta = th; }
+
+    // logw: reference log-weights G (this rank's slice); log s0 = log sum_j exp(G_j) over ALL ranks
+    void set_logw(const double* G_host, bool on_device = false) {
+        Gv.alloc(N);
+        if (on_device) d2d(Gv.p, G_host, N); else h2d(Gv.p, G_host, N);
+        aux_n.alloc(Npad);  // scratch x for the lse of G
+        d2d(aux_n.p, Gv.p, N);
+        launch_lse(aux_n.p, nullptr, nullptr, 0.0, nullptr, false);
+        gather_lse();
+        // log s0 = M + log S from the (gathered) pairs; tiny host round trip, once per problem
+        std::vector<double> pairs(2 * nranks);
+        d2h(pairs.data(), lse_pairs(), 2 * nranks);
+        sync();
+        double Mx = pairs[0], S = pairs[1];
+        for (int r = 1; r < nranks; ++r) {
+            const double mm = std::max(Mx, pairs[2 * r]);
+            S = S * std::exp(Mx - mm) + pairs[2 * r + 1] * std::exp(pairs[2 * r] - mm);
+            Mx = mm;
+        }
+        const double logs0 = Mx + std::log(S);
+        CUDA_CHECK(cudaMemcpyAsync(sc.p + SC_LOGS0, &logs0, sizeof(double), cudaMemcpyHostToDevice, stream));
+        sync();
+        have_logw = true;
+    }
+    // forces: reference weights w0 (this rank's slice)
+    void set_forces(const double* w0_host, bool on_device = false) {
+        Gv.alloc(N);      // holds w0
+        if (on_device) d2d(Gv.p, w0_host, N); else h2d(Gv.p, w0_host, N);
+        aux_n.alloc(Npad);   // x_j, later E_j (zero padded: it feeds the row pass)
+        aux_n2.alloc(Npad);  // lr_j
+        have_forces = true;
+    }
+
+    // ---- kernel launch helpers ---------------------------------------------------------------------
+    const double* lse_pairs() const { return nranks > 1 ? lse_all.p : sc.p + SC_LSE_MAX; }
+
+    void launch_lse(double* x, const double* xp, const double* d, double stp, const double* w0, bool from_col) {
+        LseArgs a{};
+        a.n = N; a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.w0 = w0;
+        a.col_partial = from_col ? partialB.p : nullptr;
+        a.col_ld = Npad; a.col_L = nRT; a.col_chunk = chunk;
+        a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+        k_update_lse<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+        ++kernels_launched;
+    }
+    void gather_lse() {
+        if (nranks > 1) comm->allgather(sc.p + SC_LSE_MAX, lse_all.p, 2, stream);
+    }
+    template <int MODE, bool SUB>
+    void launch_pass(const double* vN, const double* vMb) {
+        PassArgs a{};
+        a.nRT = nRT; a.nCB = nCB; a.T = T; a.chunk = chunk; a.evict_first = evict_first;
+        a.vN = vN; a.vMb = vMb; a.ab = ab.p;
+        a.partial = (MODE == kRowPass) ? partialA.p : partialB.p;
+        a.ld = (MODE == kRowPass) ? Mpad : Npad;
+        stream_pass_kernel<MODE, SUB><<<grid, kPassThreads, kPassSmemBytes, stream>>>(tmap, a);
+        ++passes_launched;
+        ++kernels_launched;
+    }
+    // finish a row pass that produced avg (logw: tail = 3 weighted sums, forces: tail = KL)
+    void finalize_rows(bool is_forces, int ntail, bool ab_with_avg) {
+        FinalizeArgs a{};
+        a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = chunk;
+        a.Y = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.ab_with_avg = ab_with_avg ? 1 : 0;
+        a.is_forces = is_forces ? 1 : 0; a.theta = theta;
+        a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+        a.tail = msum.p + M;
+        if (nranks > 1) {
+            k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+            ++kernels_launched;
+            comm->allreduce_sum(msum.p, M + ntail, stream);
+            a.msum = msum.p;
+        }
+        k_finalize_rows<<<(M + kVecThreads - 1) / kVecThreads, kVecThreads, 0, stream>>>(a);
+        ++kernels_launched;
+    }
+
+    // ---- log-weights evaluation (c_bioen_kernels_logw.c:525-561) ------------------------------------------
+    // x (device, N): evaluated point; when xp != nullptr it is first formed as xp + stp*d.
+    // grad == nullptr -> objective only (one pass over Y).  ddir: optional direction for sc[SC_DG].
+    void logw_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir) {
+        if (!have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
+        launch_lse(x, xp, d, stp, nullptr, false);
+        gather_lse();
+        {
+            LogwWeightsArgs a{};
+            a.n = N; a.g = x; a.G = Gv.p; a.w = w.p; a.lse_pairs = lse_pairs(); a.nranks = nranks;
+            a.msum_tail = msum.p + M; a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+            k_logw_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_pass<kRowPass, false>(w.p, nullptr);
+        finalize_rows(false, 3, true);
+        if (!grad) return;
+        launch_pass<kColPass, true>(nullptr, nullptr);
+        {
+            LogwGradArgs a{};
+            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = chunk;
+            a.g = x; a.G = Gv.p; a.w = w.p; a.d = ddir; a.grad = grad; a.theta = theta;
+            a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+            k_logw_grad<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        if (nranks > 1) comm->allreduce_sum(sc.p + SC_DG, 3, stream);  // dg, ||g||^2, ||x||^2
+    }
+    // weights only (the reference's _get_weights): w normalised over all ranks; returns nothing, see sc[]
+    void logw_weights_only(double* x) {
+        launch_lse(x, nullptr, nullptr, 0.0, nullptr, false);
+        gather_lse();
+        LogwWeightsArgs a{};
+        a.n = N; a.g = x; a.G = x; a.w = w.p; a.lse_pairs = lse_pairs(); a.nranks = nranks;
+        a.msum_tail = msum.p + M; a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+        k_logw_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+        ++kernels_launched;
+    }
+
+    // ---- forces evaluation (c_bioen_kernels_forces.c:43-76) ----------------------------------------------
+    // x (device, M): forces; formed as xp + stp*d when xp != nullptr.  The M-dimensional state is replicated
+    // on every rank.  grad == nullptr -> objective only (two passes over Y).
+    void forces_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir) {
+        if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
+        {
+            ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p};
+            k_forces_update<<<1, 1024, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_pass<kColPass, false>(nullptr, nullptr);                 // x_j = sum_i f_i y_ij
+        launch_lse(aux_n.p, nullptr, nullptr, 0.0, Gv.p, true);          // assemble x_j, (max, sum w0 e^{x-max})
+        gather_lse();
+        {
+            ForcesWeightsArgs a{};
+            a.n = N; a.x = aux_n.p; a.w0 = Gv.p; a.w = w.p; a.lr = aux_n2.p; a.lse_pairs = lse_pairs();
+            a.nranks = nranks; a.msum_tail = msum.p + M; a.partials = red_partials.p; a.ticket = ticket.p;
+            a.sc = sc.p;
+            k_forces_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_pass<kRowPass, false>(w.p, nullptr);                     // avg_i
+        finalize_rows(true, 1, false);                                  // r_i, chi2, f; ab = {r_i, 0}
+        if (!grad) return;
+        launch_pass<kColPass, false>(nullptr, nullptr);                 // t_j = sum_i y_ij r_i
+        {
+            ForcesEArgs a{};
+            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = chunk;
+            a.w = w.p; a.lr = aux_n2.p; a.E = aux_n.p; a.theta = theta;   // E overwrites x_j (no longer needed)
+            k_forces_E<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_pass<kRowPass, true>(aux_n.p, avg.p);                    // grad_i = sum_j (y_ij - avg_i) E_j
+        {
+            ForcesGradArgs a{};
+            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = chunk;
+            a.d = ddir; a.grad = grad; a.sc = sc.p;
+            if (nranks > 1) {
+                k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+                ++kernels_launched;
+                comm->allreduce_sum(msum.p, M, stream);
+                a.msum = msum.p;
+            }
+            k_forces_grad<<<1, 1024, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+    }
+    // weights only (the reference's _get_weights_from_forces): leaves normalised w in `w`
+    void forces_weights_only(double* x) {
+        ForcesUpdateArgs u{M, x, nullptr, nullptr, 0.0, ab.p, sc.p};
+        k_forces_update<<<1, 1024, 0, stream>>>(u);
+        launch_pass<kColPass, false>(nullptr, nullptr);
+        launch_lse(aux_n.p, nullptr, nullptr, 0.0, Gv.p, true);
+        gather_lse();
+        ForcesWeightsArgs a{};
+        a.n = N; a.x = aux_n.p; a.w0 = Gv.p; a.w = w.p; a.lr = aux_n2.p; a.lse_pairs = lse_pairs();
+        a.nranks = nranks; a.msum_tail = msum.p + M; a.partials = red_partials.p; a.ticket = ticket.p;
+        a.sc = sc.p;
+        k_forces_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+        kernels_launched += 3;
+    }
+    // avg = Y . v for an arbitrary N-vector v already in `w` (post-processing: yopt = y . wopt)
+    void average_of_w(double* avg_out_dev) {
+        launch_pass<kRowPass, false>(w.p, nullptr);
+        k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+        ++kernels_launched;
+        if (nranks > 1) comm->allreduce_sum(msum.p, M, stream);
+        d2d(avg_out_dev, msum.p, M);
+    }
+
+    void fetch_scalars() {
+        d2h(h_sc, sc.p, SC_COUNT);
+        sync();
+    }
+};
+
+}  // namespace bioen

@@ -1,0 +1,418 @@
+// lbfgs.cuh -- device-resident L-BFGS with liblbfgs 1.10 semantics.
+//
+// What the reference does (third-party/liblbfgs-1.10/lib/lbfgs.c, driven by c_bioen_kernels_logw.c:581-669 and
+// c_bioen_kernels_forces.c:574-662): all vectors live in host memory, every dot product is a sequential host
+// loop, every trial point calls back into the OpenMP kernels.
+//
+// Here: x, g, xp, gp, d and the m = 6 (s, y) pairs live in HBM for the whole minimisation.  The trial point
+// x = xp + stp*d is formed inside the first evaluation kernel, g.d / ||g||^2 / ||x||^2 come out of the last
+// one, the (s, y) update and the two-loop recursion are 2*bound+2 fused kernels chained through the device
+// scalar file.  The *scalar* state machine of liblbfgs (line searches, stop tests, return codes) is kept on
+// the host, bit for bit in the same order of tests, and costs one 512-byte read-back per trial point.
+// With N sharded across GPUs the vector kernels see the local slice and the raw dot products are
+// all-reduced in-stream (forces: the M-dimensional state is replicated, nothing to reduce).
+#pragma once
+#include <cmath>
+#include <cstdio>
+
+#include "context.cuh"
+
+namespace bioen {
+
+enum {
+    LBFGS_SUCCESS = 0,
+    LBFGS_STOP = 1,
+    LBFGS_ALREADY_MINIMIZED = 2,
+    LBFGSERR_UNKNOWNERROR = -1024,
+    LBFGSERR_LOGICERROR,
+    LBFGSERR_OUTOFMEMORY,
+    LBFGSERR_CANCELED,
+    LBFGSERR_INVALID_N,
+    LBFGSERR_INVALID_N_SSE,
+    LBFGSERR_INVALID_X_SSE,
+    LBFGSERR_INVALID_EPSILON,
+    LBFGSERR_INVALID_TESTPERIOD,
+    LBFGSERR_INVALID_DELTA,
+    LBFGSERR_INVALID_LINESEARCH,
+    LBFGSERR_INVALID_MINSTEP,
+    LBFGSERR_INVALID_MAXSTEP,
+    LBFGSERR_INVALID_FTOL,
+    LBFGSERR_INVALID_WOLFE,
+    LBFGSERR_INVALID_GTOL,
+    LBFGSERR_INVALID_XTOL,
+    LBFGSERR_INVALID_MAXLINESEARCH,
+    LBFGSERR_INVALID_ORTHANTWISE,
+    LBFGSERR_INVALID_ORTHANTWISE_START,
+    LBFGSERR_INVALID_ORTHANTWISE_END,
+    LBFGSERR_OUTOFINTERVAL,
+    LBFGSERR_INCORRECT_TMINMAX,
+    LBFGSERR_ROUNDING_ERROR,
+    LBFGSERR_MINIMUMSTEP,
+    LBFGSERR_MAXIMUMSTEP,
+    LBFGSERR_MAXIMUMLINESEARCH,
+    LBFGSERR_MAXIMUMITERATION,
+    LBFGSERR_WIDTHTOOSMALL,
+    LBFGSERR_INVALIDPARAMETERS,
+    LBFGSERR_INCREASEGRADIENT
+};
+
+struct LbfgsParams {  // lbfgs.h lbfgs_parameter_t with _defparam (lbfgs.c:113-118)
+    int m = 6;
+    double epsilon = 1e-5;
+    int past = 0;
+    double delta = 1e-5;
+    int max_iterations = 0;
+    int linesearch = 0;
+    int max_linesearch = 40;
+    double min_step = 1e-20, max_step = 1e20, ftol = 1e-4, wolfe = 0.9, gtol = 0.9, xtol = 1e-16;
+};
+
+struct LbfgsStats {
+    int iterations = 0, evaluations = 0;
+    double seconds = 0.0;
+};
+
+inline int lbfgs_check_params(int n, const LbfgsParams& p) {  // lbfgs.c:286-364
+    if (n <= 0) return LBFGSERR_INVALID_N;
+    if (p.epsilon < 0.) return LBFGSERR_INVALID_EPSILON;
+    if (p.past < 0) return LBFGSERR_INVALID_TESTPERIOD;
+    if (p.delta < 0.) return LBFGSERR_INVALID_DELTA;
+    if (p.min_step < 0.) return LBFGSERR_INVALID_MINSTEP;
+    if (p.max_step < p.min_step) return LBFGSERR_INVALID_MAXSTEP;
+    if (p.ftol < 0.) return LBFGSERR_INVALID_FTOL;
+    if (p.linesearch == 2 || p.linesearch == 3) {
+        if (p.wolfe <= p.ftol || 1. <= p.wolfe) return LBFGSERR_INVALID_WOLFE;
+    }
+    if (p.gtol < 0.) return LBFGSERR_INVALID_GTOL;
+    if (p.xtol < 0.) return LBFGSERR_INVALID_XTOL;
+    if (p.max_linesearch <= 0) return LBFGSERR_INVALID_MAXLINESEARCH;
+    if (p.linesearch < 0 || p.linesearch > 3) return LBFGSERR_INVALID_LINESEARCH;
+    if (p.m <= 0 || p.m > 16) return LBFGSERR_INVALIDPARAMETERS;
+    return 0;
+}
+
+// ---- More-Thuente helpers: cubic / quadratic interpolation (lbfgs.c:1021-1094) -------------------------
+namespace mt {
+inline double max3(double a, double b, double c) { return std::fmax(std::fmax(a, b), c); }
+inline double cubic(double u, double fu, double du, double v, double fv, double dv) {
+    const double d = v - u, theta = (fu - fv) * 3 / d + du + dv;
+    const double s = max3(std::fabs(theta), std::fabs(du), std::fabs(dv)), a = theta / s;
+    double gamma = s * std::sqrt(a * a - (du / s) * (dv / s));
+    if (v < u) gamma = -gamma;
+    const double p = gamma - du + theta, q = gamma - du + gamma + dv;
+    return u + (p / q) * d;
+}
+inline double cubic2(double u, double fu, double du, double v, double fv, double dv, double xmin, double xmax) {
+    const double d = v - u, theta = (fu - fv) * 3 / d + du + dv;
+    const double s = max3(std::fabs(theta), std::fabs(du), std::fabs(dv)), a = theta / s;
+    double gamma = s * std::sqrt(std::fmax(0.0, a * a - (du / s) * (dv / s)));
+    if (u < v) gamma = -gamma;
+    const double p = gamma - dv + theta, q = gamma - dv + gamma + du, r = p / q;
+    if (r < 0. && gamma != 0.) return v - r * d;
+    return a < 0 ? xmax : xmin;
+}
+inline double quad(double u, double fu, double du, double v, double fv) {
+    const double a = v - u;
+    return u + du / ((fu - fv) / a + du) / 2 * a;
+}
+inline double quad2(double u, double du, double v, double dv) {
+    const double a = u - v;
+    return v + dv / (dv - du) * a;
+}
+// update_trial_interval (lbfgs.c:1125-1292)
+inline int update(double& x, double& fx, double& dx, double& y, double& fy, double& dy, double& t, double ft,
+                  double dt, double tmin, double tmax, int& brackt) {
+    int bound;
+    const bool dsign = (dt * (dx / std::fabs(dx)) < 0.);
+    double mc, mq, newt;
+    if (brackt) {
+        if (t <= std::fmin(x, y) || std::fmax(x, y) <= t) return LBFGSERR_OUTOFINTERVAL;
+        if (0. <= dx * (t - x)) return LBFGSERR_INCREASEGRADIENT;
+        if (tmax < tmin) return LBFGSERR_INCORRECT_TMINMAX;
+    }
+    if (fx < ft) {
+        brackt = 1; bound = 1;
+        mc = cubic(x, fx, dx, t, ft, dt);
+        mq = quad(x, fx, dx, t, ft);
+        newt = (std::fabs(mc - x) < std::fabs(mq - x)) ? mc : mc + 0.5 * (mq - mc);
+    } else if (dsign) {
+        brackt = 1; bound = 0;
+        mc = cubic(x, fx, dx, t, ft, dt);
+        mq = quad2(x, dx, t, dt);
+        newt = (std::fabs(mc - t) > std::fabs(mq - t)) ? mc : mq;
+    } else if (std::fabs(dt) < std::fabs(dx)) {
+        bound = 1;
+        mc = cubic2(x, fx, dx, t, ft, dt, tmin, tmax);
+        mq = quad2(x, dx, t, dt);
+        if (brackt) newt = (std::fabs(t - mc) < std::fabs(t - mq)) ? mc : mq;
+        else newt = (std::fabs(t - mc) > std::fabs(t - mq)) ? mc : mq;
+    } else {
+        bound = 0;
+        if (brackt) newt = cubic(t, ft, dt, y, fy, dy);
+        else if (x < t) newt = tmax;
+        else newt = tmin;
+    }
+    if (fx < ft) {
+        y = t; fy = ft; dy = dt;
+    } else {
+        if (dsign) { y = x; fy = fx; dy = dx; }
+        x = t; fx = ft; dx = dt;
+    }
+    if (tmax < newt) newt = tmax;
+    if (newt < tmin) newt = tmin;
+    if (brackt && bound) {
+        mq = x + 0.66 * (y - x);
+        if (x < y) { if (mq < newt) newt = mq; }
+        else { if (newt < mq) newt = mq; }
+    }
+    t = newt;
+    return 0;
+}
+}  // namespace mt
+
+class Lbfgs {
+   public:
+    Context& C;
+    const bool forces;   // false: log-weights (n = N, sharded when C.nranks > 1); true: forces (n = M, replicated)
+    const int n;
+    LbfgsParams prm;
+    int verbose = 0;
+    LbfgsStats stats;
+
+    DevBuf<double> store;  // g, xp, gp, d, s[m], y[m]
+    double *x = nullptr, *g = nullptr, *xp = nullptr, *gp = nullptr, *d = nullptr;
+    std::vector<double*> S, Yv;
+    int vec_blocks;
+    bool reduce;
+
+    Lbfgs(Context& ctx, bool is_forces, const LbfgsParams& p)
+        : C(ctx), forces(is_forces), n(is_forces ? ctx.M : ctx.N), prm(p) {
+        vec_blocks = is_forces ? ctx.vec_blocks_m : ctx.vec_blocks_n;
+        reduce = (!is_forces) && ctx.nranks > 1;
+    }
+
+    // x_dev (device, n doubles): start point on entry, end point on exit.  Returns the liblbfgs code.
+    int run(double* x_dev, double* fx_out) {
+        x = x_dev;
+        int ret = lbfgs_check_params(n, prm);
+        if (ret) { *fx_out = 0.0; return ret; }
+        const int m = prm.m;
+        const size_t np = ((size_t)n + 15) & ~(size_t)15;
+        store.alloc(np * (4 + 2 * (size_t)m));
+        g = store.p; xp = g + np; gp = xp + np; d = gp + np;
+        S.resize(m); Yv.resize(m);
+        for (int i = 0; i < m; ++i) { S[i] = d + np * (1 + i); Yv[i] = d + np * (1 + m + i); }
+        std::vector<double> pf(prm.past > 0 ? prm.past : 0);
+        const double* h = C.h_sc;
+
+        // initial evaluation (lbfgs.c:412)
+        eval(nullptr, nullptr, 0.0, nullptr);
+        C.fetch_scalars();
+        double fx = h[SC_F];
+        if (!pf.empty()) pf[0] = fx;
+        double xnorm = std::sqrt(h[SC_XNORM2]), gnorm = std::sqrt(h[SC_GNORM2]);
+        if (xnorm < 1.0) xnorm = 1.0;
+        if (gnorm / xnorm <= prm.epsilon) { *fx_out = fx; return LBFGS_ALREADY_MINIMIZED; }
+        // d = -g ; step = 1/||d|| ; dginit = g.d = -||g||^2
+        k_axpby<<<vec_blocks, kVecThreads, 0, C.stream>>>(n, -1.0, g, 0.0, nullptr, d);
+        double step = 1.0 / gnorm;
+        double dginit = -h[SC_GNORM2];
+        bool dginit_known = true;
+        C.d2d(xp, x, n);
+        C.d2d(gp, g, n);
+
+        int k = 1, end = 0;
+        for (;;) {
+            int ls = (prm.linesearch == 0) ? linesearch_morethuente(fx, step, dginit, dginit_known)
+                                           : linesearch_backtracking(fx, step, dginit, dginit_known);
+            if (ls < 0) {
+                // revert to the previous point (lbfgs.c:475-481)
+                C.d2d(x, xp, n);
+                C.d2d(g, gp, n);
+                C.sync();
+                ret = ls;
+                break;
+            }
+            xnorm = std::sqrt(h[SC_XNORM2]);
+            gnorm = std::sqrt(h[SC_GNORM2]);
+            ++stats.iterations;  // progress callback (c_bioen_kernels_logw.c:565-576)
+            if (verbose && stats.iterations % 1000 == 0) printf("\t\tOpt Iteration %d\n", stats.iterations);
+            if (xnorm < 1.0) xnorm = 1.0;
+            if (gnorm / xnorm <= prm.epsilon) { ret = LBFGS_SUCCESS; break; }
+            if (!pf.empty()) {
+                if (prm.past <= k) {
+                    const double rate = (pf[k % prm.past] - fx) / fx;
+                    if (rate < prm.delta) { ret = LBFGS_STOP; break; }
+                }
+                pf[k % prm.past] = fx;
+            }
+            if (prm.max_iterations != 0 && prm.max_iterations < k + 1) { ret = LBFGSERR_MAXIMUMITERATION; break; }
+
+            // s, y, ys, yy; xp <- x, gp <- g (lbfgs.c:543-555, 462-463)
+            {
+                PairArgs a{n, x, g, xp, gp, S[end], Yv[end], end, C.red_partials.p, C.ticket.p, C.sc.p};
+                k_lbfgs_pair<<<vec_blocks, kVecThreads, 0, C.stream>>>(a);
+                if (reduce) C.comm->allreduce_sum(C.sc.p + SC_YS, 2, C.stream);
+                C.d2d(C.sc.p + SC_YS0 + end, C.sc.p + SC_YS, 1);
+            }
+            const int bound = (m <= k) ? m : k;
+            ++k;
+            end = (end + 1) % m;
+            two_loop(bound, end, m);
+            step = 1.0;
+            dginit_known = false;  // sc[SC_DGINIT] is read together with the first trial of the next search
+        }
+        *fx_out = fx;
+        return ret;
+    }
+
+   private:
+    // enqueue one f+g evaluation at x (= xp + stp*dir when xp_ given); dg direction optional
+    void eval(const double* xp_, const double* dir, double stp, const double* ddir) {
+        if (forces) C.forces_eval(x, xp_, dir, stp, g, ddir);
+        else C.logw_eval(x, xp_, dir, stp, g, ddir);
+        ++stats.evaluations;
+    }
+
+    // the recursion of lbfgs.c:572-598 as 2*bound+1 fused kernels; the last one also leaves g.d in SC_DGINIT
+    void two_loop(int bound, int end, int m) {
+        auto launch = [&](TwoLoopArgs& a) {
+            a.n = n; a.d = d; a.g = g; a.partials = C.red_partials.p; a.ticket = C.ticket.p; a.sc = C.sc.p;
+            k_lbfgs_twoloop<<<vec_blocks, kVecThreads, 0, C.stream>>>(a);
+            if (reduce && a.v) C.comm->allreduce_sum(C.sc.p + a.out, 1, C.stream);
+        };
+        std::vector<int> js(bound);
+        int j = end;
+        for (int i = 0; i < bound; ++i) { j = (j + m - 1) % m; js[i] = j; }   // newest ... oldest
+        {   // d = -g ; alpha_raw[j0] = s_j0 . d
+            TwoLoopArgs a{};
+            a.init = 1; a.u = nullptr; a.c_num = a.c_den = 0; a.c2_num = -1; a.s_num = -1;
+            a.v = S[js[0]]; a.out = SC_ALPHA0 + js[0];
+            launch(a);
+        }
+        for (int i = 0; i < bound; ++i) {
+            // d -= alpha_j y_j ; then either the next alpha, or (last) the H0 scaling and the first beta
+            TwoLoopArgs a{};
+            a.u = Yv[js[i]]; a.c_num = SC_ALPHA0 + js[i]; a.c_den = SC_YS0 + js[i]; a.csign = -1.0; a.c2_num = -1;
+            if (i + 1 < bound) {
+                a.s_num = -1; a.v = S[js[i + 1]]; a.out = SC_ALPHA0 + js[i + 1];
+            } else {
+                a.s_num = SC_YS; a.s_den = SC_YY; a.v = Yv[js[i]]; a.out = SC_BETA;
+            }
+            launch(a);
+        }
+        int beta_slot = SC_BETA;
+        for (int i = bound - 1; i >= 0; --i) {
+            // d += (alpha_j - beta_j) s_j ; then the next beta, or (last) g.d
+            TwoLoopArgs a{};
+            a.u = S[js[i]];
+            a.c_num = SC_ALPHA0 + js[i]; a.c_den = SC_YS0 + js[i]; a.csign = 1.0;
+            a.c2_num = beta_slot; a.c2_den = SC_YS0 + js[i]; a.c2sign = -1.0;
+            a.s_num = -1;
+            beta_slot = (beta_slot == SC_BETA) ? SC_BETA2 : SC_BETA;
+            if (i > 0) { a.v = Yv[js[i - 1]]; a.out = beta_slot; }
+            else { a.v = g; a.out = SC_DGINIT; }
+            launch(a);
+        }
+    }
+
+    // lbfgs.c:645-734.  On success h_sc holds the scalars of the accepted point.
+    int linesearch_backtracking(double& f, double& stp, double& dginit, bool& dginit_known) {
+        const double* h = C.h_sc;
+        int count = 0;
+        const double dec = 0.5, inc = 2.1;
+        if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
+        if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+        const double finit = f;
+        for (;;) {
+            eval(xp, d, stp, d);
+            C.fetch_scalars();
+            if (!dginit_known) {
+                dginit = h[SC_DGINIT];
+                dginit_known = true;
+                if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+            }
+            const double dgtest = prm.ftol * dginit;
+            f = h[SC_F];
+            ++count;
+            double width;
+            if (f > finit + stp * dgtest) {
+                width = dec;
+            } else {
+                if (prm.linesearch == 1) return count;
+                const double dg = h[SC_DG];
+                if (dg < prm.wolfe * dginit) {
+                    width = inc;
+                } else {
+                    if (prm.linesearch == 2) return count;
+                    if (dg > -prm.wolfe * dginit) width = dec;
+                    else return count;
+                }
+            }
+            if (stp < prm.min_step) return LBFGSERR_MINIMUMSTEP;
+            if (stp > prm.max_step) return LBFGSERR_MAXIMUMSTEP;
+            if (prm.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
+            stp *= width;
+        }
+    }
+
+    // lbfgs.c:812-1001
+    int linesearch_morethuente(double& f, double& stp, double& dginit, bool& dginit_known) {
+        const double* h = C.h_sc;
+        int count = 0, brackt = 0, stage1 = 1, uinfo = 0;
+        if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
+        if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+        const double finit = f;
+        double width = prm.max_step - prm.min_step, prev_width = 2.0 * width;
+        double stx = 0., sty = 0., fx = finit, fy = finit, dgx = dginit, dgy = dginit;
+        double stmin, stmax;
+        for (;;) {
+            if (brackt) { stmin = std::fmin(stx, sty); stmax = std::fmax(stx, sty); }
+            else { stmin = stx; stmax = stp + 4.0 * (stp - stx); }
+            if (stp < prm.min_step) stp = prm.min_step;
+            if (prm.max_step < stp) stp = prm.max_step;
+            if ((brackt && ((stp <= stmin || stmax <= stp) || prm.max_linesearch <= count + 1 || uinfo != 0)) ||
+                (brackt && (stmax - stmin <= prm.xtol * stmax)))
+                stp = stx;
+            eval(xp, d, stp, d);
+            C.fetch_scalars();
+            if (!dginit_known) {
+                // first trial of this search: only stx = sty = 0 so far, fill in the slope at 0
+                dginit = h[SC_DGINIT];
+                dginit_known = true;
+                if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+                dgx = dgy = dginit;
+            }
+            const double dgtest = prm.ftol * dginit;
+            f = h[SC_F];
+            double dg = h[SC_DG];
+            const double ftest1 = finit + stp * dgtest;
+            ++count;
+            if (brackt && ((stp <= stmin || stmax <= stp) || uinfo != 0)) return LBFGSERR_ROUNDING_ERROR;
+            if (stp == prm.max_step && f <= ftest1 && dg <= dgtest) return LBFGSERR_MAXIMUMSTEP;
+            if (stp == prm.min_step && (ftest1 < f || dgtest <= dg)) return LBFGSERR_MINIMUMSTEP;
+            if (brackt && (stmax - stmin) <= prm.xtol * stmax) return LBFGSERR_WIDTHTOOSMALL;
+            if (prm.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
+            if (f <= ftest1 && std::fabs(dg) <= prm.gtol * (-dginit)) return count;
+            if (stage1 && f <= ftest1 && std::fmin(prm.ftol, prm.gtol) * dginit <= dg) stage1 = 0;
+            if (stage1 && ftest1 < f && f <= fx) {
+                double fm = f - stp * dgtest, fxm = fx - stx * dgtest, fym = fy - sty * dgtest;
+                double dgm = dg - dgtest, dgxm = dgx - dgtest, dgym = dgy - dgtest;
+                uinfo = mt::update(stx, fxm, dgxm, sty, fym, dgym, stp, fm, dgm, stmin, stmax, brackt);
+                fx = fxm + stx * dgtest;
+                fy = fym + sty * dgtest;
+                dgx = dgxm + dgtest;
+                dgy = dgym + dgtest;
+            } else {
+                uinfo = mt::update(stx, fx, dgx, sty, fy, dgy, stp, f, dg, stmin, stmax, brackt);
+            }
+            if (brackt) {
+                if (0.66 * prev_width <= std::fabs(sty - stx)) stp = stx + 0.5 * (sty - stx);
+                prev_width = width;
+                width = std::fabs(sty - stx);
+            }
+        }
+    }
+};
+
+}  // namespace bioen

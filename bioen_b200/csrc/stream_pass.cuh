@@ -1,0 +1,222 @@
+// stream_pass.cuh -- the two kernels that touch the M x N matrix yTilde.
+//
+// Every BioEn evaluation is two skinny products with the same fp64 matrix:
+//
+//   ROW pass   out_i = sum_j (y_ij [- b_i]) * v_j      "yTilde . w"       reference: c_bioen_common.c:78-83,
+//                                                                          c_bioen_kernels_forces.c:330-338
+//   COL pass   out_j = sum_i a_i * (y_ij [- b_i])      "yTilde^T . r"     reference: c_bioen_kernels_logw.c:197-204,
+//                                                                          c_bioen_kernels_forces.c:140-147,311-318
+//
+// Both are HBM-bound (0.25 flop/byte) so the design goal is only: keep >100 KB of loads in flight per SM,
+// read every byte of yTilde exactly once per pass, never re-read.  One persistent CTA per SM runs a
+// producer/consumer ring:
+//
+//   * warp NW (one elected lane) is the producer: for each R x C tile it arms an mbarrier with the byte count
+//     and issues one 2-D tiled TMA load (cp.async.bulk.tensor) for the matrix tile plus one or two 1-D bulk
+//     copies for the slices of the small vectors the tile needs.  Tiles are 32 KB, the ring holds STAGES of
+//     them (6 -> 192 KB in flight per SM).  Out-of-range rows/columns are zero-filled by the TMA unit, the
+//     vectors are zero-padded, so there is no tail code anywhere.
+//   * warps 0..NW-1 are consumers.  Each warp owns a fixed slice of every tile (ROW: 4 rows x all columns,
+//     COL: all rows x 16 columns) and keeps its fp64 accumulators in registers for a whole "run" of tiles
+//     (ROW: a row-tile swept along the columns; COL: a column block swept down the rows), reads shared
+//     memory with conflict-free 128-bit loads, and releases the stage with one mbarrier arrive per warp.
+//     Warps never synchronise with each other.
+//
+// Work split: tiles are numbered run-major and cut into `nCTA` equal contiguous chunks, so the load is
+// balanced to +-1 tile whatever M and N are.  A run that straddles a chunk border is finished by two (or
+// more) CTAs; each writes its partial sums to its own slot (`slot = cta - first_cta_of_run`), and the small
+// finalize kernels (vector_kernels.cu) add the slots in a fixed order.  No atomics on data: results are
+// bit-reproducible run to run.
+#pragma once
+#include "common.cuh"
+
+namespace bioen {
+
+enum PassMode { kRowPass = 0, kColPass = 1 };
+
+constexpr int kTileR = 32;    // rows per tile
+constexpr int kTileC = 128;   // columns per tile  (128 doubles = 1 KB per tile row)
+constexpr int kStages = 6;    // ring depth
+constexpr int kConsumerWarps = 8;
+constexpr int kAuxBytes = 2048;                                   // vector slices travelling with a tile
+constexpr int kTileBytes = kTileR * kTileC * (int)sizeof(double);  // 32 KB
+constexpr int kStageBytes = kTileBytes + kAuxBytes;
+constexpr int kPassSmemBytes = kStages * kStageBytes + 2 * kStages * (int)sizeof(uint64_t) + 128;
+constexpr int kPassThreads = (kConsumerWarps + 1) * 32;
+
+struct PassArgs {
+    int nRT;            // number of row tiles     ceil(M / kTileR)
+    int nCB;            // number of column blocks ceil(N / kTileC)
+    long long T;        // nRT * nCB
+    long long chunk;    // tiles per CTA
+    int evict_first;    // 1: stream yTilde through L2 with evict_first (matrix >> L2)
+    const double* vN;   // ROW: v_j, length >= nCB*kTileC, zero padded
+    const double* vMb;  // ROW with SUB: b_i, length >= nRT*kTileR, zero padded
+    const double* ab;   // COL: interleaved {a_i, b_i}, >= nRT*kTileR pairs, zero padded
+    double* partial;    // ROW: [slot][ld] per-row partial sums; COL: [slot][ld] per-column partial sums
+    long long ld;       // leading dimension of `partial`
+};
+
+// slots a run of length L starting at tile run*L occupies: first CTA and count
+__host__ __device__ inline long long pass_first_cta(long long run, long long L, long long chunk) {
+    return (run * L) / chunk;
+}
+__host__ __device__ inline int pass_num_slots(long long run, long long L, long long chunk) {
+    return (int)(((run + 1) * L - 1) / chunk - (run * L) / chunk) + 1;
+}
+
+template <int MODE, bool SUB>
+__global__ void __launch_bounds__(kPassThreads, 1)
+    stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // 128-byte align the ring by hand (dynamic smem base is only guaranteed 16-byte aligned)
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                                           ~static_cast<uintptr_t>(127));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t0 = (long long)blockIdx.x * a.chunk;
+    const long long t1 = (t0 + a.chunk < a.T) ? t0 + a.chunk : a.T;
+    const long long L = (MODE == kRowPass) ? a.nCB : a.nRT;  // run length in tiles
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0 && t0 < t1) {
+            prefetch_tensormap(&tmap);
+            const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+            long long run = t0 / L;
+            int k = (int)(t0 - run * L);
+            int stage = 0;
+            uint32_t phase = 1;  // a fresh barrier passes a wait on parity 1
+            for (long long t = t0; t < t1; ++t) {
+                const int rt = (MODE == kRowPass) ? (int)run : k;
+                const int cb = (MODE == kRowPass) ? k : (int)run;
+                unsigned char* st = smem + (size_t)stage * kStageBytes;
+                mbar_wait(&empty[stage], phase);
+                uint32_t bytes = kTileBytes;
+                if (MODE == kRowPass) bytes += kTileC * 8 + (SUB ? kTileR * 8 : 0);
+                else bytes += kTileR * 16;
+                mbar_expect_tx(&full[stage], bytes);
+                tma_load_2d(st, &tmap, cb * kTileC, rt * kTileR, &full[stage], policy);
+                if (MODE == kRowPass) {
+                    bulk_load_1d(st + kTileBytes, a.vN + (size_t)cb * kTileC, kTileC * 8, &full[stage]);
+                    if (SUB)
+                        bulk_load_1d(st + kTileBytes + kTileC * 8, a.vMb + (size_t)rt * kTileR, kTileR * 8,
+                                     &full[stage]);
+                } else {
+                    bulk_load_1d(st + kTileBytes, a.ab + (size_t)rt * kTileR * 2, kTileR * 16, &full[stage]);
+                }
+                if (++k == (int)L) { k = 0; ++run; }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    if (t0 >= t1) return;
+    long long run = t0 / L;
+    int k = (int)(t0 - run * L);
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (MODE == kRowPass) {
+        constexpr int RPW = kTileR / kConsumerWarps;  // rows per warp = 4
+        double acc[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) acc[r] = 0.0;
+        for (long long t = t0; t < t1; ++t) {
+            const unsigned char* st = smem + (size_t)stage * kStageBytes;
+            mbar_wait(&full[stage], phase);
+            const double2* vv = reinterpret_cast<const double2*>(st + kTileBytes);
+            const double2 v0 = vv[lane], v1 = vv[32 + lane];
+            const double* bv = reinterpret_cast<const double*>(st + kTileBytes + kTileC * 8);
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const int row = warp * RPW + r;
+                const double2* yr = reinterpret_cast<const double2*>(st) + (size_t)row * (kTileC / 2);
+                double2 y0 = yr[lane], y1 = yr[32 + lane];
+                if (SUB) {
+                    const double b = bv[row];
+                    y0.x -= b; y0.y -= b; y1.x -= b; y1.y -= b;
+                }
+                double s = acc[r];
+                s = fma(y0.x, v0.x, s);
+                s = fma(y0.y, v0.y, s);
+                s = fma(y1.x, v1.x, s);
+                s = fma(y1.y, v1.y, s);
+                acc[r] = s;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            const bool run_ends = (k + 1 == (int)L);
+            if (run_ends || t + 1 == t1) {
+                const long long slot = (long long)blockIdx.x - pass_first_cta(run, L, a.chunk);
+                double* out = a.partial + slot * a.ld + run * kTileR + warp * RPW;
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const double s = warp_sum(acc[r]);
+                    if (lane == 0) out[r] = s;
+                    acc[r] = 0.0;
+                }
+            }
+            if (run_ends) { k = 0; ++run; } else { ++k; }
+        }
+    } else {
+        // warp -> 16 columns; lane -> (row group of 8 rows, column pair)
+        constexpr int CPW = kTileC / kConsumerWarps;  // 16 columns per warp
+        static_assert(CPW == 16 && kTileR == 32, "column-pass lane mapping assumes a 32 x 128 tile");
+        const int cp = lane & 7, rg = lane >> 3;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (long long t = t0; t < t1; ++t) {
+            const unsigned char* st = smem + (size_t)stage * kStageBytes;
+            mbar_wait(&full[stage], phase);
+            const double2* abv = reinterpret_cast<const double2*>(st + kTileBytes);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int row = rg * 8 + q;
+                const double2 y =
+                    (reinterpret_cast<const double2*>(st) + (size_t)row * (kTileC / 2) + warp * (CPW / 2))[cp];
+                const double2 ab = abv[row];
+                if (SUB) {
+                    acc0 = fma(ab.x, y.x - ab.y, acc0);
+                    acc1 = fma(ab.x, y.y - ab.y, acc1);
+                } else {
+                    acc0 = fma(ab.x, y.x, acc0);
+                    acc1 = fma(ab.x, y.y, acc1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            const bool run_ends = (k + 1 == (int)L);
+            if (run_ends || t + 1 == t1) {
+                // add the four row groups in a fixed order
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, 8);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
+                if (rg == 0) {
+                    const long long slot = (long long)blockIdx.x - pass_first_cta(run, L, a.chunk);
+                    double2* out = reinterpret_cast<double2*>(a.partial + slot * a.ld + run * kTileC + warp * CPW);
+                    out[cp] = make_double2(acc0, acc1);
+                }
+                acc0 = acc1 = 0.0;
+            }
+            if (run_ends) { k = 0; ++run; } else { ++k; }
+        }
+    }
+}
+
+}  // namespace bioen

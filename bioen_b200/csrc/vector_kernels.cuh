@@ -1,0 +1,582 @@
+// vector_kernels.cuh -- the O(N) and O(M) kernels around the two matrix passes, and the fused vector
+// kernels of the device-resident L-BFGS.  All reductions are fixed-order (block tree + last-block sum).
+//
+// Device scalar file: every evaluation/minimiser scalar lives in one small device array `sc[]`
+// (indices below), so kernels chain through device memory and the host reads a handful of doubles once per
+// line-search trial.
+#pragma once
+#include <float.h>
+
+#include "common.cuh"
+#include "stream_pass.cuh"
+
+namespace bioen {
+
+enum ScalarSlot {
+    SC_LSE_MAX = 0,   // local max of x            (k_update_lse)
+    SC_LSE_SUM = 1,   // local sum exp(x - max)
+    SC_KL = 2,        // forces: sum_j w_j (log w_j - log w0_j)
+    SC_GMAX = 3,      // global max
+    SC_S = 4,         // global sum exp(x - gmax)
+    SC_LOGS0 = 5,     // log sum exp(G)            (constant of the problem)
+    SC_GBAR = 6,      // <g> = sum g_j w_j
+    SC_CAPGBAR = 7,   // <G> = sum G_j w_j
+    SC_F = 8,         // objective
+    SC_CHI2 = 9,      // 1/2 sum r^2
+    SC_PRIOR = 10,    // theta * (...)  (logw)  or  theta * KL (forces)
+    SC_DG = 11,       // grad . d      } local parts until all-reduced (3 contiguous doubles)
+    SC_GNORM2 = 12,   // ||grad||^2    }
+    SC_XNORM2 = 13,   // ||x||^2       }
+    SC_GINF = 15,     // max |grad_j|  (GSL stop test)
+    // L-BFGS scalars
+    SC_YS = 16,       // y.s of the newest pair
+    SC_YY = 17,       // y.y of the newest pair
+    SC_BETA = 18,     // raw y_j . d of the running second loop
+    SC_DGINIT = 19,   // g . d for the new direction
+    SC_DNORM2 = 20,   // ||d||^2 (initial step)
+    SC_BETA2 = 21,    // second-loop dots alternate between SC_BETA and SC_BETA2
+    SC_YS0 = 24,      // ys[m] ring, up to 16 entries
+    SC_ALPHA0 = 40,   // raw s_j . d ring, up to 16 entries
+    SC_TMP0 = 56,     // generic outputs of vec_dot etc.
+    SC_COUNT = 64
+};
+
+constexpr int kVecThreads = 256;
+
+// merge two (max, sum-of-exp) pairs
+__device__ __forceinline__ void lse_merge(double& m, double& s, double m2, double s2) {
+    const double mm = fmax(m, m2);
+    s = s * exp(m - mm) + s2 * exp(m2 - mm);
+    m = mm;
+}
+
+// fixed-order block reduction of (max, sum-of-exp) pairs and one plain sum; result in thread 0
+__device__ __forceinline__ void block_lse(double& m, double& s, double& xn, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge(m, s, m2, s2);
+    }
+    xn = warp_sum(xn);
+    __syncthreads();
+    if (lane == 0) { red[wid] = m; red[32 + wid] = s; red[64 + wid] = xn; }
+    __syncthreads();
+    if (wid == 0) {
+        m = lane < nw ? red[lane] : -DBL_MAX;
+        s = lane < nw ? red[32 + lane] : 0.0;
+        xn = lane < nw ? red[64 + lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+            lse_merge(m, s, m2, s2);
+        }
+        xn = warp_sum(xn);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: optional x = xp + stp*d, then local (max, sum exp(x-max)) and ||x||^2.
+//     logw: the N-length softmax / log-sum-exp of the north star; forces: used on x_j = (yTilde^T f)_j with
+//     the prior weights folded in (w0 != nullptr -> terms w0_j exp(x_j - max)).
+//     reference: c_bioen_kernels_logw.c:55-94 (un-stabilised there), c_bioen_kernels_forces.c:151-171
+// ------------------------------------------------------------------------------------------------
+struct LseArgs {
+    int n;
+    double* x;           // in/out
+    const double* xp;    // nullptr: x is used as is
+    const double* d;
+    double stp;
+    const double* w0;    // nullptr for logw
+    // forces: x_j is first assembled from the column-pass partial sums
+    const double* col_partial;  // nullptr: x already holds the values
+    long long col_ld;
+    long long col_L, col_chunk;
+    double* partials;    // gridDim.x * 3
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_update_lse(const LseArgs a) {
+    __shared__ double red[3 * 32];
+    __shared__ bool is_last;
+    double m = -DBL_MAX, s = 0.0, xn = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        double x;
+        if (a.col_partial) {
+            const long long cb = j / kTileC;
+            const int ns = pass_num_slots(cb, a.col_L, a.col_chunk);
+            x = 0.0;
+            for (int q = 0; q < ns; ++q) x += a.col_partial[(size_t)q * a.col_ld + j];
+            a.x[j] = x;
+        } else if (a.xp) {
+            x = fma(a.stp, a.d[j], a.xp[j]);
+            a.x[j] = x;
+        } else {
+            x = a.x[j];
+        }
+        xn = fma(x, x, xn);
+        const double pw = a.w0 ? a.w0[j] : 1.0;
+        if (x > m) {
+            s = s * exp(m - x) + pw;
+            m = x;
+        } else {
+            s += pw * exp(x - m);
+        }
+    }
+    block_lse(m, s, xn, red);
+    if (threadIdx.x == 0) {
+        a.partials[blockIdx.x * 3 + 0] = m;
+        a.partials[blockIdx.x * 3 + 1] = s;
+        a.partials[blockIdx.x * 3 + 2] = xn;
+        __threadfence();
+        is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        m = -DBL_MAX; s = 0.0; xn = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            lse_merge(m, s, __ldcg(&a.partials[b * 3]), __ldcg(&a.partials[b * 3 + 1]));
+            xn += __ldcg(&a.partials[b * 3 + 2]);
+        }
+        block_lse(m, s, xn, red);
+        if (threadIdx.x == 0) {
+            a.sc[SC_LSE_MAX] = m;
+            a.sc[SC_LSE_SUM] = s;
+            a.sc[SC_XNORM2] = xn;
+            *a.ticket = 0;
+        }
+    }
+}
+
+// merge the per-rank (max, sum) pairs; every thread of every block of the next kernel calls this
+__device__ __forceinline__ void global_lse(const double* pairs, int nranks, double& M, double& S) {
+    M = pairs[0];
+    S = pairs[1];
+    for (int r = 1; r < nranks; ++r) lse_merge(M, S, pairs[2 * r], pairs[2 * r + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (logw): w_j = exp(g_j - gmax) / S and the three weighted sums of the prior / gradient
+//     reference: c_bioen_kernels_logw.c:96-127 (prior), 208-212 (<g>, <G>)
+//     The sums are appended to the M-vector that is all-reduced after the row pass: msum[M..M+2].
+// ------------------------------------------------------------------------------------------------
+struct LogwWeightsArgs {
+    int n;
+    const double* g;
+    const double* G;
+    double* w;
+    const double* lse_pairs;  // [nranks][2]
+    int nranks;
+    double* msum_tail;        // 3 doubles: sum (g-G) w, sum g w, sum G w  (local parts)
+    double* partials;
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_logw_weights(const LogwWeightsArgs a) {
+    __shared__ double red[3 * 32];
+    double M, S;
+    global_lse(a.lse_pairs, a.nranks, M, S);
+    const double inv = 1.0 / S;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const double g = a.g[j], G = a.G[j];
+        const double w = exp(g - M) * inv;
+        a.w[j] = w;
+        v[0] = fma(g - G, w, v[0]);
+        v[1] = fma(g, w, v[1]);
+        v[2] = fma(G, w, v[2]);
+    }
+    double* tail = a.msum_tail;
+    double* sc = a.sc;
+    grid_sum<3>(v, a.partials, a.ticket, red, [=](const double(&t)[3]) {
+        tail[0] = t[0];
+        tail[1] = t[1];
+        tail[2] = t[2];
+        sc[SC_GMAX] = M;
+        sc[SC_S] = S;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// slot reduction of the row pass: msum_i = sum_slots partial[slot][i]   (only needed before an all-reduce)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVecThreads)
+    k_reduce_row_slots(int m, const double* partial, long long ld, long long L, long long chunk, double* msum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int ns = pass_num_slots(i / kTileR, L, chunk);
+    double s = 0.0;
+    for (int q = 0; q < ns; ++q) s += partial[(size_t)q * ld + i];
+    msum[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: finish the row pass: avg_i, r_i = avg_i - Y_i, chi^2/2, and the objective.
+//     logw:   f = theta (sum (g-G) w - log s + log s0) + chi2      c_bioen_kernels_logw.c:122-126,143-146
+//     forces: f = theta KL + chi2                                   c_bioen_kernels_forces.c:244,276
+//     Writes ab[i] = {r_i, avg_i} (logw column pass) or {r_i, 0} (forces t_j pass) and avg[i].
+// ------------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+    int m;
+    const double* partial;   // row-pass slots (used when msum == nullptr)
+    long long ld, L, chunk;
+    const double* msum;      // already slot-reduced (and all-reduced) row sums + 3 tail scalars, or nullptr
+    const double* tail;      // logw: the 3 weighted sums; forces: KL (local tail, or all-reduced in msum)
+    const double* Y;
+    double* ab;
+    double* avg;
+    int ab_with_avg;         // 1: ab = {r, avg}; 0: ab = {r, 0}
+    int is_forces;
+    double theta;
+    double* partials;
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_finalize_rows(const FinalizeArgs a) {
+    __shared__ double red[32];
+    double v[1] = {0.0};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.m) {
+        double s;
+        if (a.msum) {
+            s = a.msum[i];
+        } else {
+            const int ns = pass_num_slots(i / kTileR, a.L, a.chunk);
+            s = 0.0;
+            for (int q = 0; q < ns; ++q) s += a.partial[(size_t)q * a.ld + i];
+        }
+        const double r = s - a.Y[i];
+        a.avg[i] = s;
+        reinterpret_cast<double2*>(a.ab)[i] = make_double2(r, a.ab_with_avg ? s : 0.0);
+        v[0] = r * r;
+    }
+    const FinalizeArgs b = a;
+    grid_sum<1>(v, a.partials, a.ticket, red, [=](const double(&t)[1]) {
+        double* sc = b.sc;
+        const double chi2 = 0.5 * t[0];
+        double prior;
+        if (b.is_forces) {
+            sc[SC_KL] = b.tail[0];
+            prior = b.tail[0] * b.theta;
+        } else {
+            // log s = gmax + log S  (the reference's un-stabilised s = sum exp(g_j))
+            const double val = b.tail[0] - (sc[SC_GMAX] + log(sc[SC_S])) + sc[SC_LOGS0];
+            prior = val * b.theta;
+            sc[SC_GBAR] = b.tail[1];
+            sc[SC_CAPGBAR] = b.tail[2];
+        }
+        sc[SC_CHI2] = chi2;
+        sc[SC_PRIOR] = prior;
+        sc[SC_F] = prior + chi2;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 (logw): finish the column pass:
+//     grad_j = w_j theta (g_j - <g> - G_j + <G>) + w_j sum_i r_i (y_ij - avg_i)   c_bioen_kernels_logw.c:214-217
+//     plus the scalars the line search / stop tests need: grad.d, ||grad||^2, max|grad|.
+// ------------------------------------------------------------------------------------------------
+struct LogwGradArgs {
+    int n;
+    const double* col_partial;
+    long long ld, L, chunk;
+    const double* g;
+    const double* G;
+    const double* w;
+    const double* d;   // may be nullptr
+    double* grad;
+    double theta;
+    double* partials;  // gridDim.x * 3
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_logw_grad(const LogwGradArgs a) {
+    __shared__ double red[3 * 32];
+    const double gbar = a.sc[SC_GBAR], Gbar = a.sc[SC_CAPGBAR];
+    double dg = 0.0, gn = 0.0, gi = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const int ns = pass_num_slots(j / kTileC, a.L, a.chunk);
+        double c = 0.0;
+        for (int q = 0; q < ns; ++q) c += a.col_partial[(size_t)q * a.ld + j];
+        const double w = a.w[j];
+        const double gr = w * a.theta * (a.g[j] - gbar - a.G[j] + Gbar) + w * c;
+        a.grad[j] = gr;
+        if (a.d) dg = fma(gr, a.d[j], dg);
+        gn = fma(gr, gr, gn);
+        gi = fmax(gi, fabs(gr));
+    }
+    double v[3] = {dg, gn, gi};
+    double* sc = a.sc;
+    grid_sum_max<2>(v, a.partials, a.ticket, red, [=](const double(&t)[3]) {
+        sc[SC_DG] = t[0];
+        sc[SC_GNORM2] = t[1];
+        sc[SC_GINF] = t[2];
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// forces: normalised weights, guarded log-ratio and KL   (c_bioen_kernels_forces.c:156-171, 246-274)
+//     w_j = w0_j exp(x_j - xmax) / S;   lr_j = log w_j - log w0_j = x_j - xmax - log S  where both
+//     w_j >= DBL_MIN and w0_j >= DBL_MIN, else 0;  KL = sum_j w_j lr_j (local part -> msum tail[0])
+// ------------------------------------------------------------------------------------------------
+struct ForcesWeightsArgs {
+    int n;
+    const double* x;
+    const double* w0;
+    double* w;
+    double* lr;
+    const double* lse_pairs;
+    int nranks;
+    double* msum_tail;  // 1 double: local KL
+    double* partials;
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_forces_weights(const ForcesWeightsArgs a) {
+    __shared__ double red[32];
+    double M, S;
+    global_lse(a.lse_pairs, a.nranks, M, S);
+    const double inv = 1.0 / S, logS = log(S);
+    double v[1] = {0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const double x = a.x[j], w0 = a.w0[j];
+        const double w = inv * (w0 * exp(x - M));
+        const double lr = (w >= DBL_MIN && w0 >= DBL_MIN) ? (x - M - logS) : 0.0;
+        a.w[j] = w;
+        a.lr[j] = lr;
+        v[0] = fma(lr, w, v[0]);
+    }
+    double* tail = a.msum_tail;
+    double* sc = a.sc;
+    grid_sum<1>(v, a.partials, a.ticket, red, [=](const double(&t)[1]) {
+        tail[0] = t[0];
+        sc[SC_GMAX] = M;
+        sc[SC_S] = S;
+    });
+}
+
+// forces: E_j = (theta (1 + lr_j) + t_j) w_j,  t_j = column-pass sums    (c_bioen_kernels_forces.c:321-328)
+struct ForcesEArgs {
+    int n;
+    const double* col_partial;
+    long long ld, L, chunk;
+    const double* w;
+    const double* lr;
+    double* E;
+    double theta;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_forces_E(const ForcesEArgs a) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const int ns = pass_num_slots(j / kTileC, a.L, a.chunk);
+        double t = 0.0;
+        for (int q = 0; q < ns; ++q) t += a.col_partial[(size_t)q * a.ld + j];
+        a.E[j] = ((1.0 + a.lr[j]) * a.theta + t) * a.w[j];
+    }
+}
+
+// forces: finish the gradient row pass: grad_i = sum_slots, plus grad.d, ||grad||^2, max|grad| (M is small:
+// one block).  When `msum` is given the slots were already reduced (and all-reduced across ranks).
+struct ForcesGradArgs {
+    int m;
+    const double* partial;
+    long long ld, L, chunk;
+    const double* msum;
+    const double* d;
+    double* grad;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(1024) k_forces_grad(const ForcesGradArgs a) {
+    __shared__ double red[3 * 32];
+    double dg = 0.0, gn = 0.0, gi = 0.0;
+    for (int i = threadIdx.x; i < a.m; i += blockDim.x) {
+        double s;
+        if (a.msum) {
+            s = a.msum[i];
+        } else {
+            const int ns = pass_num_slots(i / kTileR, a.L, a.chunk);
+            s = 0.0;
+            for (int q = 0; q < ns; ++q) s += a.partial[(size_t)q * a.ld + i];
+        }
+        a.grad[i] = s;
+        if (a.d) dg = fma(s, a.d[i], dg);
+        gn = fma(s, s, gn);
+        gi = fmax(gi, fabs(s));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    dg = warp_sum(dg); gn = warp_sum(gn); gi = warp_max(gi);
+    if (lane == 0) { red[wid] = dg; red[32 + wid] = gn; red[64 + wid] = gi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w) { dg += red[w]; gn += red[32 + w]; gi = fmax(gi, red[64 + w]); }
+        a.sc[SC_DG] = dg;
+        a.sc[SC_GNORM2] = gn;
+        a.sc[SC_GINF] = gi;
+    }
+}
+
+// forces: x = xp + stp*d (optional), ||x||^2, and ab[i] = {x_i, 0} for the first column pass (M is small)
+struct ForcesUpdateArgs {
+    int m;
+    double* x;
+    const double* xp;
+    const double* d;
+    double stp;
+    double* ab;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(1024) k_forces_update(const ForcesUpdateArgs a) {
+    __shared__ double red[32];
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < a.m; i += blockDim.x) {
+        double x = a.x[i];
+        if (a.xp) {
+            x = fma(a.stp, a.d[i], a.xp[i]);
+            a.x[i] = x;
+        }
+        reinterpret_cast<double2*>(a.ab)[i] = make_double2(x, 0.0);
+        v[0] = fma(x, x, v[0]);
+    }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) a.sc[SC_XNORM2] = v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic vector kernels (device-resident minimisers)
+// ------------------------------------------------------------------------------------------------
+// out[0..K) = sums of up to 3 dot products in one sweep; pairs given as pointers (nullptr = unused)
+struct Dot3Args {
+    int n;
+    const double *a0, *b0, *a1, *b1, *a2, *b2;
+    double* out;  // device, 3 doubles
+    double* partials;
+    unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_dot3(const Dot3Args a) {
+    __shared__ double red[3 * 32];
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        v[0] = fma(a.a0[j], a.b0[j], v[0]);
+        if (a.a1) v[1] = fma(a.a1[j], a.b1[j], v[1]);
+        if (a.a2) v[2] = fma(a.a2[j], a.b2[j], v[2]);
+    }
+    double* out = a.out;
+    grid_sum<3>(v, a.partials, a.ticket, red, [=](const double(&t)[3]) {
+        out[0] = t[0];
+        out[1] = t[1];
+        out[2] = t[2];
+    });
+}
+
+// z = alpha*x + beta*y  (z may alias x or y; y may be nullptr when beta == 0)
+__global__ void __launch_bounds__(kVecThreads)
+    k_axpby(int n, double alpha, const double* x, double beta, const double* y, double* z) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double v = alpha * x[j];
+        z[j] = y ? fma(beta, y[j], v) : v;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_max_abs(int n, const double* x, double* out) {
+    // single block, small or rarely used
+    __shared__ double red[32];
+    double m = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmax(m, fabs(x[j]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        out[0] = m;
+    }
+}
+
+// L-BFGS: s = x - xp, y = g - gp, ys = y.s, yy = y.y; then xp <- x, gp <- g for the next iteration
+//     (liblbfgs lbfgs.c:543-555 and 462-463)
+struct PairArgs {
+    int n;
+    const double *x, *g;
+    double *xp, *gp;
+    double *s, *y;
+    int slot;          // ring index: sc[SC_YS0 + slot] = ys
+    double* partials;
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_lbfgs_pair(const PairArgs a) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0.0, 0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const double x = a.x[j], g = a.g[j];
+        const double s = x - a.xp[j], y = g - a.gp[j];
+        a.s[j] = s;
+        a.y[j] = y;
+        a.xp[j] = x;
+        a.gp[j] = g;
+        v[0] = fma(y, s, v[0]);
+        v[1] = fma(y, y, v[1]);
+    }
+    double* sc = a.sc;
+    const int slot = a.slot;
+    grid_sum<2>(v, a.partials, a.ticket, red, [=](const double(&t)[2]) {
+        sc[SC_YS] = t[0];
+        sc[SC_YY] = t[1];
+        sc[SC_YS0 + slot] = t[0];
+    });
+}
+
+// One step of the two-loop recursion, fused: d <- [init ? -g : d] + coef * u ; d *= scale ; out = v . d
+//     coef and scale are formed on the device from raw dot products already sitting in sc[]:
+//       coef  = csign * sc[c_num] / sc[c_den]  (+ sc[c2_num]/sc[c2_den] * c2sign when c2_num >= 0)
+//       scale = sc[s_num] / sc[s_den]          (when s_num >= 0)
+//     so the whole recursion (liblbfgs lbfgs.c:572-598) runs without a host round trip.
+struct TwoLoopArgs {
+    int n;
+    double* d;
+    const double* g;      // used when init
+    int init;
+    const double* u;      // nullptr: no axpy
+    int c_num, c_den; double csign;
+    int c2_num, c2_den; double c2sign;
+    int s_num, s_den;
+    const double* v;      // nullptr: no dot
+    int out;              // sc index receiving the raw dot v.d
+    double* partials;
+    unsigned int* ticket;
+    double* sc;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs a) {
+    __shared__ double red[32];
+    double coef = 0.0, scale = 1.0;
+    if (a.u) {
+        coef = a.csign * (a.sc[a.c_num] / a.sc[a.c_den]);
+        if (a.c2_num >= 0) coef += a.c2sign * (a.sc[a.c2_num] / a.sc[a.c2_den]);
+    }
+    if (a.s_num >= 0) scale = a.sc[a.s_num] / a.sc[a.s_den];
+    double v[1] = {0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        double dj = a.init ? -a.g[j] : a.d[j];
+        if (a.u) dj = fma(coef, a.u[j], dj);
+        if (a.s_num >= 0) dj *= scale;
+        a.d[j] = dj;
+        if (a.v) v[0] = fma(a.v[j], dj, v[0]);
+    }
+    if (a.v) {
+        double* sc = a.sc;
+        const int out = a.out;
+        grid_sum<1>(v, a.partials, a.ticket, red, [=](const double(&t)[1]) { sc[out] = t[0]; });
+    }
+}
+
+}  // namespace bioen

@@ -1,0 +1,203 @@
+/* bioen_b200.h -- C ABI of libbioen_b200.so, the B200 (sm_100a) implementation of BioEn's optimisation
+ * hot path.  Plain C: pointers and sizes only, no CUDA or torch types.
+ *
+ * Part 1 is the drop-in boundary: the exact symbols (names, argument order, struct layouts, error
+ * convention) that the reference's Cython layer binds from its OpenMP C kernels, so that
+ * bioen/optimize/ext/c_bioen.pyx (extern blocks at lines 10-129) links against this library unchanged.
+ * All pointers in part 1 are HOST pointers owned by the caller, exactly as in the reference; the library
+ * uploads what it needs, runs on the GPU, and writes results back before returning.
+ *
+ * Part 2 is the handle API the host-side Python mirror (bioen_b200/optimize) actually uses: yTilde is
+ * uploaded once per problem and stays resident in HBM across evaluations, minimiser iterations and a whole
+ * theta series.
+ *
+ * Citations are paths relative to the reference repository root (bio-phys/BioEn v0.1.3).
+ */
+#ifndef BIOEN_B200_H
+#define BIOEN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 1 -- reference-compatible symbols
+ * ------------------------------------------------------------------------------------------------ */
+
+/* bioen/optimize/ext/c_bioen_common.h:44-60 (passed BY VALUE to the _opt_* drivers) */
+typedef struct params_t {
+    double *forces;
+    double *w0;
+    double *g;
+    double *G;
+    double *yTilde;   /* m x n, row-major, C-contiguous float64 */
+    double *YTilde;   /* m */
+    double *w;        /* n, scratch */
+    double *result;   /* n (logw) or m (forces): minimiser end point */
+    double theta;
+    double *yTildeT;  /* accepted and ignored: the GPU needs no transposed copy */
+    int caching;      /* accepted and ignored */
+    double *tmp_n;    /* scratch, may be NULL here */
+    double *tmp_m;    /* scratch, may be NULL here */
+    int m;
+    int n;
+} params_t;
+
+/* c_bioen_common.h:62-67 */
+typedef struct gsl_config_params {
+    double step_size;
+    double tol;
+    int max_iterations;
+    int algorithm;    /* 0 conjugate_fr, 1 conjugate_pr, 2 vector_bfgs2, 3 vector_bfgs, 4 steepest_descent */
+} gsl_config_params;
+
+/* c_bioen_common.h:69-79 */
+typedef struct lbfgs_config_params {
+    int linesearch;   /* 0 More-Thuente, 1 Armijo, 2 Wolfe (BioEn default), 3 strong Wolfe */
+    int max_iterations;
+    double delta;
+    double epsilon;
+    double ftol;
+    double gtol;
+    double wolfe;
+    int past;
+    int max_linesearch;
+} lbfgs_config_params;
+
+/* c_bioen_common.h:89-92 */
+typedef struct visual_params {
+    size_t debug;
+    size_t verbose;
+} visual_params;
+
+/* replaces c_bioen_kernels_logw.c:55-94 -- w = softmax(g); returns s = sum_j exp(g_j).
+ * (The device computes a max-stabilised log-sum-exp; s is reconstructed and overflows to +inf exactly when the
+ * reference's un-stabilised sum does.) */
+double _get_weights(const double *g, double *w, size_t n);
+
+/* replaces c_bioen_kernels_logw.c:131-147 -- log-weights objective.  `w` and `weights_sum` are recomputed on
+ * the device from g (every reference call site passes w = softmax(g)); `gradient`, `caching`, `yTildeT`,
+ * `tmp_n`, `tmp_m` are unused as in the reference. */
+double _bioen_log_posterior_logw(const double *g, const double *G, const double *yTilde, const double *YTilde,
+                                 const double *w, const double *gradient, double theta, int caching,
+                                 const double *yTildeT, double *tmp_n, double *tmp_m, int m, int n,
+                                 double weights_sum);
+
+/* replaces c_bioen_kernels_logw.c:151-268 -- log-weights gradient, written to gradient[n] */
+void _grad_bioen_log_posterior_logw(const double *g, const double *G, const double *yTilde, const double *YTilde,
+                                    const double *w, double *gradient, double theta, int caching,
+                                    const double *yTildeT, double *tmp_n, double *tmp_m, int m, int n,
+                                    double weights_sum);
+
+/* replaces c_bioen_kernels_logw.c:367-509 (GSL multimin driver) and 581-669 (liblbfgs driver).
+ * Return fmin; *error receives the GSL status / liblbfgs return code; func_params.result receives x. */
+double _opt_bfgs_logw(params_t func_params, gsl_config_params config, visual_params visual, int *error);
+double _opt_lbfgs_logw(params_t func_params, lbfgs_config_params config, visual_params visual, int *error);
+
+/* replaces c_bioen_kernels_forces.c:111-224 -- w ~ w0 * exp(+ yTilde^T forces), normalised */
+void _get_weights_from_forces(const double *w0, const double *yTilde, const double *forces, double *w,
+                              int caching, const double *yTildeT, double *tmp_n, size_t m, size_t n);
+
+/* replaces c_bioen_kernels_forces.c:227-277.  NOTE: like the reference this takes the WEIGHTS `w`, not the
+ * forces; the device recomputes nothing here: KL and chi^2 are evaluated for the given w. */
+double _bioen_log_posterior_forces(const double *w0, const double *yTilde, const double *YTilde, const double *w,
+                                   const double *result, double theta, int caching, const double *yTildeT,
+                                   double *tmp_n, double *tmp_m, int m, int n);
+
+/* replaces c_bioen_kernels_forces.c:280-340 -- gradient w.r.t. the forces for the given weights w */
+void _grad_bioen_log_posterior_forces(const double *w0, const double *yTilde, const double *YTilde,
+                                      const double *w, double *gradient, double theta, int caching,
+                                      const double *yTildeT, double *tmp_n, double *tmp_m, int m, int n);
+
+/* replace c_bioen_kernels_forces.c:431-570 and 574-662 */
+double _opt_bfgs_forces(params_t func_params, gsl_config_params config, visual_params visual, int *error);
+double _opt_lbfgs_forces(params_t func_params, lbfgs_config_params config, visual_params visual, int *error);
+
+/* c_bioen_common.c:32-61.  Both minimiser families are built in (no external GSL / liblbfgs needed): 1, 1.
+ * The "fast OpenMP" flag is stored and returned but has no effect: device reductions are always fixed-order
+ * (the reproducible mode).  _omp_set_num_threads is a no-op. */
+int _library_gsl(void);
+int _library_lbfgs(void);
+void _omp_set_num_threads(int n);
+void _set_fast_openmp_flag(int flag);
+int _get_fast_openmp_flag(void);
+
+/* c_bioen_error.c:14-115 -- message texts for GSL status codes and liblbfgs return codes */
+const char *bioen_gsl_error(int gsl_errno);
+const char *lbfgs_strerror(int error);
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 2 -- handle API (yTilde resident in HBM)
+ * All functions returning int return 0 on success, non-zero on failure (text: bioen_b200_last_error()).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct bioen_b200_ctx bioen_b200_ctx;
+
+enum { BIOEN_B200_LOGW = 0, BIOEN_B200_FORCES = 1 };
+
+const char *bioen_b200_last_error(void);
+int bioen_b200_device_count(void);
+
+/* (m x n) = shape of the LOCAL block of yTilde (all of it on one GPU; this rank's columns when sharded) */
+bioen_b200_ctx *bioen_b200_create(int m, int n, int device);
+void bioen_b200_destroy(bioen_b200_ctx *ctx);
+
+/* copy yTilde from host memory (row stride ld doubles) into HBM, or adopt a matrix already on the device
+ * (even row stride, 16-byte aligned base; the caller keeps ownership) */
+int bioen_b200_upload_ytilde(bioen_b200_ctx *ctx, const double *yTilde_host, size_t ld);
+int bioen_b200_adopt_ytilde(bioen_b200_ctx *ctx, double *yTilde_dev, size_t ld);
+
+/* per-method constant data: reference log-weights G[n] or reference weights w0[n], YTilde[m], theta */
+int bioen_b200_set_logw(bioen_b200_ctx *ctx, const double *G_host, const double *YTilde_host, double theta);
+int bioen_b200_set_forces(bioen_b200_ctx *ctx, const double *w0_host, const double *YTilde_host, double theta);
+int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
+
+/* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
+ * two for logw, two instead of four for forces). */
+int bioen_b200_eval(bioen_b200_ctx *ctx, int method, const double *x_host, double *f, double *grad_host);
+/* weights for log-weights g[n] / forces f[m]; w_host[n]; *sum (may be NULL) = sum_j exp(g_j) for logw */
+int bioen_b200_weights(bioen_b200_ctx *ctx, int method, const double *x_host, double *w_host, double *sum);
+/* avg[m] = yTilde . w for host w[n] (post-processing with the resident matrix) */
+int bioen_b200_average(bioen_b200_ctx *ctx, const double *w_host, double *avg_host);
+/* objective / gradient of the forces method for GIVEN weights w[n] (reference semantics, part 1) */
+int bioen_b200_forces_from_weights(bioen_b200_ctx *ctx, const double *w_host, double *f, double *grad_host);
+
+/* minimisers; x0_host/x_host have n (logw) or m (forces) entries and may alias.  The function result is the
+ * minimiser's own status (liblbfgs return code / GSL status, see part 1); *fmin the final objective;
+ * info[0] = iterations, info[1] = f+g evaluations (f-only probes counted in info[2]).  A CUDA failure returns
+ * -2000 and sets bioen_b200_last_error(). */
+int bioen_b200_opt_lbfgs(bioen_b200_ctx *ctx, int method, const double *x0_host, double *x_host,
+                         lbfgs_config_params config, visual_params visual, double *fmin, int info[4]);
+int bioen_b200_opt_gsl(bioen_b200_ctx *ctx, int method, const double *x0_host, double *x_host,
+                       gsl_config_params config, visual_params visual, double *fmin, int info[4]);
+
+/* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
+int bioen_b200_nccl_unique_id(char id[128]);
+int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks);
+
+/* device-pointer entry points (inputs already resident in HBM; used by bench.py and torch carriers).
+ * Everything is enqueued on the context's stream; bioen_b200_fetch waits for it. */
+int bioen_b200_set_logw_dev(bioen_b200_ctx *ctx, const double *G_dev, const double *YTilde_host, double theta);
+int bioen_b200_set_forces_dev(bioen_b200_ctx *ctx, const double *w0_dev, const double *YTilde_host, double theta);
+int bioen_b200_eval_dev(bioen_b200_ctx *ctx, int method, double *x_dev, double *grad_dev);
+int bioen_b200_fetch(bioen_b200_ctx *ctx, double *f, double *gnorm2);
+int bioen_b200_opt_lbfgs_dev(bioen_b200_ctx *ctx, int method, double *x_dev, lbfgs_config_params config,
+                             visual_params visual, double *fmin, int info[4]);
+/* time `steps` evaluations (after `warmup` untimed ones) with CUDA events on the context's stream.
+ * Successive steps evaluate at x + k*eps*dir so no step repeats the previous one.  Returns total ms in *ms,
+ * the mean duration of one yTilde pass kernel in *pass_ms, and the number of kernels launched inside the
+ * timed region in *launches. */
+int bioen_b200_time_evals(bioen_b200_ctx *ctx, int method, double *x_dev, double *grad_dev, int warmup, int steps,
+                          float *ms, float *pass_ms, long long *launches);
+/* generate a synthetic "generic data" yTilde block on the device (counter-based RNG, reproducible per
+ * (seed, row, global column)); see bench.py */
+int bioen_b200_generate_ytilde(bioen_b200_ctx *ctx, unsigned long long seed, long long col_offset,
+                               const double *ytrue_over_sigma_host, double inv_sigma);
+long long bioen_b200_kernels_launched(bioen_b200_ctx *ctx);
+int bioen_b200_debug_read(bioen_b200_ctx *ctx, int what, double *out_host, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOEN_B200_H */
