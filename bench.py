@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- BioEn optimisation hot path on B200: gradient (f+g) evaluations per second.
+
+Workload (BASELINE.json `metric`): log-weights method, synthetic "generic data" (seed 12345,
+sig_exp 0.5, sig_sim 1, uniform w0, G = 0), N = 1e6 structures x M = 1e3 observables per GPU, theta = 10, fp64.
+One "step" = one evaluation of the log-posterior AND its gradient at a fresh point (2 passes over yTilde).
+
+  value      steps / device time, yTilde + all vectors resident in HBM (CUDA events, max over ranks)
+  e2e        the same through the C ABI with HOST vectors (bioen_b200_eval): every step copies g from pinned
+             host memory to the device and reads the objective and the gradient back
+  roofline   the dominant kernel (stream_pass_kernel, one pass over yTilde = M*N*8 algorithmic bytes per launch),
+             timed live with CUDA events around every launch inside the timed region
+  cpu_baseline  the reference's own OpenMP C kernels (oracle/_ref, built from /root/reference by oracle/Makefile)
+             on the host cores, on a column sample of the same problem
+
+N > 1 (torchrun): the structure axis is sharded, every rank holds N = 1e6 columns (weak scaling), one fused
+NCCL all-reduce of M+3 doubles (+ tiny scalar reductions) per evaluation; `value` counts 1e6-structure
+evaluations per second summed over ranks.
+
+`--impl reference` times the reference CPU implementation alone (no GPU code on that path).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 12345
+SIG_EXP, SIG_SIM = 0.5, 1.0
+THETA = 10.0
+METRIC = "grad_evals_per_s"
+UNIT = "evals/s (f+g, logw, N=1e6 x M=1e3 per evaluation)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--m", type=int, default=1000)
+    ap.add_argument("--n", type=int, default=1000000, help="structures PER GPU")
+    ap.add_argument("--method", default="logw", choices=["logw", "forces"])
+    ap.add_argument("--cpu-cols", type=int, default=200000, help="columns of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimum", action="store_true")
+    return ap.parse_args()
+
+
+def observations(M):
+    """YTrue / sigma and YTilde of the generic-data recipe (the M-vectors are tiny: host NumPy)."""
+    rng = np.random.default_rng(SEED)
+    ytrue = rng.standard_normal(M)
+    yobs = ytrue + SIG_EXP * rng.standard_normal(M)
+    return ytrue / SIG_EXP, yobs / SIG_EXP
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled with NVML during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "sw_power_cap": 0x4, "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's OpenMP C kernels on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_evals(M, N_full, cols, steps, warmup, method):
+    """f+g evaluations/s of the reference C code (oracle/_ref) -- or of the oracle port if _ref is absent --
+    on a `cols`-column sample, scaled to N_full columns (cost is linear in N).  Returns (value, info)."""
+    from oracle import oracle as O
+    from oracle import ref
+    cores = host_cores()
+    a, YT = observations(M)
+    rng = np.random.default_rng(SEED + 1)
+    yT = np.empty((M, cols))
+    blk = 64
+    for i in range(0, M, blk):  # chunked: bounded temporaries
+        j = min(M, i + blk)
+        yT[i:j] = a[i:j, None] + (SIG_SIM / SIG_EXP) * rng.standard_normal((j - i, cols))
+    G = np.zeros(cols)
+    w0 = np.full(cols, 1.0 / cols)
+    x = 0.1 * rng.standard_normal(cols) if method == "logw" else 1e-3 * rng.standard_normal(M)
+    best = None
+    if ref.available():
+        kind = "reference"
+        ref.set_num_threads(cores)
+        ref.set_fast_openmp_flag(1)      # the reference's fastest mode
+        used = cores
+        evs = []
+        for caching in (True, False):    # the reference's transposed-cache option: time both, keep the faster
+            evs.append((ref.LogwEvaluator(G, yT, YT, THETA, caching=caching) if method == "logw"
+                        else ref.ForcesEvaluator(w0, yT, YT, THETA, caching=caching), caching))
+    else:
+        kind = "port"
+        used = 1
+        evs = [((lambda v: O.logw_fg(v, G, yT, YT, THETA)) if method == "logw"
+                else (lambda v: O.forces_fg(v, w0, yT, YT, THETA)), False)]
+    for ev, caching in evs:
+        for _ in range(max(1, warmup)):
+            ev(x)
+        times = []
+        for k in range(steps):
+            t0 = time.perf_counter()
+            ev(x + 1e-9 * k)
+            times.append(time.perf_counter() - t0)
+        if best is None or min(times) < best[0]:
+            best = (min(times), float(np.mean(times)), caching)
+    dt_best, dt_mean, caching = best
+    per_eval_full = dt_best * (N_full / cols)
+    info = {"kind": kind, "cores": used, "ms_per_eval_sample": 1e3 * dt_best,
+            "sample": "%d of %d columns x %d rows (%.1f GB), best of %d f+g evaluations (mean %.1f ms, best "
+                      "%.1f ms), fast_openmp=1, yTildeT cache %s (faster of on/off); evals/s scaled by %d/%d "
+                      "(cost linear in N)" % (cols, N_full, M, M * cols * 8 / 1e9, steps, 1e3 * dt_mean,
+                                              1e3 * dt_best, "on" if caching else "off", cols, N_full)}
+    return 1.0 / per_eval_full, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    t_wall = time.perf_counter()
+    value, info = cpu_reference_evals(args.m, args.n, args.cpu_cols, steps, min(args.warmup, 2), args.method)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d, theta=%g"
+                               % (args.method, args.n, args.m, THETA), "method": args.method},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import bioen_b200
+    from bioen_b200 import _lib
+    from bioen_b200.problem import FORCES, LOGW
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1)" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    M, N = args.m, args.n
+    method = LOGW if args.method == "logw" else FORCES
+    nvar = N if method == LOGW else M
+    a, YT = observations(M)
+
+    prob = bioen_b200.Problem(shape=(M, N), device=local)
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            _lib.check(_lib.load().bioen_b200_nccl_unique_id(raw), "nccl_unique_id")
+            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        prob.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world, N * world)
+    t0 = time.perf_counter()
+    prob.generate(SEED, rank * N, a, SIG_SIM / SIG_EXP)      # this rank's columns of the global matrix
+    gen_s = time.perf_counter() - t0
+    n_total = N * world
+    if method == LOGW:
+        prob.set_logw(np.zeros(N), YT, THETA)
+    else:
+        prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
+
+    # start point: non-uniform weights (SURVEY 8d parity point); replicated vector for forces
+    rng = np.random.default_rng(SEED + 7 + (rank if method == LOGW else 0))
+    x_host = torch.empty(nvar, dtype=torch.float64).pin_memory()
+    g_host = torch.empty(nvar, dtype=torch.float64).pin_memory()
+    x_np, g_np = x_host.numpy(), g_host.numpy()
+    x_np[:] = (0.1 if method == LOGW else 1e-3) * rng.standard_normal(nvar)
+    x_dev = x_host.to(dev)
+    g_dev = torch.zeros_like(x_dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------------
+    barrier()
+    with ClockSampler(local) as clk:
+        ms, pass_ms, launches = prob.time_evals(x_dev.data_ptr(), g_dev.data_ptr(), args.warmup, args.steps)
+    barrier()
+    t = torch.tensor([ms, pass_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, pass_ms = float(t[0]), float(t[1])
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host vectors through the C ABI ------------------------------------------------------
+    lib = _lib.load()
+    f = ctypes.c_double()
+    e2e_steps = args.steps
+    for k in range(args.warmup):
+        _lib.check(lib.bioen_b200_eval(prob._h, method, _lib.ptr(x_np), ctypes.byref(f), _lib.ptr(g_np)), "eval")
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        x_np[0] += 1e-9          # a new point every step
+        _lib.check(lib.bioen_b200_eval(prob._h, method, _lib.ptr(x_np), ctypes.byref(f), _lib.ptr(g_np)), "eval")
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(te[0])
+
+    # ---- time to optimum (device L-BFGS, BioEn defaults) -----------------------------------------------
+    optimum = None
+    if not args.no_optimum:
+        x0 = np.zeros(nvar)
+        barrier()
+        t0 = time.perf_counter()
+        xo, fmin, code, info = prob.opt_lbfgs(x0)
+        barrier()
+        optimum = {"seconds": time.perf_counter() - t0, "code": code, "fmin": fmin,
+                   "iterations": info["iterations"], "evaluations": info["evaluations"],
+                   "minimizer": "device L-BFGS (liblbfgs semantics, BioEn defaults: linesearch=2, past=10, "
+                                "delta=1e-6, epsilon=1e-6)", "includes": "x0 H2D + result D2H; yTilde resident"}
+
+    peak, peak_src = measured_peak()
+    alg_bytes = float(M) * N * 8.0
+    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d per GPU (yTilde %.1f GB fp64 "
+                        "per GPU, N sharded over %d GPU(s)), theta=%g" % (args.method, N, M, alg_bytes / 1e9,
+                                                                         world, THETA),
+            "method": args.method, "n_per_gpu": N, "m": M, "n_total": n_total,
+            "l2": "inputs (%.1f GB) larger than L2 (126 MB); every step evaluates a new point" % (alg_bytes / 1e9),
+            "global_evals_per_s": args.steps / (ms * 1e-3),
+            "generate_s": gen_s,
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "stream_pass_kernel (one pass over yTilde)", "bytes_per_launch": alg_bytes,
+                     "ms_per_launch": pass_ms,
+                     "step_frac": (2 * M * N * 8.0) / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,
+                "api": "bioen_b200_eval (C ABI, pinned host vectors; yTilde resident after one upload)"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if optimum:
+        line["time_to_optimum"] = optimum
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_reference_evals(M, N, args.cpu_cols, 5, 1, args.method)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"]}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+    prob.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,763 @@
+// bioen_b200.cu -- the C ABI of libbioen_b200.so (see include/bioen_b200.h).
+//
+// Part 1 re-exports the symbols of the reference's C extension with the same signatures and host-pointer
+// ownership rules (bioen/optimize/ext/c_bioen.pyx:10-129 is the binding a maintainer keeps unchanged);
+// every call uploads its inputs, runs on the GPU and copies the results back.  Part 2 is the handle API with
+// yTilde resident in HBM that the Python mirror and bench.py use.
+//
+// There is no CPU fallback anywhere in this file: without a usable sm_100 device every entry point fails
+// (error text in bioen_b200_last_error(), NaN / non-zero status as the return value).
+#include "../../include/bioen_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <mutex>
+
+#include "context.cuh"
+#include "gsl_min.cuh"
+#include "lbfgs.cuh"
+
+using namespace bioen;
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_last_error;
+thread_local int g_error_pending = 0;
+int g_fast_flag = 0;
+
+void set_error(const char* where, const std::exception& e) {
+    g_last_error = std::string(where) + ": " + e.what();
+    g_error_pending = 1;
+    fprintf(stderr, "%s\n", g_last_error.c_str());
+}
+
+template <class F>
+int guarded(const char* where, F&& body) {
+    try {
+        body();
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(where, e);
+        // leave no sticky error behind in the runtime
+        cudaGetLastError();
+        return 1;
+    }
+}
+const double kNaN = std::numeric_limits<double>::quiet_NaN();
+}  // namespace
+
+struct bioen_b200_ctx {
+    Context C;
+    std::unique_ptr<Comm> comm;
+    DevBuf<double> xn, gn, xm, gm;  // staging vectors for host-pointer calls
+    bioen_b200_ctx(int m, int n, int dev) : C(m, n, dev) {}
+    double* x_for(int method) {
+        if (method == BIOEN_B200_FORCES) {
+            if (!xm.p) { xm.alloc(C.Mpad); gm.alloc(C.Mpad); }
+            return xm.p;
+        }
+        if (!xn.p) { xn.alloc(C.Npad); gn.alloc(C.Npad); }
+        return xn.p;
+    }
+    double* g_for(int method) {
+        x_for(method);
+        return method == BIOEN_B200_FORCES ? gm.p : gn.p;
+    }
+    int dim(int method) const { return method == BIOEN_B200_FORCES ? C.M : C.N; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// synthetic "generic data" generator (bench.py, large-size property tests)
+//   yTilde_ij = a_i + b * z(seed, i, col_offset + j),   z ~ N(0,1) from a counter-based hash (splitmix64
+//   finaliser on (seed, row, global column)) and Box-Muller.  tests/util_rng.py restates it in NumPy.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_generate(double* Y, long long ld, int m, int n, unsigned long long seed,
+                                                   long long col_offset, const double* a, double b) {
+    const long long total = (long long)m * n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n);
+        const int j = (int)(t - (long long)i * n);
+        const unsigned long long ctr = ((unsigned long long)i << 40) + (unsigned long long)(col_offset + j);
+        const unsigned long long h1 = mix64(seed + 0x9E3779B97F4A7C15ULL * (ctr + 1));
+        const unsigned long long h2 = mix64(h1 + 0x9E3779B97F4A7C15ULL);
+        const double u1 = ((double)(h1 >> 11) + 1.0) * 0x1.0p-53;  // (0, 1]
+        const double u2 = (double)(h2 >> 11) * 0x1.0p-53;          // [0, 1)
+        const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        Y[(size_t)i * ld + j] = fma(b, z, a[i]);
+    }
+}
+
+// x <- x + eps*dir on the device (time_evals: no two timed steps evaluate the same point)
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------
+// Part 2 -- handle API
+// ---------------------------------------------------------------------------------------------------
+const char* bioen_b200_last_error(void) { return g_last_error.c_str(); }
+
+int bioen_b200_error_pending(void) {
+    const int p = g_error_pending;
+    g_error_pending = 0;
+    return p;
+}
+
+int bioen_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+bioen_b200_ctx* bioen_b200_create(int m, int n, int device) {
+    bioen_b200_ctx* ctx = nullptr;
+    guarded("bioen_b200_create", [&] { ctx = new bioen_b200_ctx(m, n, device); });
+    return ctx;
+}
+
+void bioen_b200_destroy(bioen_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->C.device);
+    cudaStreamSynchronize(ctx->C.stream);
+    delete ctx;
+}
+
+int bioen_b200_upload_ytilde(bioen_b200_ctx* ctx, const double* yTilde_host, size_t ld) {
+    return guarded("bioen_b200_upload_ytilde", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.upload_matrix(yTilde_host, ld);
+        ctx->C.sync();
+    });
+}
+
+int bioen_b200_adopt_ytilde(bioen_b200_ctx* ctx, double* yTilde_dev, size_t ld) {
+    return guarded("bioen_b200_adopt_ytilde", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.adopt_matrix(yTilde_dev, ld);
+    });
+}
+
+int bioen_b200_alloc_ytilde(bioen_b200_ctx* ctx) {
+    return guarded("bioen_b200_alloc_ytilde", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.alloc_matrix();
+    });
+}
+
+int bioen_b200_set_logw(bioen_b200_ctx* ctx, const double* G_host, const double* YTilde_host, double theta) {
+    return guarded("bioen_b200_set_logw", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.set_observations(YTilde_host);
+        ctx->C.set_theta(theta);
+        ctx->C.set_logw(G_host, false);
+    });
+}
+
+int bioen_b200_set_forces(bioen_b200_ctx* ctx, const double* w0_host, const double* YTilde_host, double theta) {
+    return guarded("bioen_b200_set_forces", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.set_observations(YTilde_host);
+        ctx->C.set_theta(theta);
+        ctx->C.set_forces(w0_host, false);
+        ctx->C.sync();
+    });
+}
+
+int bioen_b200_set_logw_dev(bioen_b200_ctx* ctx, const double* G_dev, const double* YTilde_host, double theta) {
+    return guarded("bioen_b200_set_logw_dev", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.set_observations(YTilde_host);
+        ctx->C.set_theta(theta);
+        ctx->C.set_logw(G_dev, true);
+    });
+}
+
+int bioen_b200_set_forces_dev(bioen_b200_ctx* ctx, const double* w0_dev, const double* YTilde_host, double theta) {
+    return guarded("bioen_b200_set_forces_dev", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.set_observations(YTilde_host);
+        ctx->C.set_theta(theta);
+        ctx->C.set_forces(w0_dev, true);
+        ctx->C.sync();
+    });
+}
+
+int bioen_b200_set_theta(bioen_b200_ctx* ctx, double theta) {
+    ctx->C.set_theta(theta);
+    return 0;
+}
+
+int bioen_b200_eval(bioen_b200_ctx* ctx, int method, const double* x_host, double* f, double* grad_host) {
+    return guarded("bioen_b200_eval", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const int n = ctx->dim(method);
+        double* x = ctx->x_for(method);
+        double* g = grad_host ? ctx->g_for(method) : nullptr;
+        C.h2d(x, x_host, n);
+        if (method == BIOEN_B200_FORCES) C.forces_eval(x, nullptr, nullptr, 0.0, g, nullptr);
+        else C.logw_eval(x, nullptr, nullptr, 0.0, g, nullptr);
+        if (grad_host) C.d2h(grad_host, g, n);
+        C.fetch_scalars();
+        if (f) *f = C.h_sc[SC_F];
+    });
+}
+
+int bioen_b200_weights(bioen_b200_ctx* ctx, int method, const double* x_host, double* w_host, double* sum) {
+    return guarded("bioen_b200_weights", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const int n = ctx->dim(method);
+        double* x = ctx->x_for(method);
+        C.h2d(x, x_host, n);
+        if (method == BIOEN_B200_FORCES) C.forces_weights_only(x);
+        else C.logw_weights_only(x);
+        C.d2h(w_host, C.w.p, C.N);
+        C.fetch_scalars();
+        // the reference returns the un-stabilised sum_j exp(g_j)
+        if (sum) *sum = std::exp(C.h_sc[SC_GMAX]) * C.h_sc[SC_S];
+    });
+}
+
+int bioen_b200_average(bioen_b200_ctx* ctx, const double* w_host, double* avg_host) {
+    return guarded("bioen_b200_average", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        C.h2d(C.w.p, w_host, C.N);
+        C.average_of_w(C.avg.p);
+        C.d2h(avg_host, C.avg.p, C.M);
+        C.sync();
+    });
+}
+
+int bioen_b200_forces_from_weights(bioen_b200_ctx* ctx, const double* w_host, double* f, double* grad_host) {
+    return guarded("bioen_b200_forces_from_weights", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        double* g = grad_host ? ctx->g_for(BIOEN_B200_FORCES) : nullptr;
+        C.h2d(C.w.p, w_host, C.N);
+        C.forces_from_weights(g);
+        if (grad_host) C.d2h(grad_host, g, C.M);
+        C.fetch_scalars();
+        if (f) *f = C.h_sc[SC_F];
+    });
+}
+
+static LbfgsParams to_params(const lbfgs_config_params& c) {
+    // c_bioen_kernels_logw.c:607-617: lbfgs_parameter_init then nine overrides; m, min/max_step, xtol stay default
+    LbfgsParams p;
+    p.linesearch = c.linesearch;
+    p.max_iterations = c.max_iterations;
+    p.delta = c.delta;
+    p.epsilon = c.epsilon;
+    p.ftol = c.ftol;
+    p.gtol = c.gtol;
+    p.wolfe = c.wolfe;
+    p.past = c.past;
+    p.max_linesearch = c.max_linesearch;
+    return p;
+}
+
+static void print_lbfgs_header(const lbfgs_config_params& c) {
+    printf("L-BFGS minimizer (bioen_b200, device resident)\n");
+    printf("\t=========================\n");
+    printf("\tlinesearch               : %d\n", c.linesearch);
+    printf("\tmax_iterations           : %d\n", c.max_iterations);
+    printf("\tdelta                    : %lf\n", c.delta);
+    printf("\tepsilon                  : %lf\n", c.epsilon);
+    printf("\tftol                     : %lf\n", c.ftol);
+    printf("\tgtol                     : %lf\n", c.gtol);
+    printf("\twolfe                    : %lf\n", c.wolfe);
+    printf("\tpast                     : %d\n", c.past);
+    printf("\tmax_linesearch           : %d\n", c.max_linesearch);
+    printf("\t=========================\n");
+}
+
+static int run_lbfgs_dev(bioen_b200_ctx* ctx, int method, double* x_dev, lbfgs_config_params config,
+                         visual_params visual, double* fmin, int info[4]) {
+    Context& C = ctx->C;
+    if (visual.verbose) print_lbfgs_header(config);
+    const auto t0 = std::chrono::steady_clock::now();
+    Lbfgs opt(C, method == BIOEN_B200_FORCES, to_params(config));
+    opt.verbose = (int)visual.verbose;
+    double fx = 0.0;
+    const int ret = opt.run(x_dev, &fx);
+    C.sync();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (fmin) *fmin = fx;
+    if (info) {
+        info[0] = opt.stats.iterations;
+        info[1] = opt.stats.evaluations;
+        info[2] = 0;
+        info[3] = 0;
+    }
+    if (visual.verbose) {
+        printf("\t%s\n", lbfgs_strerror(ret));
+        printf("\tConfig: m=%d and n=%d\n", C.M, C.N);
+        printf("\tCurrent function value  = %.6lf\n", fx);
+        printf("\tIterations              : %d\n", opt.stats.iterations);
+        printf("\tTime(s) of L-BFGS       : %.12lf\n", secs);
+        printf("\tTime(s) per iter        : %.12lf\n", secs / (opt.stats.iterations ? opt.stats.iterations : 1));
+    }
+    return ret;
+}
+
+int bioen_b200_opt_lbfgs_dev(bioen_b200_ctx* ctx, int method, double* x_dev, lbfgs_config_params config,
+                             visual_params visual, double* fmin, int info[4]) {
+    int ret = -2000;
+    guarded("bioen_b200_opt_lbfgs_dev", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ret = run_lbfgs_dev(ctx, method, x_dev, config, visual, fmin, info);
+    });
+    return ret;
+}
+
+int bioen_b200_opt_lbfgs(bioen_b200_ctx* ctx, int method, const double* x0_host, double* x_host,
+                         lbfgs_config_params config, visual_params visual, double* fmin, int info[4]) {
+    int ret = -2000;
+    guarded("bioen_b200_opt_lbfgs", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const int n = ctx->dim(method);
+        double* x = ctx->x_for(method);
+        C.h2d(x, x0_host, n);
+        const int r = run_lbfgs_dev(ctx, method, x, config, visual, fmin, info);
+        C.d2h(x_host, x, n);
+        C.sync();
+        ret = r;
+    });
+    return ret;
+}
+
+int bioen_b200_opt_gsl(bioen_b200_ctx* ctx, int method, const double* x0_host, double* x_host,
+                       gsl_config_params config, visual_params visual, double* fmin, int info[4]) {
+    int ret = -2000;
+    guarded("bioen_b200_opt_gsl", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const int n = ctx->dim(method);
+        double* x = ctx->x_for(method);
+        C.h2d(x, x0_host, n);
+        if (visual.verbose) {
+            static const char* names[] = {"conjugate_fr", "conjugate_pr", "vector_bfgs2", "vector_bfgs",
+                                          "steepest_descent"};
+            printf("\t=========================\n");
+            printf("\tGSL minimizer            : %s (bioen_b200, device resident)\n",
+                   (config.algorithm >= 0 && config.algorithm <= 4) ? names[config.algorithm] : "?");
+            printf("\ttol                      : %f\n", config.tol);
+            printf("\tstep_size                : %f\n", config.step_size);
+            printf("\tmax_iteration            : %d\n", config.max_iterations);
+            printf("\t=========================\n");
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        GslStats st;
+        double fx = 0.0;
+        const int r = gsl_minimize(C, method == BIOEN_B200_FORCES, x, config.algorithm, config.step_size, config.tol,
+                                   config.max_iterations, (int)visual.verbose, &fx, &st);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        C.d2h(x_host, x, n);
+        C.sync();
+        if (fmin) *fmin = fx;
+        if (info) {
+            info[0] = st.iterations;
+            info[1] = st.n_fdf + st.n_df;
+            info[2] = st.n_f;
+            info[3] = 0;
+        }
+        if (visual.verbose) {
+            printf("\t%s\n", bioen_gsl_error(r));
+            printf("\tConfig: m=%d and n=%d\n", C.M, C.N);
+            printf("\tCurrent function value  = %.6lf\n", fx);
+            printf("\tIterations              : %d\n", st.iterations);
+            printf("\tMinimization time [s]   : %.12lf\n", secs);
+            printf("\tTime [s] per iteration  : %.12lf\n", secs / (st.iterations ? st.iterations : 1));
+        }
+        ret = r;
+    });
+    return ret;
+}
+
+int bioen_b200_nccl_unique_id(char id[128]) {
+    return guarded("bioen_b200_nccl_unique_id", [&] { Comm::unique_id(id); });
+}
+
+int bioen_b200_comm_init(bioen_b200_ctx* ctx, const char id[128], int rank, int nranks, long long n_total) {
+    return guarded("bioen_b200_comm_init", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->comm.reset(new Comm(id, rank, nranks));
+        ctx->C.set_comm(ctx->comm.get());
+        ctx->C.N_total = n_total;
+    });
+}
+
+int bioen_b200_eval_dev(bioen_b200_ctx* ctx, int method, double* x_dev, double* grad_dev) {
+    return guarded("bioen_b200_eval_dev", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        if (method == BIOEN_B200_FORCES) C.forces_eval(x_dev, nullptr, nullptr, 0.0, grad_dev, nullptr);
+        else C.logw_eval(x_dev, nullptr, nullptr, 0.0, grad_dev, nullptr);
+    });
+}
+
+int bioen_b200_fetch(bioen_b200_ctx* ctx, double* f, double* gnorm2) {
+    return guarded("bioen_b200_fetch", [&] {
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.fetch_scalars();
+        if (f) *f = ctx->C.h_sc[SC_F];
+        if (gnorm2) *gnorm2 = ctx->C.h_sc[SC_GNORM2];
+    });
+}
+
+int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double* grad_dev, int warmup, int steps,
+                          float* ms, float* pass_ms, long long* launches) {
+    return guarded("bioen_b200_time_evals", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const bool forces = (method == BIOEN_B200_FORCES);
+        const int n = forces ? C.M : C.N;
+        const int blocks = forces ? C.vec_blocks_m : C.vec_blocks_n;
+        // direction: a copy of the start point's gradient scaled tiny, so every step evaluates a new point
+        DevBuf<double> xp, dir;
+        xp.alloc(((size_t)n + 15) & ~(size_t)15);
+        dir.alloc(((size_t)n + 15) & ~(size_t)15);
+        C.d2d(xp.p, x_dev, n);
+        if (forces) C.forces_eval(x_dev, nullptr, nullptr, 0.0, grad_dev, nullptr);
+        else C.logw_eval(x_dev, nullptr, nullptr, 0.0, grad_dev, nullptr);
+        C.fetch_scalars();
+        const double gn = std::sqrt(C.h_sc[SC_GNORM2]);
+        k_axpby<<<blocks, kVecThreads, 0, C.stream>>>(n, gn > 0 ? -1e-6 / gn : 0.0, grad_dev, 0.0, nullptr, dir.p);
+        auto one = [&](int k) {
+            if (forces) C.forces_eval(x_dev, xp.p, dir.p, (double)(k + 1), grad_dev, dir.p);
+            else C.logw_eval(x_dev, xp.p, dir.p, (double)(k + 1), grad_dev, dir.p);
+        };
+        for (int k = 0; k < warmup; ++k) one(k);
+        C.sync();
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        C.begin_pass_timing(steps * 4);
+        const long long k0 = C.kernels_launched;
+        CUDA_CHECK(cudaEventRecord(e0, C.stream));
+        for (int k = 0; k < steps; ++k) one(warmup + k);
+        CUDA_CHECK(cudaEventRecord(e1, C.stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float total = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&total, e0, e1));
+        if (ms) *ms = total;
+        if (launches) *launches = C.kernels_launched - k0;
+        const float pm = C.end_pass_timing();
+        if (pass_ms) *pass_ms = pm;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+
+int bioen_b200_generate_ytilde(bioen_b200_ctx* ctx, unsigned long long seed, long long col_offset,
+                               const double* ytrue_over_sigma_host, double inv_sigma) {
+    return guarded("bioen_b200_generate_ytilde", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        if (!C.Y) C.alloc_matrix();
+        C.h2d(C.avg.p, ytrue_over_sigma_host, C.M);
+        k_generate<<<C.num_sms * 8, 256, 0, C.stream>>>(C.Y, C.ld, C.M, C.N, seed, col_offset, C.avg.p, inv_sigma);
+        CUDA_CHECK(cudaGetLastError());
+        ++C.kernels_launched;
+        C.sync();
+    });
+}
+
+int bioen_b200_download_ytilde(bioen_b200_ctx* ctx, int row0, int nrows, long long col0, long long ncols,
+                               double* out_host) {
+    return guarded("bioen_b200_download_ytilde", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        if (!C.Y) throw std::logic_error("bioen_b200: no matrix");
+        if (row0 < 0 || nrows < 0 || row0 + nrows > C.M || col0 < 0 || ncols < 0 || col0 + ncols > C.N)
+            throw std::invalid_argument("bioen_b200: block out of range");
+        CUDA_CHECK(cudaMemcpy2DAsync(out_host, (size_t)ncols * sizeof(double), C.Y + (size_t)row0 * C.ld + col0,
+                                     (size_t)C.ld * sizeof(double), (size_t)ncols * sizeof(double), nrows,
+                                     cudaMemcpyDeviceToHost, C.stream));
+        C.sync();
+    });
+}
+
+long long bioen_b200_kernels_launched(bioen_b200_ctx* ctx) { return ctx->C.kernels_launched; }
+
+int bioen_b200_debug_read(bioen_b200_ctx* ctx, int what, double* out_host, size_t count) {
+    return guarded("bioen_b200_debug_read", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const double* src = nullptr;
+        size_t cap = 0;
+        switch (what) {
+            case 0: src = C.sc.p; cap = SC_COUNT; break;
+            case 1: src = C.w.p; cap = C.N; break;
+            case 2: src = C.avg.p; cap = C.M; break;
+            case 3: src = C.aux_n.p; cap = C.aux_n.n; break;
+            case 4: src = C.aux_n2.p; cap = C.aux_n2.n; break;
+            default: throw std::invalid_argument("bioen_b200: unknown debug buffer");
+        }
+        if (count > cap) throw std::invalid_argument("bioen_b200: debug read too long");
+        C.d2h(out_host, src, count);
+        C.sync();
+    });
+}
+
+void* bioen_b200_stream(bioen_b200_ctx* ctx) { return (void*)ctx->C.stream; }
+
+// ---------------------------------------------------------------------------------------------------
+// Part 1 -- reference-compatible symbols (host pointers in, host pointers out)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct TempProblem {
+    bioen_b200_ctx* ctx = nullptr;
+    TempProblem(int m, int n, const double* yTilde) {
+        ctx = new bioen_b200_ctx(m, n, 0);
+        if (yTilde) {
+            ctx->C.upload_matrix(yTilde, (size_t)n);
+        }
+    }
+    ~TempProblem() {
+        if (ctx) {
+            cudaStreamSynchronize(ctx->C.stream);
+            delete ctx;
+        }
+    }
+};
+}  // namespace
+
+double _get_weights(const double* g, double* w, size_t n) {
+    double s = kNaN;
+    guarded("_get_weights", [&] {
+        TempProblem P(1, (int)n, nullptr);
+        double sum = 0.0;
+        Context& C = P.ctx->C;
+        double* x = P.ctx->x_for(BIOEN_B200_LOGW);
+        C.h2d(x, g, n);
+        C.logw_weights_only(x);
+        C.d2h(w, C.w.p, n);
+        C.fetch_scalars();
+        sum = std::exp(C.h_sc[SC_GMAX]) * C.h_sc[SC_S];
+        s = sum;
+    });
+    return s;
+}
+
+double _bioen_log_posterior_logw(const double* g, const double* G, const double* yTilde, const double* YTilde,
+                                 const double* /*w*/, const double* /*gradient*/, double theta, int /*caching*/,
+                                 const double* /*yTildeT*/, double* /*tmp_n*/, double* /*tmp_m*/, int m, int n,
+                                 double /*weights_sum*/) {
+    double f = kNaN;
+    guarded("_bioen_log_posterior_logw", [&] {
+        TempProblem P(m, n, yTilde);
+        if (bioen_b200_set_logw(P.ctx, G, YTilde, theta)) throw std::runtime_error(g_last_error);
+        if (bioen_b200_eval(P.ctx, BIOEN_B200_LOGW, g, &f, nullptr)) throw std::runtime_error(g_last_error);
+    });
+    return f;
+}
+
+void _grad_bioen_log_posterior_logw(const double* g, const double* G, const double* yTilde, const double* YTilde,
+                                    const double* /*w*/, double* gradient, double theta, int /*caching*/,
+                                    const double* /*yTildeT*/, double* /*tmp_n*/, double* /*tmp_m*/, int m, int n,
+                                    double /*weights_sum*/) {
+    guarded("_grad_bioen_log_posterior_logw", [&] {
+        TempProblem P(m, n, yTilde);
+        double f;
+        if (bioen_b200_set_logw(P.ctx, G, YTilde, theta)) throw std::runtime_error(g_last_error);
+        if (bioen_b200_eval(P.ctx, BIOEN_B200_LOGW, g, &f, gradient)) throw std::runtime_error(g_last_error);
+    });
+}
+
+double _opt_lbfgs_logw(params_t p, lbfgs_config_params config, visual_params visual, int* error) {
+    double fmin = kNaN;
+    int err = -2000;
+    guarded("_opt_lbfgs_logw", [&] {
+        TempProblem P(p.m, p.n, p.yTilde);
+        int info[4];
+        if (bioen_b200_set_logw(P.ctx, p.G, p.YTilde, p.theta)) throw std::runtime_error(g_last_error);
+        err = bioen_b200_opt_lbfgs(P.ctx, BIOEN_B200_LOGW, p.g, p.result, config, visual, &fmin, info);
+        if (err == -2000) throw std::runtime_error(g_last_error);
+    });
+    if (error) *error = err;
+    return fmin;
+}
+
+double _opt_bfgs_logw(params_t p, gsl_config_params config, visual_params visual, int* error) {
+    double fmin = kNaN;
+    int err = -2000;
+    guarded("_opt_bfgs_logw", [&] {
+        TempProblem P(p.m, p.n, p.yTilde);
+        int info[4];
+        if (bioen_b200_set_logw(P.ctx, p.G, p.YTilde, p.theta)) throw std::runtime_error(g_last_error);
+        err = bioen_b200_opt_gsl(P.ctx, BIOEN_B200_LOGW, p.g, p.result, config, visual, &fmin, info);
+        if (err == -2000) throw std::runtime_error(g_last_error);
+    });
+    if (error) *error = err;
+    return fmin;
+}
+
+void _get_weights_from_forces(const double* w0, const double* yTilde, const double* forces, double* w,
+                              int /*caching*/, const double* /*yTildeT*/, double* /*tmp_n*/, size_t m, size_t n) {
+    guarded("_get_weights_from_forces", [&] {
+        TempProblem P((int)m, (int)n, yTilde);
+        std::vector<double> zeros(m, 0.0);
+        if (bioen_b200_set_forces(P.ctx, w0, zeros.data(), 0.0)) throw std::runtime_error(g_last_error);
+        if (bioen_b200_weights(P.ctx, BIOEN_B200_FORCES, forces, w, nullptr)) throw std::runtime_error(g_last_error);
+    });
+}
+
+double _bioen_log_posterior_forces(const double* w0, const double* yTilde, const double* YTilde, const double* w,
+                                   const double* /*result*/, double theta, int /*caching*/,
+                                   const double* /*yTildeT*/, double* /*tmp_n*/, double* /*tmp_m*/, int m, int n) {
+    double f = kNaN;
+    guarded("_bioen_log_posterior_forces", [&] {
+        TempProblem P(m, n, yTilde);
+        if (bioen_b200_set_forces(P.ctx, w0, YTilde, theta)) throw std::runtime_error(g_last_error);
+        if (bioen_b200_forces_from_weights(P.ctx, w, &f, nullptr)) throw std::runtime_error(g_last_error);
+    });
+    return f;
+}
+
+void _grad_bioen_log_posterior_forces(const double* w0, const double* yTilde, const double* YTilde, const double* w,
+                                      double* gradient, double theta, int /*caching*/, const double* /*yTildeT*/,
+                                      double* /*tmp_n*/, double* /*tmp_m*/, int m, int n) {
+    guarded("_grad_bioen_log_posterior_forces", [&] {
+        TempProblem P(m, n, yTilde);
+        double f;
+        if (bioen_b200_set_forces(P.ctx, w0, YTilde, theta)) throw std::runtime_error(g_last_error);
+        if (bioen_b200_forces_from_weights(P.ctx, w, &f, gradient)) throw std::runtime_error(g_last_error);
+    });
+}
+
+double _opt_lbfgs_forces(params_t p, lbfgs_config_params config, visual_params visual, int* error) {
+    double fmin = kNaN;
+    int err = -2000;
+    guarded("_opt_lbfgs_forces", [&] {
+        TempProblem P(p.m, p.n, p.yTilde);
+        int info[4];
+        if (bioen_b200_set_forces(P.ctx, p.w0, p.YTilde, p.theta)) throw std::runtime_error(g_last_error);
+        err = bioen_b200_opt_lbfgs(P.ctx, BIOEN_B200_FORCES, p.forces, p.result, config, visual, &fmin, info);
+        if (err == -2000) throw std::runtime_error(g_last_error);
+    });
+    if (error) *error = err;
+    return fmin;
+}
+
+double _opt_bfgs_forces(params_t p, gsl_config_params config, visual_params visual, int* error) {
+    double fmin = kNaN;
+    int err = -2000;
+    guarded("_opt_bfgs_forces", [&] {
+        TempProblem P(p.m, p.n, p.yTilde);
+        int info[4];
+        if (bioen_b200_set_forces(P.ctx, p.w0, p.YTilde, p.theta)) throw std::runtime_error(g_last_error);
+        err = bioen_b200_opt_gsl(P.ctx, BIOEN_B200_FORCES, p.forces, p.result, config, visual, &fmin, info);
+        if (err == -2000) throw std::runtime_error(g_last_error);
+    });
+    if (error) *error = err;
+    return fmin;
+}
+
+int _library_gsl(void) { return 1; }
+int _library_lbfgs(void) { return 1; }
+void _omp_set_num_threads(int) {}
+void _set_fast_openmp_flag(int flag) { g_fast_flag = flag; }
+int _get_fast_openmp_flag(void) { return g_fast_flag; }
+
+// message texts: the public strings of GSL 2.5 err/strerror.c and of c_bioen_error.c:25-115
+const char* bioen_gsl_error(int e) {
+    switch (e) {
+        case 0: return "success";
+        case -1: return "failure";
+        case -2: return "the iteration has not converged yet";
+        case 1: return "input domain error";
+        case 2: return "output range error";
+        case 3: return "invalid pointer";
+        case 4: return "invalid argument supplied by user";
+        case 5: return "generic failure";
+        case 6: return "factorization failed";
+        case 7: return "sanity check failed - shouldn't happen";
+        case 8: return "malloc failed";
+        case 9: return "problem with user-supplied function";
+        case 10: return "iterative process is out of control";
+        case 11: return "exceeded max number of iterations";
+        case 12: return "tried to divide by zero";
+        case 13: return "specified tolerance is invalid or theoretically unattainable";
+        case 14: return "failed to reach the specified tolerance";
+        case 15: return "underflow";
+        case 16: return "overflow";
+        case 17: return "loss of accuracy";
+        case 18: return "roundoff error";
+        case 19: return "matrix/vector sizes are not conformant";
+        case 20: return "matrix not square";
+        case 21: return "singularity or extremely bad function behavior detected";
+        case 22: return "integral or series is divergent";
+        case 23: return "the required feature is not supported by this hardware platform";
+        case 24: return "the requested feature is not (yet) implemented";
+        case 25: return "cache limit exceeded";
+        case 26: return "table limit exceeded";
+        case 27: return "iteration is not making progress towards solution";
+        case 28: return "jacobian evaluations are not improving the solution";
+        case 29: return "cannot reach the specified tolerance in F";
+        case 30: return "cannot reach the specified tolerance in X";
+        case 31: return "cannot reach the specified tolerance in gradient";
+        case 32: return "end of file";
+        default: return "unknown error code";
+    }
+}
+
+const char* lbfgs_strerror(int e) {
+    static const char* const neg[] = {
+        /* -1024 */ "Unknown error.",
+        /* -1023 */ "Logic error.",
+        /* -1022 */ "Insufficient memory.",
+        /* -1021 */ "The minimization process has been canceled.",
+        /* -1020 */ "Invalid number of variables specified.",
+        /* -1019 */ "Invalid number of variables (for SSE) specified.",
+        /* -1018 */ "The array x must be aligned to 16 (for SSE).",
+        /* -1017 */ "Invalid parameter lbfgs_parameter_t::epsilon specified.",
+        /* -1016 */ "Invalid parameter lbfgs_parameter_t::past specified.",
+        /* -1015 */ "Invalid parameter lbfgs_parameter_t::delta specified.",
+        /* -1014 */ "Invalid parameter lbfgs_parameter_t::linesearch specified.",
+        /* -1013 */ "Invalid parameter lbfgs_parameter_t::max_step specified",
+        /* -1012 */ "Invalid parameter lbfgs_parameter_t::max_step specified.",
+        /* -1011 */ "Invalid parameter lbfgs_parameter_t::ftol specified.",
+        /* -1010 */ "Invalid parameter lbfgs_parameter_t::wolfe specified.",
+        /* -1009 */ "Invalid parameter lbfgs_parameter_t::gtol specified.",
+        /* -1008 */ "Invalid parameter lbfgs_parameter_t::xtol specified.",
+        /* -1007 */ "Invalid parameter lbfgs_parameter_t::max_linesearch specified.",
+        /* -1006 */ "Invalid parameter lbfgs_parameter_t::orthantwise_c specified.",
+        /* -1005 */ "Invalid parameter lbfgs_parameter_t::orthantwise_start specified.",
+        /* -1004 */ "Invalid parameter lbfgs_parameter_t::orthantwise_end specified.",
+        /* -1003 */ "The line-search step went out of the interval of uncertainty.",
+        /* -1002 */ "A logic error occurred; alternatively, the interval of uncertainty",
+        /* -1001 */
+        "A rounding error occurred; alternatively, no line-search step satisfies the sufficient decrease and "
+        "curvature conditions.",
+        /* -1000 */ "The line-search step became smaller than lbfgs_parameter_t::min_step.",
+        /*  -999 */ "The line-search step became larger than lbfgs_parameter_t::max_step.",
+        /*  -998 */ "The line-search routine reaches the maximum number of evaluations.",
+        /*  -997 */ "The algorithm routine reaches the maximum number of iterations.",
+        /*  -996 */ "Relative width of the interval of uncertainty is at most lbfgs_parameter_t::xtol.",
+        /*  -995 */ "A logic error (negative line-search step) occurred.",
+        /*  -994 */ "The current search direction increases the objective function value.",
+    };
+    if (e == 0) return "Convergence reached.";
+    if (e == 1) return "LBFGS_STOP";
+    if (e == 2) return "The initial variables already minimize the objective function.";
+    if (e >= -1024 && e <= -994) return neg[e + 1024];
+    return "(unknown)";
+}
+
+}  // extern "C"

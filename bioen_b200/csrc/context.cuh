@@ -146,6 +146,7 @@ class Context {
 
     ~Context() {
         if (h_sc) cudaFreeHost(h_sc);
+        for (cudaEvent_t e : pass_ev) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 
@@ -165,6 +166,16 @@ class Context {
         if (ld != N) CUDA_CHECK(cudaMemsetAsync(Y, 0, (size_t)M * ld * sizeof(double), stream));
         CUDA_CHECK(cudaMemcpy2DAsync(Y, ld * sizeof(double), host, ld_host * sizeof(double), (size_t)N * sizeof(double),
                                      M, cudaMemcpyHostToDevice, stream));
+        make_tensor_map();
+    }
+    // allocate an uninitialised device matrix (filled by the on-device generator)
+    void alloc_matrix() {
+        ld = round_up(N, 16);
+        Yown.release();
+        CUDA_CHECK(cudaMalloc(&Yown.p, (size_t)M * ld * sizeof(double)));
+        Yown.n = (size_t)M * ld;
+        Y = Yown.p;
+        CUDA_CHECK(cudaMemsetAsync(Y, 0, (size_t)M * ld * sizeof(double), stream));
         make_tensor_map();
     }
     // use a matrix that already lives in HBM (row stride `ld_dev` doubles, must be even; base 16-byte aligned)
@@ -263,9 +274,41 @@ class Context {
         a.vN = vN; a.vMb = vMb; a.ab = ab.p;
         a.partial = (MODE == kRowPass) ? partialA.p : partialB.p;
         a.ld = (MODE == kRowPass) ? Mpad : Npad;
+        if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
+        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
         stream_pass_kernel<MODE, SUB><<<grid, kPassThreads, kPassSmemBytes, stream>>>(tmap, a);
+        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+        CUDA_CHECK(cudaGetLastError());
         ++passes_launched;
         ++kernels_launched;
+    }
+    // per-launch CUDA-event timing of the matrix passes (bench.py roofline): events bracket every pass kernel
+    // on this stream between begin_pass_timing() and end_pass_timing(), which returns the mean duration in ms
+    std::vector<cudaEvent_t> pass_ev;
+    size_t pass_ev_used = 0;
+    bool pass_timing = false;
+    void begin_pass_timing(int max_passes) {
+        while (pass_ev.size() < (size_t)max_passes * 2) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            pass_ev.push_back(e);
+        }
+        pass_ev_used = 0;
+        pass_timing = true;
+    }
+    float end_pass_timing() {
+        pass_timing = false;
+        sync();
+        double total = 0.0;
+        size_t cnt = 0;
+        for (size_t i = 0; i + 1 < pass_ev_used; i += 2) {
+            float t = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&t, pass_ev[i], pass_ev[i + 1]));
+            total += t;
+            ++cnt;
+        }
+        return cnt ? (float)(total / cnt) : 0.f;
     }
     // finish a row pass that produced avg (logw: tail = 3 weighted sums, forces: tail = KL)
     void finalize_rows(bool is_forces, int ntail, bool ab_with_avg) {
@@ -384,6 +427,42 @@ class Context {
         a.sc = sc.p;
         k_forces_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
         kernels_launched += 3;
+    }
+    // objective (and gradient when grad != nullptr) of the forces method for GIVEN weights already in `w`
+    // (reference semantics of _bioen_log_posterior_forces / _grad_bioen_log_posterior_forces,
+    // c_bioen_kernels_forces.c:227-340)
+    void forces_from_weights(double* grad) {
+        if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
+        {
+            ForcesLrArgs a{N, w.p, Gv.p, aux_n2.p, msum.p + M, red_partials.p, ticket.p};
+            k_forces_lr_from_w<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_pass<kRowPass, false>(w.p, nullptr);
+        finalize_rows(true, 1, false);
+        if (!grad) return;
+        launch_pass<kColPass, false>(nullptr, nullptr);
+        {
+            ForcesEArgs a{};
+            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = chunk;
+            a.w = w.p; a.lr = aux_n2.p; a.E = aux_n.p; a.theta = theta;
+            k_forces_E<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_pass<kRowPass, true>(aux_n.p, avg.p);
+        {
+            ForcesGradArgs a{};
+            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = chunk;
+            a.d = nullptr; a.grad = grad; a.sc = sc.p;
+            if (nranks > 1) {
+                k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+                ++kernels_launched;
+                comm->allreduce_sum(msum.p, M, stream);
+                a.msum = msum.p;
+            }
+            k_forces_grad<<<1, 1024, 0, stream>>>(a);
+            ++kernels_launched;
+        }
     }
     // avg = Y . v for an arbitrary N-vector v already in `w` (post-processing: yopt = y . wopt)
     void average_of_w(double* avg_out_dev) {

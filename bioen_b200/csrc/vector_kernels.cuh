@@ -361,6 +361,31 @@ __global__ void __launch_bounds__(kVecThreads) k_forces_weights(const ForcesWeig
     });
 }
 
+// forces, reference entry points that receive the WEIGHTS instead of the forces
+// (c_bioen_kernels_forces.c:246-274): lr_j = log w_j - log w0_j where both >= DBL_MIN, else 0; KL = sum w_j lr_j
+struct ForcesLrArgs {
+    int n;
+    const double* w;
+    const double* w0;
+    double* lr;
+    double* msum_tail;
+    double* partials;
+    unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_forces_lr_from_w(const ForcesLrArgs a) {
+    __shared__ double red[32];
+    double v[1] = {0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const double w = a.w[j], w0 = a.w0[j];
+        const double lr = (w >= DBL_MIN && w0 >= DBL_MIN) ? (log(w) - log(w0)) : 0.0;
+        a.lr[j] = lr;
+        v[0] = fma(lr, w, v[0]);
+    }
+    double* tail = a.msum_tail;
+    grid_sum<1>(v, a.partials, a.ticket, red, [=](const double(&t)[1]) { tail[0] = t[0]; });
+}
+
 // forces: E_j = (theta (1 + lr_j) + t_j) w_j,  t_j = column-pass sums    (c_bioen_kernels_forces.c:321-328)
 struct ForcesEArgs {
     int n;

@@ -1,0 +1,43 @@
+"""Shared helpers of the optimize API (mirror of bioen/optimize/common.py)."""
+import numpy as np
+
+from .. import _lib
+from ..problem import Problem
+
+
+def _is_matrix(a):
+    return isinstance(a, np.matrix)
+
+
+def chiSqrTerm(w, yTilde, YTilde):
+    """0.5 * || yTilde.w - YTilde ||^2 (legacy host helper, bioen/optimize/common.py:5-39)."""
+    v = np.asarray(yTilde, dtype=np.float64) @ _lib.vec(w) - _lib.vec(YTilde)
+    return 0.5 * float(v @ v)
+
+
+def getAve(w, y):
+    """Ensemble averages y.w as a flat (m,) array (legacy host helper, bioen/optimize/common.py:42-60)."""
+    return np.asarray(y, dtype=np.float64) @ _lib.vec(w)
+
+
+def device_average(w, y, problem=None):
+    """y.w computed on the GPU; `problem` is reused when it already holds `y`."""
+    if problem is not None:
+        return problem.average(w)
+    with Problem(y) as p:
+        return p.average(w)
+
+
+def print_highlighted(text, verbose=True):
+    """bioen/optimize/common.py:63-80"""
+    if verbose:
+        n = len(text)
+        print("-" * n)
+        print(text)
+        print("-" * n)
+
+
+def set_caching_heuristics(m, n):
+    """bioen/optimize/common.py:83-106: True iff m*n*8 bytes <= 8 GiB.  The value is carried in the cfg dict for
+    compatibility; the GPU kernels never need the transposed copy."""
+    return not (m * n * 8 > 8 * 2 ** 30)

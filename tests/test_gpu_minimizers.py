@@ -1,0 +1,151 @@
+"""GPU: the device-resident minimisers against the reference's end points (golden, produced by the unmodified
+reference C code + liblbfgs + GSL) and against the oracle's restatement run on identical inputs.
+
+Tolerances (north_star): same final objective to 1e-8 relative, converged weights within 1e-6 max-abs.
+"""
+import numpy as np
+import pytest
+
+from conftest import FORCES_FIXTURES, LOGW_FIXTURES, load_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+F_TOL = 1e-8
+W_TOL = 1e-6
+GSL_ALGS = ["conjugate_fr", "conjugate_pr", "bfgs2", "bfgs", "steepest_descent"]
+
+
+def _softmax(g):
+    e = np.exp(g - g.max())
+    return e / e.sum()
+
+
+def _setup(p, d):
+    if d["kind"] == "logw":
+        p.set_logw(d["G"], d["YTilde"], d["theta"])
+        return d["GInit"].ravel()
+    p.set_forces(d["w0"], d["YTilde"], d["theta"])
+    return d["forces_init"].ravel()
+
+
+@pytest.mark.parametrize("name", LOGW_FIXTURES + FORCES_FIXTURES)
+@pytest.mark.parametrize("ls", [0, 1, 2, 3])
+def test_lbfgs_matches_reference_endpoint(name, ls):
+    import bioen_b200
+    d = load_golden(name)
+    with bioen_b200.Problem(d["yTilde"]) as p:
+        x0 = _setup(p, d)
+        x, fmin, code, info = p.opt_lbfgs(x0, linesearch=ls)
+        assert code == d["lbfgs%d_code" % ls], (code, info)
+        assert rel(fmin, d["lbfgs%d_fmin" % ls]) < F_TOL
+        # fmin must be the objective at the returned point (test_find_opt_analytical_grad_logw.py:162-188)
+        assert rel(p.objective(x), fmin) < 5e-13
+        if code in (0, 1, 2):
+            if d["kind"] == "logw":
+                assert np.max(np.abs(_softmax(x) - _softmax(d["lbfgs%d_x" % ls]))) < W_TOL
+            else:
+                w, _ = p.weights(x)
+                wr, _ = p.weights(d["lbfgs%d_x" % ls])
+                assert np.max(np.abs(w - wr)) < W_TOL
+
+
+@pytest.mark.parametrize("name", ["data_16x15", "data_potra_part_2_logw_M205xN10", "data_forces_M64xN64",
+                                  "data_deer_test_forces_M808xN10"])
+@pytest.mark.parametrize("alg", GSL_ALGS)
+def test_gsl_matches_reference_endpoint(name, alg):
+    import bioen_b200
+    from bioen_b200.optimize.ext import c_bioen
+    d = load_golden(name)
+    with bioen_b200.Problem(d["yTilde"]) as p:
+        x0 = _setup(p, d)
+        x, fmin, code, info = p.opt_gsl(x0, algorithm=c_bioen.get_gsl_method(alg))
+        assert code == d["gsl_%s_code" % alg], (code, info)
+        assert rel(fmin, d["gsl_%s_fmin" % alg]) < F_TOL
+        assert rel(p.objective(x), fmin) < 5e-13
+
+
+def test_lbfgs_synthetic_vs_oracle_and_reference(oracle):
+    """SURVEY 8d synthetic problem: same stop code, evaluation count and end point as liblbfgs."""
+    import bioen_b200
+    d = load_golden("synthetic_M100xN20000")
+    P = oracle.synthetic_problem(int(d["M"]), int(d["N"]), seed=int(d["seed"]))
+    theta = d["theta"]
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        for ls in (0, 2):
+            p.set_logw(P["G"], P["YTilde"], theta)
+            x, fmin, code, info = p.opt_lbfgs(P["GInit"], linesearch=ls)
+            assert code == d["logw_lbfgs%d_code" % ls]
+            assert rel(fmin, d["logw_lbfgs%d_fmin" % ls]) < F_TOL
+            assert np.max(np.abs(_softmax(x) - _softmax(d["logw_lbfgs%d_x" % ls]))) < W_TOL
+            r = oracle.lbfgs(lambda v: oracle.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], theta), P["GInit"],
+                             linesearch=ls)
+            assert r["code"] == code and rel(fmin, r["fx"]) < F_TOL
+            assert abs(r["iterations"] - info["iterations"]) <= 2
+            p.set_forces(P["w0"], P["YTilde"], theta)
+            x, fmin, code, info = p.opt_lbfgs(P["forces_init"], linesearch=ls)
+            assert code == d["forces_lbfgs%d_code" % ls]
+            assert rel(fmin, d["forces_lbfgs%d_fmin" % ls]) < F_TOL
+        p.set_logw(P["G"], P["YTilde"], theta)
+        x, fmin, code, info = p.opt_gsl(P["GInit"])
+        assert code == d["logw_gsl_bfgs2_code"] and rel(fmin, d["logw_gsl_bfgs2_fmin"]) < F_TOL
+        p.set_forces(P["w0"], P["YTilde"], theta)
+        x, fmin, code, info = p.opt_gsl(P["forces_init"])
+        assert code == d["forces_gsl_bfgs2_code"] and rel(fmin, d["forces_gsl_bfgs2_fmin"]) < F_TOL
+
+
+def test_lbfgs_parameter_validation_codes():
+    """lbfgs.c:286-364: each invalid parameter maps to its own negative code, before any evaluation."""
+    import bioen_b200
+    d = load_golden("data_16x15")
+    with bioen_b200.Problem(d["yTilde"]) as p:
+        x0 = _setup(p, d)
+        for kw, code in ((dict(epsilon=-1.0), -1017), (dict(past=-1), -1016), (dict(delta=-1.0), -1015),
+                         (dict(ftol=-1.0), -1011), (dict(wolfe=1.5), -1010), (dict(gtol=-0.1), -1009),
+                         (dict(max_linesearch=0), -1007), (dict(linesearch=7), -1014)):
+            assert p.opt_lbfgs(x0, **kw)[2] == code, kw
+        # max_iterations reached: -997, and x / fmin of the last iterate are kept
+        x, fmin, code, info = p.opt_lbfgs(x0, max_iterations=2)
+        assert code == -997 and info["iterations"] == 2 and fmin < p.objective(x0)
+        # already minimised start point
+        xo = p.opt_lbfgs(x0, epsilon=1e-9, delta=0.0, past=0)[0]
+        assert p.opt_lbfgs(xo, epsilon=1e-3)[2] == 2
+
+
+def test_part1_drivers_and_error_convention():
+    """c_bioen mirror: success returns (x, fmin); failures raise RuntimeError with 'return code'
+    (test_error_opt_logw.py / test_error_opt_forces.py)."""
+    from bioen_b200 import optimize
+    from bioen_b200.optimize.ext import c_bioen
+    d = load_golden("data_16x15")
+    cfg = optimize.minimize.Parameters("lbfgs")
+    cfg["verbose"] = False
+    cfg["cache_ytilde_transposed"] = False
+    x, fmin = c_bioen.bioen_opt_lbfgs_logw(d["GInit"].ravel(), d["G"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    assert rel(fmin, d["lbfgs2_fmin"]) < F_TOL and x.shape == (16,)
+    cfg["params"]["delta"] = -1
+    with pytest.raises(RuntimeError, match="return code"):
+        c_bioen.bioen_opt_lbfgs_logw(d["GInit"].ravel(), d["G"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    cfg = optimize.minimize.Parameters("gsl")
+    cfg["verbose"] = False
+    cfg["cache_ytilde_transposed"] = False
+    x, fmin = c_bioen.bioen_opt_bfgs_logw(d["GInit"].ravel(), d["G"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    assert rel(fmin, d["gsl_bfgs2_fmin"]) < F_TOL
+    cfg["algorithm"] = "TEST_INVALID"
+    with pytest.raises(RuntimeError, match="return code"):
+        c_bioen.bioen_opt_bfgs_logw(d["GInit"].ravel(), d["G"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    d = load_golden("data_forces_M64xN64")
+    cfg = optimize.minimize.Parameters("lbfgs")
+    cfg["verbose"] = False
+    cfg["cache_ytilde_transposed"] = False
+    x, fmin = c_bioen.bioen_opt_lbfgs_forces(d["forces_init"].ravel(), d["w0"], d["yTilde"], d["YTilde"],
+                                             d["theta"], cfg)
+    assert rel(fmin, d["lbfgs2_fmin"]) < F_TOL and x.shape == (64,)
+    cfg["params"]["delta"] = -1
+    with pytest.raises(RuntimeError, match="return code"):
+        c_bioen.bioen_opt_lbfgs_forces(d["forces_init"].ravel(), d["w0"], d["yTilde"], d["YTilde"], d["theta"], cfg)
+    cfg = optimize.minimize.Parameters("gsl")
+    cfg["verbose"] = False
+    cfg["cache_ytilde_transposed"] = False
+    x, fmin = c_bioen.bioen_opt_bfgs_forces(d["forces_init"].ravel(), d["w0"], d["yTilde"], d["YTilde"],
+                                            d["theta"], cfg)
+    assert rel(fmin, d["gsl_bfgs2_fmin"]) < F_TOL
