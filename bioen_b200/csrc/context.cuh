@@ -260,6 +260,7 @@ class Context {
         a.n = N; a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.w0 = w0;
         a.col_partial = from_col ? partialB.p : nullptr;
         a.col_ld = Npad; a.col_L = nRT; a.col_chunk = chunk;
+        a.write_xnorm = from_col ? 0 : 1;
         a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
         k_update_lse<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
         ++kernels_launched;

@@ -8,7 +8,8 @@
 // x = xp + stp*d is formed inside the first evaluation kernel, g.d / ||g||^2 / ||x||^2 come out of the last
 // one, the (s, y) update and the two-loop recursion are 2*bound+2 fused kernels chained through the device
 // scalar file.  The *scalar* state machine of liblbfgs (line searches, stop tests, return codes) is kept on
-// the host, bit for bit in the same order of tests, and costs one 512-byte read-back per trial point.
+// the host, bit for bit in the same order of tests, and costs one 512-byte read-back per trial point (plus one
+// per iteration for the new direction's slope g.d).
 // With N sharded across GPUs the vector kernels see the local slice and the raw dot products are
 // all-reduced in-stream (forces: the M-dimensional state is replicated, nothing to reduce).
 #pragma once
@@ -260,7 +261,7 @@ class Lbfgs {
             end = (end + 1) % m;
             two_loop(bound, end, m);
             step = 1.0;
-            dginit_known = false;  // sc[SC_DGINIT] is read together with the first trial of the next search
+            dginit_known = false;  // sc[SC_DGINIT] is read at the start of the next line search
         }
         *fx_out = fx;
         return ret;
@@ -324,14 +325,16 @@ class Lbfgs {
         if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
         if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
         const double finit = f;
+        if (!dginit_known) {
+            // g.d of the new direction was left in the scalar file by the last two-loop kernel
+            C.fetch_scalars();
+            dginit = h[SC_DGINIT];
+            dginit_known = true;
+            if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+        }
         for (;;) {
             eval(xp, d, stp, d);
             C.fetch_scalars();
-            if (!dginit_known) {
-                dginit = h[SC_DGINIT];
-                dginit_known = true;
-                if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
-            }
             const double dgtest = prm.ftol * dginit;
             f = h[SC_F];
             ++count;
@@ -363,6 +366,12 @@ class Lbfgs {
         if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
         if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
         const double finit = f;
+        if (!dginit_known) {
+            C.fetch_scalars();
+            dginit = h[SC_DGINIT];
+            dginit_known = true;
+            if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+        }
         double width = prm.max_step - prm.min_step, prev_width = 2.0 * width;
         double stx = 0., sty = 0., fx = finit, fy = finit, dgx = dginit, dgy = dginit;
         double stmin, stmax;
@@ -376,13 +385,6 @@ class Lbfgs {
                 stp = stx;
             eval(xp, d, stp, d);
             C.fetch_scalars();
-            if (!dginit_known) {
-                // first trial of this search: only stx = sty = 0 so far, fill in the slope at 0
-                dginit = h[SC_DGINIT];
-                dginit_known = true;
-                if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
-                dgx = dgy = dginit;
-            }
             const double dgtest = prm.ftol * dginit;
             f = h[SC_F];
             double dg = h[SC_DG];

@@ -92,6 +92,7 @@ struct LseArgs {
     const double* col_partial;  // nullptr: x already holds the values
     long long col_ld;
     long long col_L, col_chunk;
+    int write_xnorm;     // 1: sc[SC_XNORM2] = ||x||^2 (logw: x are the variables; forces: x_j is derived, keep ||f||^2)
     double* partials;    // gridDim.x * 3
     unsigned int* ticket;
     double* sc;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kVecThreads) k_update_lse(const LseArgs a) {
         if (threadIdx.x == 0) {
             a.sc[SC_LSE_MAX] = m;
             a.sc[SC_LSE_SUM] = s;
-            a.sc[SC_XNORM2] = xn;
+            if (a.write_xnorm) a.sc[SC_XNORM2] = xn;
             *a.ticket = 0;
         }
     }

@@ -118,8 +118,11 @@ def _run_scipy(cfg, f, fprime, x0, label):
     p = cfg["params"]
     if alg in ("lbfgs", "fmin_l_bfgs_b"):
         common.print_highlighted("method L-BFGS", cfg["verbose"])
-        return sopt.fmin_l_bfgs_b(f, x0, fprime=fprime, epsilon=p["epsilon"], pgtol=p["pgtol"],
-                                  maxiter=p["max_iterations"], disp=cfg["verbose"])
+        kw = dict(fprime=fprime, epsilon=p["epsilon"], pgtol=p["pgtol"], maxiter=p["max_iterations"])
+        try:
+            return sopt.fmin_l_bfgs_b(f, x0, disp=cfg["verbose"], **kw)      # as the reference calls it
+        except TypeError:                                                    # SciPy >= 1.18 dropped `disp`
+            return sopt.fmin_l_bfgs_b(f, x0, **kw)
     if alg in ("bfgs", "fmin_bfgs"):
         common.print_highlighted("method BFGS", cfg["verbose"])
         return sopt.fmin_bfgs(f, x0, fprime=fprime, epsilon=p["epsilon"], gtol=p["gtol"],

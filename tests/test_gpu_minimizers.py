@@ -28,40 +28,70 @@ def _setup(p, d):
     return d["forces_init"].ravel()
 
 
+def _bound(d, key):
+    """1e-8, widened to 30x the reference's OWN end-point noise for this problem/minimiser where that is larger
+    (|fmin - fmin_alt| between its reproducible and its fast OpenMP mode, stored by make_golden.py): long,
+    chaotic trajectories (steepest descent hitting max_iterations, Fletcher-Reeves on ill-conditioned data) do
+    not reproduce to 1e-8 between two runs of the reference itself."""
+    noise = abs(d[key + "_fmin_alt"] - d[key + "_fmin"]) / abs(d[key + "_fmin"])
+    return max(F_TOL, 30.0 * noise) if np.isfinite(noise) else None
+
+
 @pytest.mark.parametrize("name", LOGW_FIXTURES + FORCES_FIXTURES)
 @pytest.mark.parametrize("ls", [0, 1, 2, 3])
 def test_lbfgs_matches_reference_endpoint(name, ls):
     import bioen_b200
     d = load_golden(name)
+    key = "lbfgs%d" % ls
     with bioen_b200.Problem(d["yTilde"]) as p:
         x0 = _setup(p, d)
         x, fmin, code, info = p.opt_lbfgs(x0, linesearch=ls)
-        assert code == d["lbfgs%d_code" % ls], (code, info)
-        assert rel(fmin, d["lbfgs%d_fmin" % ls]) < F_TOL
-        # fmin must be the objective at the returned point (test_find_opt_analytical_grad_logw.py:162-188)
-        assert rel(p.objective(x), fmin) < 5e-13
+        assert code == d[key + "_code"], (code, info)
+        assert rel(fmin, d[key + "_fmin"]) < _bound(d, key)
         if code in (0, 1, 2):
+            # fmin must be the objective at the returned point (test_find_opt_analytical_grad_logw.py:162-188);
+            # after a failed line search liblbfgs returns the reverted x with the last trial's f (lbfgs.c:475-481)
+            assert rel(p.objective(x), fmin) < 5e-13
             if d["kind"] == "logw":
-                assert np.max(np.abs(_softmax(x) - _softmax(d["lbfgs%d_x" % ls]))) < W_TOL
+                assert np.max(np.abs(_softmax(x) - _softmax(d[key + "_x"]))) < W_TOL
             else:
                 w, _ = p.weights(x)
-                wr, _ = p.weights(d["lbfgs%d_x" % ls])
+                wr, _ = p.weights(d[key + "_x"])
                 assert np.max(np.abs(w - wr)) < W_TOL
 
 
-@pytest.mark.parametrize("name", ["data_16x15", "data_potra_part_2_logw_M205xN10", "data_forces_M64xN64",
+@pytest.mark.parametrize("name", ["data_16x15", "data_deer_test_logw_M808xN10", "data_potra_part_2_logw_M205xN10",
+                                  "data_potra_part_1_logw_M808xN80", "data_forces_M64xN64",
                                   "data_deer_test_forces_M808xN10"])
 @pytest.mark.parametrize("alg", GSL_ALGS)
 def test_gsl_matches_reference_endpoint(name, alg):
     import bioen_b200
     from bioen_b200.optimize.ext import c_bioen
     d = load_golden(name)
+    key = "gsl_" + alg
     with bioen_b200.Problem(d["yTilde"]) as p:
         x0 = _setup(p, d)
         x, fmin, code, info = p.opt_gsl(x0, algorithm=c_bioen.get_gsl_method(alg))
-        assert code == d["gsl_%s_code" % alg], (code, info)
-        assert rel(fmin, d["gsl_%s_fmin" % alg]) < F_TOL
+        assert code == d[key + "_code"], (code, info)
+        assert rel(fmin, d[key + "_fmin"]) < _bound(d, key)
         assert rel(p.objective(x), fmin) < 5e-13
+
+
+def test_gsl_chaotic_fixture_stays_within_reference_tolerance():
+    """data_potra_part_2_logw_M808xN10 (808 x 100; excluded from the reference's own test list): |grad|_inf
+    jumps by 4 orders of magnitude between consecutive bfgs2 iterations near the end, the reference's two
+    OpenMP modes end with different GSL codes (conjugate_fr: 0 vs 27) and its vector_bfgs end point is NaN.
+    Checked at the reference's own 10 % bar only."""
+    import bioen_b200
+    from bioen_b200.optimize.ext import c_bioen
+    d = load_golden("data_potra_part_2_logw_M808xN10")
+    with bioen_b200.Problem(d["yTilde"]) as p:
+        x0 = _setup(p, d)
+        for alg in ("conjugate_pr", "bfgs2"):
+            x, fmin, code, info = p.opt_gsl(x0, algorithm=c_bioen.get_gsl_method(alg))
+            assert code in (0, -2, 27)
+            assert rel(fmin, d["gsl_%s_fmin" % alg]) < 1e-6
+            assert rel(fmin, d["ref_scalar"]) < 1e-1
 
 
 def test_lbfgs_synthetic_vs_oracle_and_reference(oracle):
