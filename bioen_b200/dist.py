@@ -1,0 +1,130 @@
+"""Multi-GPU plumbing: the structure axis N is sharded over the ranks of a torch.distributed job (one process
+per GPU).  torch.distributed is used ONLY to bootstrap (broadcast the NCCL unique id, scatter/gather host
+vectors); the per-evaluation collectives are issued by libbioen_b200.so itself on its compute stream
+(csrc/comm.cuh): one all-reduce of M+3 doubles per log-weights evaluation, 1-2 doubles per L-BFGS dot product.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .problem import FORCES, LOGW, Problem
+
+
+def shard_bounds(n_total, rank, world):
+    """Contiguous column range [lo, hi) of `rank`; the remainder is spread over the first ranks."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_total, world):
+    return [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
+
+
+def broadcast_bytes(payload, nbytes, src=0, group=None, device=None):
+    """Broadcast a fixed-size byte string from `src` through torch.distributed (any backend)."""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if dist.get_rank(group) == src:
+        buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(buf, src, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def allgather_vector(local, n_total, group=None, device=None):
+    """Concatenate the rank-local slices of an N-vector (host NumPy in, host NumPy out)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_total, world)
+    mx = max(sizes)
+    pad = torch.zeros(mx, dtype=torch.float64, device=device)
+    pad[:local.size] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(pad.device)
+    out = [torch.zeros(mx, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
+
+
+def connect(problem, n_total, group=None, device=None):
+    """Create the library's NCCL communicator for `problem` (this rank's column block)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    raw = b"\0" * 128
+    if rank == 0:
+        cbuf = ctypes.create_string_buffer(128)
+        _lib.check(_lib.load().bioen_b200_nccl_unique_id(cbuf), "nccl_unique_id")
+        raw = cbuf.raw
+    uid = broadcast_bytes(raw, 128, 0, group, device)
+    problem.comm_init(uid, rank, world, n_total)
+    return problem
+
+
+class ShardedProblem:
+    """A BioEn problem whose N columns are spread over the ranks of the default process group.
+
+    Every rank passes the FULL host arrays (or its own slice with `presliced=True`); N-vectors returned by
+    the methods are full-length (gathered), so the object can be used like `Problem` on every rank."""
+
+    def __init__(self, yTilde, device, group=None, presliced=False, n_total=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.tdev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else None
+        yT = np.asarray(yTilde, dtype=np.float64)
+        self.n_total = int(n_total if presliced else yT.shape[1])
+        self.lo, self.hi = shard_bounds(self.n_total, self.rank, self.world)
+        local = yT if presliced else np.ascontiguousarray(yT[:, self.lo:self.hi])
+        self.m = local.shape[0]
+        self.p = Problem(local, device=device)
+        if self.world > 1:
+            connect(self.p, self.n_total, group, self.tdev)
+
+    def _slice(self, v):
+        v = _lib.vec(v)
+        return v[self.lo:self.hi] if v.size == self.n_total else v
+
+    def _gather(self, v):
+        return allgather_vector(v, self.n_total, self.group, self.tdev) if self.world > 1 else v
+
+    def set_logw(self, G, YTilde, theta):
+        self.p.set_logw(self._slice(G), YTilde, theta)
+
+    def set_forces(self, w0, YTilde, theta):
+        self.p.set_forces(self._slice(w0), YTilde, theta)
+
+    def objective_and_gradient(self, x):
+        if self.p.method == LOGW:
+            f, g = self.p.objective_and_gradient(self._slice(x))
+            return f, self._gather(g)
+        return self.p.objective_and_gradient(x)
+
+    def objective(self, x):
+        return self.p.objective(self._slice(x) if self.p.method == LOGW else x)
+
+    def weights(self, x):
+        w, s = self.p.weights(self._slice(x) if self.p.method == LOGW else x)
+        return self._gather(w), s
+
+    def opt_lbfgs(self, x0, **cfg):
+        if self.p.method == LOGW:
+            x, fmin, code, info = self.p.opt_lbfgs(self._slice(x0), **cfg)
+            return self._gather(x), fmin, code, info
+        return self.p.opt_lbfgs(x0, **cfg)
+
+    def opt_gsl(self, x0, **cfg):
+        if self.p.method == LOGW:
+            x, fmin, code, info = self.p.opt_gsl(self._slice(x0), **cfg)
+            return self._gather(x), fmin, code, info
+        return self.p.opt_gsl(x0, **cfg)
+
+    def close(self):
+        self.p.close()
+
+
+__all__ = ["shard_bounds", "shard_sizes", "broadcast_bytes", "allgather_vector", "connect", "ShardedProblem",
+           "LOGW", "FORCES"]

@@ -1,0 +1,73 @@
+"""Run under torchrun on >= 2 GPUs: the N-sharded path (NCCL inside libbioen_b200.so) against the oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/mgpu_check.py
+Exits non-zero on any mismatch.  tests/test_gpu_multi.py launches it when the box has >= 2 GPUs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bioen_b200 import dist as D  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+rel = lambda a, b: abs(a - b) / max(abs(b), 1e-300)
+gerr = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for (M, N, theta) in ((37, 5001, 1.0), (100, 20000, 10.0), (300, 1000 * world + 3, 3.0)):
+        P = O.synthetic_problem(M, N, seed=12345)
+        rng = np.random.default_rng(3)
+        G = 0.1 * rng.standard_normal(N)
+        g1 = G + 0.1 * rng.standard_normal(N)
+        w0 = rng.random(N) + 0.1
+        w0 /= w0.sum()
+        f1 = 1e-3 * rng.standard_normal(M)
+        sp = D.ShardedProblem(P["yTilde"], device=local)
+        # log-weights evaluation + weights
+        sp.set_logw(G, P["YTilde"], theta)
+        f, g = sp.objective_and_gradient(g1)
+        fo, go = O.logw_fg(g1, G, P["yTilde"], P["YTilde"], theta)
+        assert rel(f, fo) < 1e-11 and gerr(g, go) < 1e-11, ("logw eval", M, N, rel(f, fo), gerr(g, go))
+        assert rel(sp.objective(g1), fo) < 1e-11
+        w, s = sp.weights(g1)
+        wo, so = O.logw_weights(g1)
+        assert np.max(np.abs(w - wo)) < 1e-15 and rel(s, so) < 1e-13
+        # forces evaluation (replicated M-vector state)
+        sp.set_forces(w0, P["YTilde"], theta)
+        f, g = sp.objective_and_gradient(f1)
+        fo, go = O.forces_fg(f1, w0, P["yTilde"], P["YTilde"], theta)
+        assert rel(f, fo) < 1e-11 and gerr(g, go) < 1e-11, ("forces eval", M, N, rel(f, fo), gerr(g, go))
+        # minimisers: sharded L-BFGS / GSL follow the single-process oracle
+        sp.set_logw(P["G"], P["YTilde"], theta)
+        for ls in (0, 2):
+            x, fmin, code, info = sp.opt_lbfgs(P["GInit"], linesearch=ls)
+            r = O.lbfgs(lambda v: O.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], theta), P["GInit"], linesearch=ls)
+            assert code == r["code"], ("lbfgs code", M, N, ls, code, r["code"])
+            tol = 1e-8 if r["iterations"] < 150 else 1e-4
+            assert rel(fmin, r["fx"]) < tol, ("lbfgs fmin", M, N, ls, fmin, r["fx"], info, r["iterations"])
+        x, fmin, code, info = sp.opt_gsl(P["GInit"])
+        r = O.gsl_minimize(lambda v: O.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], theta), P["GInit"])
+        assert code == r["code"] and rel(fmin, r["fx"]) < 1e-7, ("gsl", M, N, code, r["code"], fmin, r["fx"])
+        sp.set_forces(P["w0"], P["YTilde"], theta)
+        x, fmin, code, info = sp.opt_lbfgs(P["forces_init"])
+        r = O.lbfgs(lambda v: O.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], theta), P["forces_init"])
+        assert code == r["code"] and rel(fmin, r["fx"]) < 1e-7, ("forces lbfgs", M, N, code, r["code"], fmin, r["fx"])
+        sp.close()
+        if rank == 0:
+            print("mgpu_check ok: M=%d N=%d world=%d" % (M, N, world), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

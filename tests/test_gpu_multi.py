@@ -1,0 +1,21 @@
+"""GPU, >= 2 devices: launches tests/mgpu_check.py under torchrun (N-sharded path with NCCL inside the library)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_two_ranks_match_oracle():
+    import bioen_b200
+    n = bioen_b200.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("mgpu_check ok") == 3
