@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-cols", type=int, default=200000, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimum", action="store_true")
+    ap.add_argument("--unfused-forces", action="store_true", help="forces: four tile passes instead of two fused")
     return ap.parse_args()
 
 
@@ -244,6 +245,8 @@ def run_b200(args):
     if method == LOGW:
         prob.set_logw(np.zeros(N), YT, THETA)
     else:
+        if args.unfused_forces:
+            prob.set_option(1, 0)
         prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
 
     # start point: non-uniform weights (SURVEY 8d parity point); replicated vector for forces

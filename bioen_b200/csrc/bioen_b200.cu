@@ -194,6 +194,15 @@ int bioen_b200_set_forces_dev(bioen_b200_ctx* ctx, const double* w0_dev, const d
     });
 }
 
+int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
+    return guarded("bioen_b200_set_option", [&] {
+        switch (option) {
+            case BIOEN_B200_OPT_FUSED_FORCES: ctx->C.allow_fused = value != 0; break;
+            default: throw std::invalid_argument("bioen_b200: unknown option");
+        }
+    });
+}
+
 int bioen_b200_set_theta(bioen_b200_ctx* ctx, double theta) {
     ctx->C.set_theta(theta);
     return 0;

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "comm.cuh"
+#include "fused_pass.cuh"
 #include "stream_pass.cuh"
 #include "vector_kernels.cuh"
 
@@ -87,6 +88,14 @@ class Context {
     DevBuf<double> partialA, partialB, ab, avg, msum, Yobs, w, aux_n, aux_n2, Gv, sc, red_partials, lse_all;
     DevBuf<unsigned int> ticket;
     double* h_sc = nullptr;  // pinned
+
+    // structure-major copy + geometry of the fused two-pass forces kernels (fused_pass.cuh)
+    DevBuf<double> Yt, fpart, flse;
+    long long ldt = 0, f_nslab = 0, f_chunk = 0;
+    int f_C = 0, f_stages = 0, f_grid = 0, f_KI = 0, f_smem = 0, f_T = 1, f_rows = 0, f_rows_per_cta = 1;
+    bool f_team = false;
+    bool fused_ready = false;
+    bool allow_fused = true;   // bioen_b200_set_option: 0 forces the four-pass tile kernels
     double theta = 0.0;
     bool have_logw = false, have_forces = false;
     long long passes_launched = 0, kernels_launched = 0;
@@ -201,6 +210,8 @@ class Context {
             snprintf(buf, sizeof buf, "bioen_b200: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
             throw CudaError(buf);
         }
+        fused_ready = false;   // the structure-major copy (if any) belongs to the previous matrix
+        Yt.release();
         // a matrix that fits in L2 with room to spare is kept there between the two passes
         evict_first = ((double)M * (double)ld * 8.0 > 80.0e6) ? 1 : 0;
     }
@@ -250,6 +261,176 @@ class Context {
         aux_n.alloc(Npad);   // x_j, later E_j (zero padded: it feeds the row pass)
         aux_n2.alloc(Npad);  // lr_j
         have_forces = true;
+        if (allow_fused && Y && !fused_ready) prepare_fused();
+    }
+
+    // ---- fused two-pass forces path ------------------------------------------------------------------------
+    bool fused_eligible() const {
+        const long long l = (M + 1LL) & ~1LL;
+        return M >= kFMinM && l <= kFMaxLdt;
+    }
+    void prepare_fused() {
+        if (!fused_eligible()) return;
+        ldt = (M + 1LL) & ~1LL;
+        Yt.release();
+        CUDA_CHECK(cudaMalloc(&Yt.p, (size_t)N * ldt * sizeof(double)));
+        Yt.n = (size_t)N * ldt;
+        {
+            dim3 grid((unsigned)((N + 31) / 32), (unsigned)((ldt + 31) / 32));
+            k_transpose<<<grid, 256, 0, stream>>>(Y, ld, M, N, Yt.p, ldt);
+            CUDA_CHECK(cudaGetLastError());
+            ++kernels_launched;
+        }
+        const long long row_bytes = ldt * 8;
+        const long long smem_max = 232448 - 128;   // 227 KB opt-in limit minus our alignment slack
+        f_team = false;
+        if (ldt <= kTMaxLdt) {
+            // team variant: T warps per structure, 8/T independent teams per CTA
+            f_T = ldt <= 1024 ? 1 : ldt <= 2048 ? 2 : 4;
+            const int teams = kTWarps / f_T;
+            const long long need = (ldt + 64LL * f_T - 1) / (64LL * f_T);
+            f_KI = need <= 4 ? 4 : need <= 8 ? 8 : 16;
+            f_C = (int)std::max(1LL, std::min((long long)kFCMax, 8192LL / row_bytes));
+            const long long stage_bytes = ((long long)f_C * row_bytes + 127) & ~127LL;
+            const long long fixed = 2 * row_bytes + 2 * kTMaxRing * 8 + 2LL * kTWarps * 8 + 256;
+            const long long st = std::min((long long)kTMaxRing / teams, (smem_max - fixed) / (teams * stage_bytes));
+            if (st >= 2) {
+                f_team = true;
+                f_stages = (int)st;
+                f_rows_per_cta = teams;
+                f_smem = (int)(teams * st * stage_bytes + fixed) + 128;
+            }
+        }
+        if (!f_team) {
+            f_C = (int)std::max(1LL, std::min((long long)kFCMax, (long long)kFSlabTarget / row_bytes));
+            const long long stage_bytes = ((long long)f_C * row_bytes + 127) & ~127LL;
+            f_stages = (int)std::max(2LL, std::min((long long)kFMaxStages, (long long)kFSmemBudget / stage_bytes));
+            const int need = (int)((ldt + 511) / 512);
+            f_KI = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
+            f_rows_per_cta = 1;
+            f_smem = (int)(f_stages * stage_bytes) + 2 * kFMaxStages * 8 + 2 * (kFConsumers / 32) * kFCMax * 8 + 128;
+        }
+        f_nslab = ((long long)N + f_C - 1) / f_C;
+        f_grid = (int)std::min<long long>(num_sms, f_nslab);
+        f_chunk = (f_nslab + f_grid - 1) / f_grid;
+        f_grid = (int)((f_nslab + f_chunk - 1) / f_chunk);
+        f_rows = f_grid * f_rows_per_cta;
+        fpart.alloc((size_t)f_rows * Mpad);
+        flse.alloc((size_t)2 * f_rows);
+        set_fused_attr();
+        fused_ready = true;
+    }
+    template <int KI>
+    void set_fused_attr_ki() {
+        CUDA_CHECK(cudaFuncSetAttribute(fused_struct_pass<KI, kFusedSoftmaxAvg>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(fused_struct_pass<KI, kFusedGradient>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
+    }
+    template <int KI, int T>
+    void set_team_attr() {
+        CUDA_CHECK(cudaFuncSetAttribute(fused_team_pass<KI, T, kFusedSoftmaxAvg>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(fused_team_pass<KI, T, kFusedGradient>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
+    }
+    void set_fused_attr() {
+        if (f_team) {
+            if (f_T == 1 && f_KI == 4) set_team_attr<4, 1>();
+            else if (f_T == 1 && f_KI == 8) set_team_attr<8, 1>();
+            else if (f_T == 1) set_team_attr<16, 1>();
+            else if (f_T == 2) set_team_attr<16, 2>();
+            else set_team_attr<16, 4>();
+            return;
+        }
+        switch (f_KI) {
+            case 1: set_fused_attr_ki<1>(); break;
+            case 2: set_fused_attr_ki<2>(); break;
+            case 4: set_fused_attr_ki<4>(); break;
+            case 8: set_fused_attr_ki<8>(); break;
+            default: set_fused_attr_ki<16>(); break;
+        }
+    }
+    template <int KIND>
+    void launch_fused(const double* bvec, const double* s0, const double* s1, double* xout) {
+        const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
+        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+        if (f_team) {
+            TeamArgs a{};
+            a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;
+            a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta; a.xout = xout;
+            a.part = fpart.p; a.ldp = Mpad; a.lse = flse.p; a.evict_first = evict_first;
+            if (f_T == 1 && f_KI == 4) fused_team_pass<4, 1, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
+            else if (f_T == 1 && f_KI == 8) fused_team_pass<8, 1, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
+            else if (f_T == 1) fused_team_pass<16, 1, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
+            else if (f_T == 2) fused_team_pass<16, 2, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
+            else fused_team_pass<16, 4, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
+        } else {
+            FusedArgs a{};
+            a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;
+            a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta; a.xout = xout;
+            a.part = fpart.p; a.ldp = Mpad; a.lse = flse.p;
+            switch (f_KI) {
+                case 1: fused_struct_pass<1, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
+                case 2: fused_struct_pass<2, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
+                case 4: fused_struct_pass<4, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
+                case 8: fused_struct_pass<8, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
+                default: fused_struct_pass<16, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
+            }
+        }
+        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+        CUDA_CHECK(cudaGetLastError());
+        ++passes_launched;
+        ++kernels_launched;
+    }
+    void merge_fused_rows(bool scaled, int ntail) {
+        k_fused_merge_rows<<<(M + 31) / 32, 256, 0, stream>>>(
+            M, f_rows, fpart.p, Mpad, scaled ? flse.p : nullptr, lse_pairs(), nranks, msum.p);
+        ++kernels_launched;
+        if (nranks > 1) comm->allreduce_sum(msum.p, M + ntail, stream);
+    }
+    void forces_eval_fused(double* x, const double* xp, const double* d, double stp, double* grad,
+                           const double* ddir) {
+        {
+            ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p};
+            k_forces_update<<<1, 1024, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        launch_fused<kFusedSoftmaxAvg>(nullptr, Gv.p, nullptr, aux_n.p);   // x_j, CTA-local softmax, avg partials
+        k_fused_lse_merge<<<1, 256, 0, stream>>>(f_rows, flse.p, sc.p + SC_LSE_MAX);
+        ++kernels_launched;
+        gather_lse();
+        {
+            ForcesWeightsArgs a{};
+            a.n = N; a.x = aux_n.p; a.w0 = Gv.p; a.w = w.p; a.lr = aux_n2.p; a.lse_pairs = lse_pairs();
+            a.nranks = nranks; a.msum_tail = msum.p + M; a.partials = red_partials.p; a.ticket = ticket.p;
+            a.sc = sc.p;
+            k_forces_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+        merge_fused_rows(true, 1);
+        finalize_rows_from_msum(true, false);
+        if (!grad) return;
+        launch_fused<kFusedGradient>(avg.p, w.p, aux_n2.p, nullptr);       // t_j, E_j, grad partials
+        merge_fused_rows(false, 0);
+        {
+            ForcesGradArgs a{};
+            a.m = M; a.partial = nullptr; a.ld = Mpad; a.L = nCB; a.chunk = chunk; a.msum = msum.p;
+            a.d = ddir; a.grad = grad; a.sc = sc.p;
+            k_forces_grad<<<1, 1024, 0, stream>>>(a);
+            ++kernels_launched;
+        }
+    }
+    // k_finalize_rows on an msum that is already slot-, CTA- and rank-reduced
+    void finalize_rows_from_msum(bool is_forces, bool ab_with_avg) {
+        FinalizeArgs a{};
+        a.m = M; a.partial = nullptr; a.ld = Mpad; a.L = nCB; a.chunk = chunk; a.msum = msum.p;
+        a.Y = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.ab_with_avg = ab_with_avg ? 1 : 0;
+        a.is_forces = is_forces ? 1 : 0; a.theta = theta;
+        a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+        a.tail = msum.p + M;
+        k_finalize_rows<<<(M + kVecThreads - 1) / kVecThreads, kVecThreads, 0, stream>>>(a);
+        ++kernels_launched;
     }
 
     // ---- kernel launch helpers ---------------------------------------------------------------------
@@ -373,6 +554,10 @@ class Context {
     // on every rank.  grad == nullptr -> objective only (two passes over Y).
     void forces_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
+        if (fused_ready && allow_fused) {
+            forces_eval_fused(x, xp, d, stp, grad, ddir);
+            return;
+        }
         {
             ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p};
             k_forces_update<<<1, 1024, 0, stream>>>(a);

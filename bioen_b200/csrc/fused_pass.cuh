@@ -1,0 +1,506 @@
+// fused_pass.cuh -- the forces method in TWO passes over the matrix (the algorithmic minimum)
+// instead of the reference's five (c_bioen_kernels_forces.c:43-76) or the four of the unfused tile kernels.
+//
+// The forces evaluation alternates a reduction over the observables i (per structure j) with a reduction over
+// the structures j (per observable i):
+//
+//   F1   x_j = sum_i f_i y_ij  ->  e_j = w0_j exp(x_j - max)  ->  avg_i ~ sum_j y_ij e_j       kernels_forces.c:128-171, 93-109
+//   F2   t_j = sum_i r_i y_ij  ->  E_j = (theta (1 + lr_j) + t_j) w_j  ->  grad_i = sum_j (y_ij - avg_i) E_j      :298-338
+//
+// In the reference's observable-major layout (M x N) the first reduction needs a whole COLUMN before the second
+// can start, and a column block of useful width does not fit in shared memory.  So the forces method keeps a
+// second, structure-major copy  Yt[j][i]  (N x ldt; the reference's own `yTildeT` cache, c_bioen.pyx:391-393,
+// made once on the device by k_transpose): now all M observables of a structure are contiguous, a "slab" of C
+// whole structures (~48 KB) is ONE 1-D bulk copy (cp.async.bulk, completion on an mbarrier), and both reductions
+// run out of the same shared-memory slab:
+//
+//   phase A   every thread owns a fixed set of observable pairs i (coefficients a_i, b_i live in registers for
+//             the whole kernel) and forms its part of the C dot products; warp shuffle + one named barrier give
+//             every warp the C column sums (lane c holds structure c)
+//   transform lane c turns its sum into the per-structure factor v_c (online softmax with a running max for
+//             F1, the E_j formula for F2); the per-structure inputs were prefetched before the slab arrived
+//   phase B   acc_i += (y_ci - b_i) v_c  for the thread's own observables; accumulators stay in registers over
+//             all slabs of the CTA and are written once, to the CTA's own row of `part`
+//
+// Persistent: one CTA per SM, producer warp + 8 consumer warps, ring of 3-8 slabs, equal contiguous chunks of
+// slabs per CTA.  All reductions are fixed-order: bit-reproducible run to run.  HBM traffic: N*ldt*8 bytes per
+// kernel, read exactly once.
+#pragma once
+#include <float.h>
+
+#include "common.cuh"
+
+namespace bioen {
+
+constexpr int kFConsumers = 256;            // 8 consumer warps
+constexpr int kFThreads = kFConsumers + 32;  // + producer warp
+constexpr int kFCMax = 8;                   // structures per slab (<= 32: one lane per structure)
+constexpr int kFMaxStages = 8;
+constexpr int kFSlabTarget = 48 * 1024;
+constexpr int kFSmemBudget = 200 * 1024;
+constexpr int kFMinM = 256;                 // below this the thread mapping is mostly idle: use the tile kernels
+constexpr int kFMaxLdt = 8192;              // 16 pair-slots x 512 observables
+
+enum FusedKind { kFusedSoftmaxAvg = 0, kFusedGradient = 1 };
+
+struct FusedArgs {
+    const double* Yt;      // N x ldt, structure-major, ldt even, pad column zero
+    long long ldt;
+    int M, N;
+    int C;                 // structures per slab
+    int stages;
+    long long nslab, chunk;
+    const double* ab;      // interleaved {a_i, *}: a_i = f_i (F1) or r_i (F2); zero padded
+    const double* b;       // F2: avg_i (zero padded); F1: unused
+    const double* s0;      // per structure: w0_j (F1) or w_j (F2)
+    const double* s1;      // F2: lr_j
+    double theta;
+    double* xout;          // F1: x_j
+    double* part;          // [gridDim.x][ldp] accumulators
+    long long ldp;
+    double* lse;           // F1: [gridDim.x][2] = running (max, sum) of the CTA
+};
+
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory"); }
+
+template <int KI, int KIND>
+__global__ void __launch_bounds__(kFThreads, 1) fused_struct_pass(const FusedArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                                           ~static_cast<uintptr_t>(127));
+    const int slab_bytes = a.C * (int)a.ldt * 8;
+    const int stage_bytes = (slab_bytes + 127) & ~127;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+    uint64_t* empty = full + kFMaxStages;
+    double* red = reinterpret_cast<double*>(empty + kFMaxStages);  // [2][8 warps][kFCMax]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long s_begin = (long long)blockIdx.x * a.chunk;
+    const long long s_end = (s_begin + a.chunk < a.nslab) ? s_begin + a.chunk : a.nslab;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFConsumers / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kFConsumers / 32) {
+        // ------------------------------------------------------------------ producer: one bulk copy per slab
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 1;
+            for (long long s = s_begin; s < s_end; ++s) {
+                const long long j0 = s * a.C;
+                const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
+                const uint32_t bytes = (uint32_t)Cs * (uint32_t)a.ldt * 8u;
+                mbar_wait(&empty[stage], phase);
+                mbar_expect_tx(&full[stage], bytes);
+                bulk_load_1d(smem + (size_t)stage * stage_bytes, a.Yt + (size_t)j0 * a.ldt, bytes, &full[stage]);
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int t = threadIdx.x;  // 0..255
+    double2 areg[KI], breg[KI], acc[KI];
+    bool live[KI];
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+        const int p = 2 * (t + kFConsumers * k);
+        live[k] = p < a.ldt;
+        areg[k] = make_double2(0.0, 0.0);
+        breg[k] = make_double2(0.0, 0.0);
+        acc[k] = make_double2(0.0, 0.0);
+        if (live[k]) {
+            areg[k] = make_double2(a.ab[2 * p], a.ab[2 * p + 2]);
+            if (KIND == kFusedGradient) breg[k] = make_double2(a.b[p], a.b[p + 1]);
+        }
+    }
+    double m_run = -DBL_MAX, S_run = 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int par = 0;
+
+    for (long long s = s_begin; s < s_end; ++s) {
+        const long long j0 = s * a.C;
+        const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
+        // per-structure inputs of this slab: issued before the wait so their latency hides behind it
+        double q0 = 0.0, q1 = 0.0;
+        if (lane < Cs) {
+            q0 = __ldg(a.s0 + j0 + lane);
+            if (KIND == kFusedGradient) q1 = __ldg(a.s1 + j0 + lane);
+        }
+        mbar_wait(&full[stage], phase);
+        const double* slab = reinterpret_cast<const double*>(smem + (size_t)stage * stage_bytes);
+
+        // ---- phase A: partial dot products over this thread's observables
+        double p[kFCMax];
+#pragma unroll
+        for (int c = 0; c < kFCMax; ++c) {
+            p[c] = 0.0;
+            if (c < Cs) {
+#pragma unroll
+                for (int k = 0; k < KI; ++k) {
+                    if (live[k]) {
+                        const double2 y =
+                            *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + 2 * (t + kFConsumers * k));
+                        p[c] = fma(y.x, areg[k].x, p[c]);
+                        p[c] = fma(y.y, areg[k].y, p[c]);
+                    }
+                }
+            }
+        }
+        double* redp = red + par * (kFConsumers / 32) * kFCMax;
+#pragma unroll
+        for (int c = 0; c < kFCMax; ++c) {
+            if (c < Cs) {
+                const double v = warp_sum(p[c]);
+                if (lane == 0) redp[warp * kFCMax + c] = v;
+            }
+        }
+        consumer_barrier();
+        double cj = 0.0;
+        if (lane < Cs) {
+#pragma unroll
+            for (int w = 0; w < kFConsumers / 32; ++w) cj += redp[w * kFCMax + lane];
+        }
+        par ^= 1;
+
+        // ---- per-structure transform (lane c <-> structure c; every warp computes the same values)
+        double v;
+        if (KIND == kFusedSoftmaxAvg) {
+            const double mx = warp_max(lane < Cs ? cj : -DBL_MAX);
+            const double m_new = fmax(m_run, mx);
+            const double sc = exp(m_run - m_new);
+            v = (lane < Cs) ? q0 * exp(cj - m_new) : 0.0;
+            S_run = S_run * sc + warp_sum(v);
+            m_run = m_new;
+            if (sc != 1.0) {
+#pragma unroll
+                for (int k = 0; k < KI; ++k) { acc[k].x *= sc; acc[k].y *= sc; }
+            }
+            if (warp == 0 && lane < Cs) a.xout[j0 + lane] = cj;
+        } else {
+            v = (lane < Cs) ? ((1.0 + q1) * a.theta + cj) * q0 : 0.0;
+        }
+
+        // ---- phase B: accumulate the structures of the slab into this thread's observables
+#pragma unroll
+        for (int c = 0; c < kFCMax; ++c) {
+            if (c < Cs) {
+                const double vc = __shfl_sync(0xffffffffu, v, c);
+#pragma unroll
+                for (int k = 0; k < KI; ++k) {
+                    if (live[k]) {
+                        const double2 y =
+                            *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + 2 * (t + kFConsumers * k));
+                        if (KIND == kFusedGradient) {
+                            acc[k].x = fma(y.x - breg[k].x, vc, acc[k].x);
+                            acc[k].y = fma(y.y - breg[k].y, vc, acc[k].y);
+                        } else {
+                            acc[k].x = fma(y.x, vc, acc[k].x);
+                            acc[k].y = fma(y.y, vc, acc[k].y);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    }
+
+    double* out = a.part + (size_t)blockIdx.x * a.ldp;
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+        if (live[k]) *reinterpret_cast<double2*>(out + 2 * (t + kFConsumers * k)) = acc[k];
+    }
+    if (KIND == kFusedSoftmaxAvg && t == 0) {
+        a.lse[2 * blockIdx.x] = m_run;
+        a.lse[2 * blockIdx.x + 1] = S_run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Team variant (ldt <= 4096): the block-wide kernel above synchronises all 8 warps twice per slab and its
+// per-slab dependency chain (shuffle reductions, exp) is longer than the time the slab takes to arrive, so it
+// runs at half the HBM rate.  Here a TEAM of T warps (T = 1 for M <= 1024) owns whole structures on its own:
+// the structure's M values are loaded from shared memory ONCE into registers, dotted with a_i, reduced with
+// shuffles (plus one T-warp named barrier when T > 1), turned into the per-structure factor, and accumulated
+// into the team's register-resident M-vector.  The 8/T teams of a CTA run on different structures with no
+// synchronisation between them, so one team's latency chain hides behind the others' arithmetic.  Each team
+// has its own ring of slabs (its own full/empty mbarriers); one producer lane feeds all rings.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTWarps = 8;                   // consumer warps per CTA
+constexpr int kTThreads = (kTWarps + 1) * 32;
+constexpr int kTMaxRing = 32;                // teams * stages
+constexpr int kTMaxLdt = 4096;
+
+struct TeamArgs {
+    const double* Yt;
+    long long ldt;
+    int M, N;
+    int C;                 // structures per slab (<= kFCMax)
+    int stages;            // ring depth per team
+    long long nslab, chunk;
+    const double* ab;      // interleaved {a_i, *}
+    const double* b;       // F2: avg_i
+    const double* s0;      // w0_j (F1) / w_j (F2)
+    const double* s1;      // lr_j (F2)
+    double theta;
+    double* xout;
+    double* part;          // [gridDim.x * teams][ldp]
+    long long ldp;
+    double* lse;           // [gridDim.x * teams][2]
+    int evict_first;       // 1: the matrix is much larger than L2, stream it through
+};
+
+template <int KI, int T, int KIND>
+__global__ void __launch_bounds__(kTThreads, 1) fused_team_pass(const TeamArgs a) {
+    constexpr int TEAMS = kTWarps / T;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                                           ~static_cast<uintptr_t>(127));
+    const int slab_bytes = a.C * (int)a.ldt * 8;
+    const int stage_bytes = (slab_bytes + 127) & ~127;
+    unsigned char* ring = smem;                                              // [TEAMS][stages][stage_bytes]
+    double* a_s = reinterpret_cast<double*>(ring + (size_t)TEAMS * a.stages * stage_bytes);   // [ldt]
+    double* b_s = a_s + a.ldt;                                               // [ldt] (F2 only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(b_s + (KIND == kFusedGradient ? a.ldt : 0));
+    uint64_t* empty = full + kTMaxRing;
+    double* tred = reinterpret_cast<double*>(empty + kTMaxRing);             // [TEAMS][2][T]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long s_begin = (long long)blockIdx.x * a.chunk;
+    const long long s_end = (s_begin + a.chunk < a.nslab) ? s_begin + a.chunk : a.nslab;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TEAMS * a.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], T);
+        }
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < a.ldt; i += blockDim.x) {
+        a_s[i] = a.ab[2 * i];
+        if (KIND == kFusedGradient) b_s[i] = a.b[i];
+    }
+    __syncthreads();
+
+    if (warp == kTWarps) {
+        // ------------------------------------------------------------------ producer
+        // one lane feeds all team rings round-robin; no divisions in the loop (one copy every ~300 cycles)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 1;   // a fresh barrier passes a wait on parity 1
+            const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+            long long s = s_begin;
+            while (s < s_end) {
+#pragma unroll 1
+                for (int team = 0; team < TEAMS && s < s_end; ++team, ++s) {
+                    const int slot = team * a.stages + stage;
+                    const long long j0 = s * a.C;
+                    const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
+                    const uint32_t bytes = (uint32_t)Cs * (uint32_t)a.ldt * 8u;
+                    mbar_wait(&empty[slot], phase);
+                    mbar_expect_tx(&full[slot], bytes);
+                    bulk_load_1d_hint(ring + (size_t)slot * stage_bytes, a.Yt + (size_t)j0 * a.ldt, bytes, &full[slot],
+                                      policy);
+                }
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int team = warp / T, wt = warp % T;
+    const int p0 = 2 * (lane + 32 * wt);   // this thread's observable pairs: p0 + 64*T*k
+    double2 acc[KI];
+#pragma unroll
+    for (int k = 0; k < KI; ++k) acc[k] = make_double2(0.0, 0.0);
+    double m_run = -DBL_MAX, S_run = 0.0;
+    int par = 0;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long s = s_begin + team; s < s_end; s += TEAMS) {
+        const int slot = team * a.stages + stage;
+        const long long j0 = s * a.C;
+        const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
+        // per-structure inputs of the slab's first structure: issued before the wait so the latency hides
+        double q0n = __ldg(a.s0 + j0), q1n = 0.0;
+        if (KIND == kFusedGradient) q1n = __ldg(a.s1 + j0);
+        mbar_wait(&full[slot], phase);
+        const double* slab = reinterpret_cast<const double*>(ring + (size_t)slot * stage_bytes);
+#pragma unroll 1
+        for (int c = 0; c < Cs; ++c) {
+            {
+                const double q0 = q0n, q1 = q1n;
+                if (c + 1 < Cs) {   // prefetch the next structure's inputs behind this one's arithmetic
+                    q0n = __ldg(a.s0 + j0 + c + 1);
+                    if (KIND == kFusedGradient) q1n = __ldg(a.s1 + j0 + c + 1);
+                }
+                // ---- phase A: the structure's values into registers, dot with a_i
+                double2 y[KI];
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < KI; ++k) {
+                    y[k] = make_double2(0.0, 0.0);
+                    if ((p0 + 64 * T * k) < a.ldt) {
+                        y[k] = *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + (p0 + 64 * T * k));
+                        const double2 av = *reinterpret_cast<const double2*>(a_s + (p0 + 64 * T * k));
+                        if (k & 1) { d2 = fma(y[k].x, av.x, d2); d3 = fma(y[k].y, av.y, d3); }
+                        else       { d0 = fma(y[k].x, av.x, d0); d1 = fma(y[k].y, av.y, d1); }
+                    }
+                }
+                double x = warp_sum((d0 + d1) + (d2 + d3));
+                if (T > 1) {
+                    double* tr = tred + (team * 2 + par) * T;
+                    if (lane == 0) tr[wt] = x;
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(T * 32) : "memory");
+                    x = 0.0;
+#pragma unroll
+                    for (int w = 0; w < T; ++w) x += tr[w];
+                    par ^= 1;
+                }
+                // ---- per-structure factor
+                double v;
+                if (KIND == kFusedSoftmaxAvg) {
+                    if (x > m_run) {   // new running maximum: rescale what has been accumulated (rare)
+                        const double sc = exp(m_run - x);
+                        S_run *= sc;
+#pragma unroll
+                        for (int k = 0; k < KI; ++k) { acc[k].x *= sc; acc[k].y *= sc; }
+                        m_run = x;
+                    }
+                    v = q0 * exp(x - m_run);
+                    S_run += v;
+                    if (wt == 0 && lane == 0) a.xout[j0 + c] = x;
+                } else {
+                    v = ((1.0 + q1) * a.theta + x) * q0;
+                }
+                // ---- phase B: accumulate from registers
+#pragma unroll
+                for (int k = 0; k < KI; ++k) {
+                    if (KIND == kFusedGradient) {
+                        if ((p0 + 64 * T * k) < a.ldt) {
+                            const double2 bv = *reinterpret_cast<const double2*>(b_s + (p0 + 64 * T * k));
+                            acc[k].x = fma(y[k].x - bv.x, v, acc[k].x);
+                            acc[k].y = fma(y[k].y - bv.y, v, acc[k].y);
+                        }
+                    } else {
+                        acc[k].x = fma(y[k].x, v, acc[k].x);
+                        acc[k].y = fma(y[k].y, v, acc[k].y);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    }
+
+    const size_t row = (size_t)blockIdx.x * TEAMS + team;
+    double* out = a.part + row * a.ldp;
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+        if ((p0 + 64 * T * k) < a.ldt) *reinterpret_cast<double2*>(out + (p0 + 64 * T * k)) = acc[k];
+    }
+    if (KIND == kFusedSoftmaxAvg && wt == 0 && lane == 0) {
+        a.lse[2 * row] = m_run;
+        a.lse[2 * row + 1] = S_run;
+    }
+}
+
+// merge the rows' running (max, sum) pairs into this rank's pair (one block, fixed-order tree)
+__global__ void __launch_bounds__(256) k_fused_lse_merge(int nrows, const double* lse, double* sc_pair) {
+    __shared__ double sm[256], ss[256];
+    double m = -DBL_MAX, s = 0.0;
+    for (int c = threadIdx.x; c < nrows; c += 256) {
+        const double m2 = lse[2 * c], s2 = lse[2 * c + 1];
+        const double mm = fmax(m, m2);
+        s = s * exp(m - mm) + s2 * exp(m2 - mm);
+        m = mm;
+    }
+    sm[threadIdx.x] = m;
+    ss[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double m1 = sm[threadIdx.x], m2 = sm[threadIdx.x + o];
+            const double mm = fmax(m1, m2);
+            ss[threadIdx.x] = ss[threadIdx.x] * exp(m1 - mm) + ss[threadIdx.x + o] * exp(m2 - mm);
+            sm[threadIdx.x] = mm;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        sc_pair[0] = sm[0];
+        sc_pair[1] = ss[0];
+    }
+}
+
+// out_i = sum_rows part[row][i] * scale_row;  scale_row = exp(m_row - M) / S with (M, S) the global pair (F1), or 1.
+// One block per 32 observables; 8 row-groups per block split the rows, combined in a fixed order.
+__global__ void __launch_bounds__(256) k_fused_merge_rows(int m, int nrows, const double* part, long long ldp,
+                                                          const double* lse_rows, const double* lse_pairs, int nranks,
+                                                          double* out) {
+    __shared__ double red[8][33];
+    double M = 0.0, inv = 1.0;
+    if (lse_rows) {
+        double S;
+        M = lse_pairs[0]; S = lse_pairs[1];
+        for (int r = 1; r < nranks; ++r) {
+            const double m2 = lse_pairs[2 * r], s2 = lse_pairs[2 * r + 1];
+            const double mm = fmax(M, m2);
+            S = S * exp(M - mm) + s2 * exp(m2 - mm);
+            M = mm;
+        }
+        inv = 1.0 / S;
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    for (int c = ty; c < nrows; c += 8) {
+        const double scale = lse_rows ? exp(lse_rows[2 * c] - M) * inv : 1.0;
+        if (i < m) s = fma(part[(size_t)c * ldp + i], scale, s);
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < m) {
+        double t = red[0][tx];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) t += red[g][tx];
+        out[i] = t;
+    }
+}
+
+// Yt[j][i] = Y[i][j]  (32 x 32 tiles through shared memory); pad column (ldt > M) is zeroed
+__global__ void __launch_bounds__(256) k_transpose(const double* __restrict__ Y, long long ld, int M, int N,
+                                                   double* __restrict__ Yt, long long ldt) {
+    __shared__ double tile[32][33];
+    const long long j0 = (long long)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r;
+        const long long j = j0 + tx;
+        tile[r][tx] = (i < M && j < N) ? Y[(size_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const long long j = j0 + r;
+        const int i = i0 + tx;
+        if (j < N && i < ldt) Yt[(size_t)j * ldt + i] = tile[tx][r];
+    }
+}
+
+}  // namespace bioen

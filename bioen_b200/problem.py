@@ -107,6 +107,10 @@ class Problem:
         _lib.check(self._lib.bioen_b200_set_forces(self._h, _lib.ptr(w0), _lib.ptr(Y), float(theta)), "set_forces")
         self.method = FORCES
 
+    def set_option(self, option, value):
+        """Tuning switches of include/bioen_b200.h (1 = fused two-pass forces kernels, default on)."""
+        _lib.check(self._lib.bioen_b200_set_option(self._h, int(option), int(value)), "set_option")
+
     def set_theta(self, theta):
         self._lib.bioen_b200_set_theta(self._h, float(theta))
 

@@ -160,6 +160,10 @@ int bioen_b200_download_ytilde(bioen_b200_ctx *ctx, int row0, int nrows, long lo
 int bioen_b200_set_logw(bioen_b200_ctx *ctx, const double *G_host, const double *YTilde_host, double theta);
 int bioen_b200_set_forces(bioen_b200_ctx *ctx, const double *w0_host, const double *YTilde_host, double theta);
 int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
+/* tuning switches (call before bioen_b200_set_forces).  BIOEN_B200_OPT_FUSED_FORCES (default 1): keep a
+ * structure-major copy of yTilde and evaluate the forces method in two fused passes instead of four */
+enum { BIOEN_B200_OPT_FUSED_FORCES = 1 };
+int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
  * two for logw, two instead of four for forces). */

@@ -169,3 +169,49 @@ def test_device_generator_is_the_documented_hash():
     assert np.max(np.abs(Y - ref)) < 1e-12
     assert np.array_equal(blk, Y[3:7, 100:150])
     assert abs(np.mean((Y - a[:, None]) / 2.0)) < 0.05 and abs(np.std((Y - a[:, None]) / 2.0) - 1) < 0.05
+
+
+# fused two-pass forces kernels (structure-major copy, csrc/fused_pass.cuh): eligible for 256 <= M <= 8192;
+# slab width C = 8 (M <= 768) ... 1 (M > 3072), register tiling KI = 1 ... 16
+FUSED_SHAPES = [(256, 1000), (300, 9), (511, 4097), (1000, 20000), (1500, 3000), (3073, 700), (4100, 300),
+                (8192, 70), (8193, 70)]
+
+
+@pytest.mark.parametrize("M,N", FUSED_SHAPES)
+def test_forces_fused_vs_unfused_vs_oracle(oracle, M, N):
+    import bioen_b200
+    P = oracle.synthetic_problem(M, N, seed=M + N)
+    rng = np.random.default_rng(M)
+    w0 = rng.random(N) + 0.05
+    w0 /= w0.sum()
+    f1 = (2e-2 / np.sqrt(M)) * rng.standard_normal(M)
+    theta = 2.5
+    fo, go = oracle.forces_fg(f1, w0, P["yTilde"], P["YTilde"], theta)
+    res = {}
+    for fused in (1, 0):
+        with bioen_b200.Problem(P["yTilde"]) as p:
+            p.set_option(1, fused)
+            p.set_forces(w0, P["YTilde"], theta)
+            f, g = p.objective_and_gradient(f1)
+            assert rel(f, fo) < TOL and grad_err(g, go) < TOL, (fused, rel(f, fo), grad_err(g, go))
+            assert rel(p.objective(f1), fo) < TOL
+            res[fused] = (f, g, p.kernels_launched())
+            # a second, different point through the same context (accumulators / barriers are reusable)
+            f2, g2 = p.objective_and_gradient(-0.5 * f1)
+            fo2, go2 = oracle.forces_fg(-0.5 * f1, w0, P["yTilde"], P["YTilde"], theta)
+            assert rel(f2, fo2) < TOL and grad_err(g2, go2) < TOL
+    assert rel(res[1][0], res[0][0]) < 1e-13
+
+
+def test_forces_fused_minimiser_and_reproducibility(oracle):
+    import bioen_b200
+    P = oracle.synthetic_problem(400, 30000, seed=77)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        p.set_forces(P["w0"], P["YTilde"], 10.0)
+        x, fmin, code, info = p.opt_lbfgs(P["forces_init"])
+        r = oracle.lbfgs(lambda v: oracle.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], 10.0), P["forces_init"])
+        assert code == r["code"] and rel(fmin, r["fx"]) < 1e-8, (code, r["code"], fmin, r["fx"], info)
+        f0, g0 = p.objective_and_gradient(x)
+        for _ in range(3):
+            f, g = p.objective_and_gradient(x)
+            assert f == f0 and np.array_equal(g, g0)
