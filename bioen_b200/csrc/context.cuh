@@ -12,6 +12,7 @@
 // One evaluation = 2 passes over Y (logw) or 4 (forces, unfused) + a few O(N)/O(M) kernels, all enqueued
 // on one stream with no host synchronisation; the caller fetches sc[] when it needs numbers.
 #pragma once
+#include <cstdlib>
 #include <vector>
 
 #include "comm.cuh"
@@ -137,7 +138,7 @@ class Context {
         avg.alloc(Mpad);
         msum.alloc(Mpad + 8);
         Yobs.alloc(Mpad);
-        w.alloc(Npad);
+        w.alloc(Npad + 8);   // +8: the fused kernels copy 16-byte windows that may end one element past N
         sc.alloc(SC_COUNT);
         red_partials.alloc((size_t)std::max(vec_blocks_n, vec_blocks_m) * 4 + 16);
         ticket.alloc(4);
@@ -256,10 +257,10 @@ class Context {
     }
     // forces: reference weights w0 (this rank's slice)
     void set_forces(const double* w0_host, bool on_device = false) {
-        Gv.alloc(N);      // holds w0
+        Gv.alloc(Npad + 8);      // holds w0
         if (on_device) d2d(Gv.p, w0_host, N); else h2d(Gv.p, w0_host, N);
-        aux_n.alloc(Npad);   // x_j, later E_j (zero padded: it feeds the row pass)
-        aux_n2.alloc(Npad);  // lr_j
+        aux_n.alloc(Npad + 8);   // x_j, later E_j (zero padded: it feeds the row pass)
+        aux_n2.alloc(Npad + 8);  // lr_j
         have_forces = true;
         if (allow_fused && Y && !fused_ready) prepare_fused();
     }
@@ -285,19 +286,24 @@ class Context {
         const long long smem_max = 232448 - 128;   // 227 KB opt-in limit minus our alignment slack
         f_team = false;
         if (ldt <= kTMaxLdt) {
-            // team variant: T warps per structure, 8/T independent teams per CTA
+            // team variant: T warps per structure, 8/T independent teams per CTA.  Measured at M = 1000:
+            // T = 1 (eight independent warps) 1.28 ms per pass, T = 2 1.34 ms, T = 4 2.1 ms.
             f_T = ldt <= 1024 ? 1 : ldt <= 2048 ? 2 : 4;
+            if (const char* e = getenv("BIOEN_B200_FUSED_T")) {
+                const int t = atoi(e);
+                if ((t == 1 || t == 2 || t == 4) && ldt <= 1024LL * t) f_T = t;
+            }
             const int teams = kTWarps / f_T;
             const long long need = (ldt + 64LL * f_T - 1) / (64LL * f_T);
             f_KI = need <= 4 ? 4 : need <= 8 ? 8 : 16;
             f_C = (int)std::max(1LL, std::min((long long)kFCMax, 8192LL / row_bytes));
-            const long long stage_bytes = ((long long)f_C * row_bytes + 127) & ~127LL;
+            const long long stage_bytes = (((long long)f_C * row_bytes + 127) & ~127LL) + kTAuxBytes;
             const long long fixed = 2 * row_bytes + 2 * kTMaxRing * 8 + 2LL * kTWarps * 8 + 256;
             const long long st = std::min((long long)kTMaxRing / teams, (smem_max - fixed) / (teams * stage_bytes));
             if (st >= 2) {
                 f_team = true;
                 f_stages = (int)st;
-                f_rows_per_cta = teams;
+                f_rows_per_cta = 1;   // the kernel combines its teams before writing
                 f_smem = (int)(teams * st * stage_bytes + fixed) + 128;
             }
         }
@@ -334,13 +340,23 @@ class Context {
         CUDA_CHECK(cudaFuncSetAttribute(fused_team_pass<KI, T, kFusedGradient>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
     }
+#define BIOEN_TEAM_DISPATCH(FN)                                   \
+    do {                                                          \
+        if (f_T == 1 && f_KI == 4) { FN(4, 1); }                  \
+        else if (f_T == 1 && f_KI == 8) { FN(8, 1); }             \
+        else if (f_T == 1) { FN(16, 1); }                         \
+        else if (f_T == 2 && f_KI == 4) { FN(4, 2); }             \
+        else if (f_T == 2 && f_KI == 8) { FN(8, 2); }             \
+        else if (f_T == 2) { FN(16, 2); }                         \
+        else if (f_KI == 4) { FN(4, 4); }                         \
+        else if (f_KI == 8) { FN(8, 4); }                         \
+        else { FN(16, 4); }                                       \
+    } while (0)
     void set_fused_attr() {
         if (f_team) {
-            if (f_T == 1 && f_KI == 4) set_team_attr<4, 1>();
-            else if (f_T == 1 && f_KI == 8) set_team_attr<8, 1>();
-            else if (f_T == 1) set_team_attr<16, 1>();
-            else if (f_T == 2) set_team_attr<16, 2>();
-            else set_team_attr<16, 4>();
+#define BIOEN_SET_ATTR(KI_, T_) set_team_attr<KI_, T_>()
+            BIOEN_TEAM_DISPATCH(BIOEN_SET_ATTR);
+#undef BIOEN_SET_ATTR
             return;
         }
         switch (f_KI) {
@@ -360,11 +376,9 @@ class Context {
             a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;
             a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta; a.xout = xout;
             a.part = fpart.p; a.ldp = Mpad; a.lse = flse.p; a.evict_first = evict_first;
-            if (f_T == 1 && f_KI == 4) fused_team_pass<4, 1, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
-            else if (f_T == 1 && f_KI == 8) fused_team_pass<8, 1, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
-            else if (f_T == 1) fused_team_pass<16, 1, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
-            else if (f_T == 2) fused_team_pass<16, 2, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
-            else fused_team_pass<16, 4, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a);
+#define BIOEN_LAUNCH_TEAM(KI_, T_) fused_team_pass<KI_, T_, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a)
+            BIOEN_TEAM_DISPATCH(BIOEN_LAUNCH_TEAM);
+#undef BIOEN_LAUNCH_TEAM
         } else {
             FusedArgs a{};
             a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;

@@ -66,8 +66,9 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 template <int KI, int KIND>
 __global__ void __launch_bounds__(kFThreads, 1) fused_struct_pass(const FusedArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
-                                                           ~static_cast<uintptr_t>(127));
+    // offset arithmetic on the extern array (not a uintptr_t round trip) keeps the shared address space known
+    // to the compiler: LDS instead of generic LD.E
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     const int slab_bytes = a.C * (int)a.ldt * 8;
     const int stage_bytes = (slab_bytes + 127) & ~127;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
@@ -237,9 +238,10 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_struct_pass(const FusedArg
 // has its own ring of slabs (its own full/empty mbarriers); one producer lane feeds all rings.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTWarps = 8;                   // consumer warps per CTA
-constexpr int kTThreads = (kTWarps + 1) * 32;
+constexpr int kTThreads = kTWarps * 32;      // no producer warp: every team feeds its own ring
 constexpr int kTMaxRing = 32;                // teams * stages
 constexpr int kTMaxLdt = 4096;
+constexpr int kTAuxBytes = 256;              // per ring slot: two windows of <= 10 doubles (w0 | w, lr)
 
 struct TeamArgs {
     const double* Yt;
@@ -254,36 +256,34 @@ struct TeamArgs {
     const double* s1;      // lr_j (F2)
     double theta;
     double* xout;
-    double* part;          // [gridDim.x * teams][ldp]
+    double* part;          // [gridDim.x][ldp]  (the teams of a CTA are combined in the kernel)
     long long ldp;
-    double* lse;           // [gridDim.x * teams][2]
+    double* lse;           // [gridDim.x][2]
     int evict_first;       // 1: the matrix is much larger than L2, stream it through
 };
 
 template <int KI, int T, int KIND>
 __global__ void __launch_bounds__(kTThreads, 1) fused_team_pass(const TeamArgs a) {
     constexpr int TEAMS = kTWarps / T;
+    // NOTE: index the extern array directly.  Rounding the base through uintptr_t makes the compiler lose the
+    // shared address space and emit generic LD.E instead of LDS.  Bulk copies need 16-byte alignment only,
+    // which the declaration guarantees.
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
-                                                           ~static_cast<uintptr_t>(127));
     const int slab_bytes = a.C * (int)a.ldt * 8;
-    const int stage_bytes = (slab_bytes + 127) & ~127;
-    unsigned char* ring = smem;                                              // [TEAMS][stages][stage_bytes]
+    const int aux_off = (slab_bytes + 127) & ~127;       // per-structure inputs ride along with the slab
+    const int stage_bytes = aux_off + kTAuxBytes;
+    unsigned char* ring = smem_raw;                                          // [TEAMS][stages][stage_bytes]
     double* a_s = reinterpret_cast<double*>(ring + (size_t)TEAMS * a.stages * stage_bytes);   // [ldt]
     double* b_s = a_s + a.ldt;                                               // [ldt] (F2 only)
     uint64_t* full = reinterpret_cast<uint64_t*>(b_s + (KIND == kFusedGradient ? a.ldt : 0));
-    uint64_t* empty = full + kTMaxRing;
-    double* tred = reinterpret_cast<double*>(empty + kTMaxRing);             // [TEAMS][2][T]
+    double* tred = reinterpret_cast<double*>(full + kTMaxRing);              // [TEAMS][2][T]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long s_begin = (long long)blockIdx.x * a.chunk;
     const long long s_end = (s_begin + a.chunk < a.nslab) ? s_begin + a.chunk : a.nslab;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TEAMS * a.stages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], T);
-        }
+        for (int s = 0; s < TEAMS * a.stages; ++s) mbar_init(&full[s], 1);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < a.ldt; i += blockDim.x) {
@@ -292,129 +292,162 @@ __global__ void __launch_bounds__(kTThreads, 1) fused_team_pass(const TeamArgs a
     }
     __syncthreads();
 
-    if (warp == kTWarps) {
-        // ------------------------------------------------------------------ producer
-        // one lane feeds all team rings round-robin; no divisions in the loop (one copy every ~300 cycles)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 1;   // a fresh barrier passes a wait on parity 1
-            const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
-            long long s = s_begin;
-            while (s < s_end) {
-#pragma unroll 1
-                for (int team = 0; team < TEAMS && s < s_end; ++team, ++s) {
-                    const int slot = team * a.stages + stage;
-                    const long long j0 = s * a.C;
-                    const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
-                    const uint32_t bytes = (uint32_t)Cs * (uint32_t)a.ldt * 8u;
-                    mbar_wait(&empty[slot], phase);
-                    mbar_expect_tx(&full[slot], bytes);
-                    bulk_load_1d_hint(ring + (size_t)slot * stage_bytes, a.Yt + (size_t)j0 * a.ldt, bytes, &full[slot],
-                                      policy);
-                }
-                if (++stage == a.stages) { stage = 0; phase ^= 1; }
-            }
+    // There is no producer warp: a single lane cannot issue one 8 KB bulk copy every ~300 cycles (measured:
+    // the kernel ran producer-bound).  Every team feeds its own ring: as soon as a slab has been read into
+    // registers its slot is refilled with the slab `stages` rounds ahead, so all slots but the one being read
+    // are always in flight and no empty-barrier handshake is needed.
+    const int team = warp / T, wt = warp % T;
+    const bool issuer = (wt == 0 && lane == 0);
+    const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+    auto issue = [&](long long s, int slot) {
+        const long long j0 = s * a.C;
+        const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
+        const uint32_t bytes = (uint32_t)Cs * (uint32_t)a.ldt * 8u;
+        // per-structure inputs (w0_j, or w_j and lr_j): 16-byte aligned window around [j0, j0 + Cs).  They must
+        // not be fetched by dependent loads: with ~20 MB of bulk copies queued on the chip a DRAM load that
+        // the arithmetic waits for costs several microseconds.
+        const long long jb = j0 & ~1LL;
+        const uint32_t abytes = (uint32_t)(((j0 + Cs - jb) + 1) & ~1LL) * 8u;
+        unsigned char* st = ring + (size_t)slot * stage_bytes;
+        mbar_expect_tx(&full[slot], bytes + abytes * (KIND == kFusedGradient ? 2u : 1u));
+        bulk_load_1d_hint(st, a.Yt + (size_t)j0 * a.ldt, bytes, &full[slot], policy);
+        bulk_load_1d(st + aux_off, a.s0 + jb, abytes, &full[slot]);
+        if (KIND == kFusedGradient) bulk_load_1d(st + aux_off + kTAuxBytes / 2, a.s1 + jb, abytes, &full[slot]);
+    };
+    if (issuer) {
+        for (int i = 0; i < a.stages; ++i) {
+            const long long s = s_begin + team + (long long)TEAMS * i;
+            if (s < s_end) issue(s, team * a.stages + i);
         }
-        return;
     }
 
-    // ---------------------------------------------------------------------- consumers
-    const int team = warp / T, wt = warp % T;
     const int p0 = 2 * (lane + 32 * wt);   // this thread's observable pairs: p0 + 64*T*k
     double2 acc[KI];
 #pragma unroll
     for (int k = 0; k < KI; ++k) acc[k] = make_double2(0.0, 0.0);
     double m_run = -DBL_MAX, S_run = 0.0;
     int par = 0;
-
     int stage = 0;
     uint32_t phase = 0;
+    const long long refill = (long long)TEAMS * a.stages;
+
     for (long long s = s_begin + team; s < s_end; s += TEAMS) {
         const int slot = team * a.stages + stage;
         const long long j0 = s * a.C;
         const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
-        // per-structure inputs of the slab's first structure: issued before the wait so the latency hides
-        double q0n = __ldg(a.s0 + j0), q1n = 0.0;
-        if (KIND == kFusedGradient) q1n = __ldg(a.s1 + j0);
         mbar_wait(&full[slot], phase);
         const double* slab = reinterpret_cast<const double*>(ring + (size_t)slot * stage_bytes);
+        const double* aux0 = reinterpret_cast<const double*>(ring + (size_t)slot * stage_bytes + aux_off) + (j0 & 1);
+        const double* aux1 = aux0 + kTAuxBytes / 16;
 #pragma unroll 1
         for (int c = 0; c < Cs; ++c) {
-            {
-                const double q0 = q0n, q1 = q1n;
-                if (c + 1 < Cs) {   // prefetch the next structure's inputs behind this one's arithmetic
-                    q0n = __ldg(a.s0 + j0 + c + 1);
-                    if (KIND == kFusedGradient) q1n = __ldg(a.s1 + j0 + c + 1);
-                }
-                // ---- phase A: the structure's values into registers, dot with a_i
-                double2 y[KI];
-                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            const double q0 = aux0[c];
+            const double q1 = (KIND == kFusedGradient) ? aux1[c] : 0.0;
+            // ---- phase A: the structure's values into registers, dot with a_i
+            double2 y[KI];
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-                for (int k = 0; k < KI; ++k) {
-                    y[k] = make_double2(0.0, 0.0);
+            for (int k = 0; k < KI; ++k) {
+                y[k] = make_double2(0.0, 0.0);
+                if ((p0 + 64 * T * k) < a.ldt) {
+                    y[k] = *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + (p0 + 64 * T * k));
+                    const double2 av = *reinterpret_cast<const double2*>(a_s + (p0 + 64 * T * k));
+                    if (k & 1) { d2 = fma(y[k].x, av.x, d2); d3 = fma(y[k].y, av.y, d3); }
+                    else       { d0 = fma(y[k].x, av.x, d0); d1 = fma(y[k].y, av.y, d1); }
+                }
+            }
+            double x = warp_sum((d0 + d1) + (d2 + d3));
+            if (T > 1) {
+                double* tr = tred + (team * 2 + par) * T;
+                if (lane == 0) tr[wt] = x;
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(T * 32) : "memory");
+                x = 0.0;
+#pragma unroll
+                for (int w = 0; w < T; ++w) x += tr[w];
+                par ^= 1;
+            }
+            if (c == Cs - 1) {
+                // the whole slab has been read (this structure is in registers, q0/q1 too; for T > 1 the team
+                // barrier above ordered every warp's reads): refill the slot for `stages` rounds ahead
+                __syncwarp();
+                if (issuer && s + refill < s_end) {
+                    fence_proxy_async();
+                    issue(s + refill, slot);
+                }
+            }
+            // ---- per-structure factor
+            double v;
+            if (KIND == kFusedSoftmaxAvg) {
+                if (x > m_run) {   // new running maximum: rescale what has been accumulated (rare)
+                    const double sc = exp(m_run - x);
+                    S_run *= sc;
+#pragma unroll
+                    for (int k = 0; k < KI; ++k) { acc[k].x *= sc; acc[k].y *= sc; }
+                    m_run = x;
+                }
+                v = q0 * exp(x - m_run);
+                S_run += v;
+                if (wt == 0 && lane == 0) a.xout[j0 + c] = x;
+            } else {
+                v = ((1.0 + q1) * a.theta + x) * q0;
+            }
+            // ---- phase B: accumulate from registers
+#pragma unroll
+            for (int k = 0; k < KI; ++k) {
+                if (KIND == kFusedGradient) {
                     if ((p0 + 64 * T * k) < a.ldt) {
-                        y[k] = *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + (p0 + 64 * T * k));
-                        const double2 av = *reinterpret_cast<const double2*>(a_s + (p0 + 64 * T * k));
-                        if (k & 1) { d2 = fma(y[k].x, av.x, d2); d3 = fma(y[k].y, av.y, d3); }
-                        else       { d0 = fma(y[k].x, av.x, d0); d1 = fma(y[k].y, av.y, d1); }
+                        const double2 bv = *reinterpret_cast<const double2*>(b_s + (p0 + 64 * T * k));
+                        acc[k].x = fma(y[k].x - bv.x, v, acc[k].x);
+                        acc[k].y = fma(y[k].y - bv.y, v, acc[k].y);
                     }
-                }
-                double x = warp_sum((d0 + d1) + (d2 + d3));
-                if (T > 1) {
-                    double* tr = tred + (team * 2 + par) * T;
-                    if (lane == 0) tr[wt] = x;
-                    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(T * 32) : "memory");
-                    x = 0.0;
-#pragma unroll
-                    for (int w = 0; w < T; ++w) x += tr[w];
-                    par ^= 1;
-                }
-                // ---- per-structure factor
-                double v;
-                if (KIND == kFusedSoftmaxAvg) {
-                    if (x > m_run) {   // new running maximum: rescale what has been accumulated (rare)
-                        const double sc = exp(m_run - x);
-                        S_run *= sc;
-#pragma unroll
-                        for (int k = 0; k < KI; ++k) { acc[k].x *= sc; acc[k].y *= sc; }
-                        m_run = x;
-                    }
-                    v = q0 * exp(x - m_run);
-                    S_run += v;
-                    if (wt == 0 && lane == 0) a.xout[j0 + c] = x;
                 } else {
-                    v = ((1.0 + q1) * a.theta + x) * q0;
-                }
-                // ---- phase B: accumulate from registers
-#pragma unroll
-                for (int k = 0; k < KI; ++k) {
-                    if (KIND == kFusedGradient) {
-                        if ((p0 + 64 * T * k) < a.ldt) {
-                            const double2 bv = *reinterpret_cast<const double2*>(b_s + (p0 + 64 * T * k));
-                            acc[k].x = fma(y[k].x - bv.x, v, acc[k].x);
-                            acc[k].y = fma(y[k].y - bv.y, v, acc[k].y);
-                        }
-                    } else {
-                        acc[k].x = fma(y[k].x, v, acc[k].x);
-                        acc[k].y = fma(y[k].y, v, acc[k].y);
-                    }
+                    acc[k].x = fma(y[k].x, v, acc[k].x);
+                    acc[k].y = fma(y[k].y, v, acc[k].y);
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
     }
 
-    const size_t row = (size_t)blockIdx.x * TEAMS + team;
-    double* out = a.part + row * a.ldp;
+    // ---- combine the teams of the CTA in shared memory (the ring is free now: every copy issued was consumed)
+    __syncthreads();
+    double* tm = reinterpret_cast<double*>(ring);                 // [TEAMS][ldt]
+    double* tm_m = tred;                                          // [TEAMS]
+    double* tm_S = tred + TEAMS;                                  // [TEAMS]  (tred holds 2*kTWarps doubles)
 #pragma unroll
     for (int k = 0; k < KI; ++k) {
-        if ((p0 + 64 * T * k) < a.ldt) *reinterpret_cast<double2*>(out + (p0 + 64 * T * k)) = acc[k];
+        if ((p0 + 64 * T * k) < a.ldt)
+            *reinterpret_cast<double2*>(tm + (size_t)team * a.ldt + (p0 + 64 * T * k)) = acc[k];
     }
     if (KIND == kFusedSoftmaxAvg && wt == 0 && lane == 0) {
-        a.lse[2 * row] = m_run;
-        a.lse[2 * row + 1] = S_run;
+        tm_m[team] = m_run;
+        tm_S[team] = S_run;
+    }
+    __syncthreads();
+    double scale[TEAMS];
+    double m_cta = -DBL_MAX, S_cta = 0.0;
+    if (KIND == kFusedSoftmaxAvg) {
+#pragma unroll
+        for (int t = 0; t < TEAMS; ++t) m_cta = fmax(m_cta, tm_m[t]);
+#pragma unroll
+        for (int t = 0; t < TEAMS; ++t) {
+            scale[t] = exp(tm_m[t] - m_cta);
+            S_cta = fma(tm_S[t], scale[t], S_cta);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < TEAMS; ++t) scale[t] = 1.0;
+    }
+    double* out = a.part + (size_t)blockIdx.x * a.ldp;
+    for (int i = threadIdx.x; i < a.ldt; i += blockDim.x) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < TEAMS; ++t) v = fma(tm[(size_t)t * a.ldt + i], scale[t], v);
+        out[i] = v;
+    }
+    if (KIND == kFusedSoftmaxAvg && threadIdx.x == 0) {
+        a.lse[2 * blockIdx.x] = m_cta;
+        a.lse[2 * blockIdx.x + 1] = S_cta;
     }
 }
 

@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(kPassThreads, 1)
     stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // 128-byte align the ring by hand (dynamic smem base is only guaranteed 16-byte aligned)
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
-                                                           ~static_cast<uintptr_t>(127));
+    // offset arithmetic on the extern array (not a uintptr_t round trip) keeps the shared address space known
+    // to the compiler: LDS instead of generic LD.E
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
 
