@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 
+#include "batched.cuh"
 #include "context.cuh"
 #include "gsl_min.cuh"
 #include "lbfgs.cuh"
@@ -396,6 +397,37 @@ int bioen_b200_opt_gsl(bioen_b200_ctx* ctx, int method, const double* x0_host, d
         ret = r;
     });
     return ret;
+}
+
+int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int K, const double* thetas, const double* x0_host, double* x_host,
+                          lbfgs_config_params config, visual_params visual, double* fmin, int* codes, int* info,
+                          double* stats) {
+    return guarded("bioen_b200_theta_scan", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const auto t0 = std::chrono::steady_clock::now();
+        ThetaScan scan(C, K, to_params(config));
+        scan.verbose = (int)visual.verbose;
+        const std::vector<ScanResult> res = scan.run(thetas, x0_host, x_host);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int q = 0; q < K; ++q) {
+            if (fmin) fmin[q] = res[q].fmin;
+            if (codes) codes[q] = res[q].code;
+            if (info) { info[2 * q] = res[q].iterations; info[2 * q + 1] = res[q].evaluations; }
+        }
+        if (stats) {
+            stats[0] = (double)scan.rounds;
+            stats[1] = (double)scan.gemm_launches;
+            stats[2] = secs;
+            stats[3] = 0.0;
+        }
+        if (visual.verbose) {
+            printf("theta scan: %d problems, %lld lockstep rounds, %.6f s\n", K, scan.rounds, secs);
+            for (int q = 0; q < K; ++q)
+                printf("\ttheta = %-12g %s  f = %.6lf  iterations %d\n", thetas[q], lbfgs_strerror(res[q].code),
+                       res[q].fmin, res[q].iterations);
+        }
+    });
 }
 
 int bioen_b200_nccl_unique_id(char id[128]) {

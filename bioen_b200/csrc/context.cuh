@@ -270,18 +270,21 @@ class Context {
         const long long l = (M + 1LL) & ~1LL;
         return M >= kFMinM && l <= kFMaxLdt;
     }
-    void prepare_fused() {
-        if (!fused_eligible()) return;
+    // structure-major copy Yt[j][i] of the resident matrix (the reference's yTildeT cache, made on the device)
+    void make_transposed() {
+        if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         ldt = (M + 1LL) & ~1LL;
         Yt.release();
         CUDA_CHECK(cudaMalloc(&Yt.p, (size_t)N * ldt * sizeof(double)));
         Yt.n = (size_t)N * ldt;
-        {
-            dim3 grid((unsigned)((N + 31) / 32), (unsigned)((ldt + 31) / 32));
-            k_transpose<<<grid, 256, 0, stream>>>(Y, ld, M, N, Yt.p, ldt);
-            CUDA_CHECK(cudaGetLastError());
-            ++kernels_launched;
-        }
+        dim3 grid((unsigned)((N + 31) / 32), (unsigned)((ldt + 31) / 32));
+        k_transpose<<<grid, 256, 0, stream>>>(Y, ld, M, N, Yt.p, ldt);
+        CUDA_CHECK(cudaGetLastError());
+        ++kernels_launched;
+    }
+    void prepare_fused() {
+        if (!fused_eligible()) return;
+        if (!Yt.p) make_transposed();
         const long long row_bytes = ldt * 8;
         const long long smem_max = 232448 - 128;   // 227 KB opt-in limit minus our alignment slack
         f_team = false;

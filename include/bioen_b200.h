@@ -184,6 +184,16 @@ int bioen_b200_opt_lbfgs(bioen_b200_ctx *ctx, int method, const double *x0_host,
 int bioen_b200_opt_gsl(bioen_b200_ctx *ctx, int method, const double *x0_host, double *x_host,
                        gsl_config_params config, visual_params visual, double *fmin, int info[4]);
 
+/* theta scan (L-curve): K <= 32 log-weights problems that differ only in theta (and start point) minimised together
+ * by K lockstep L-BFGS machines; every evaluation streams yTilde once for all K (fp64 tensor-core skinny GEMMs).
+ * Requires bioen_b200_set_logw (its theta is ignored).  x0_host / x_host: [K][n] row-major; fmin[K]; codes[K]
+ * (liblbfgs return codes); info[2K] = {iterations, evaluations} per problem; stats[4] = {lockstep rounds, GEMM
+ * launches, seconds, 0}.  The reference's counterpart is the Python loop over theta in
+ * bioen/analyze/procedure.py:62-83. */
+int bioen_b200_theta_scan(bioen_b200_ctx *ctx, int K, const double *thetas, const double *x0_host, double *x_host,
+                          lbfgs_config_params config, visual_params visual, double *fmin, int *codes, int *info,
+                          double *stats);
+
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);

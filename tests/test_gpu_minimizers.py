@@ -179,3 +179,61 @@ def test_part1_drivers_and_error_convention():
     x, fmin = c_bioen.bioen_opt_bfgs_forces(d["forces_init"].ravel(), d["w0"], d["yTilde"], d["YTilde"],
                                             d["theta"], cfg)
     assert rel(fmin, d["gsl_bfgs2_fmin"]) < F_TOL
+
+
+# ---- theta scan: K problems minimised together (batched fp64 tensor-core evaluations, lockstep L-BFGS) -----------
+def test_theta_scan_matches_single_problem_runs(oracle):
+    import bioen_b200
+    P = oracle.synthetic_problem(100, 20000, seed=12345)
+    thetas = np.array([1000.0, 300.0, 100.0, 30.0, 10.0, 3.0, 1.0, 0.3, 100.0, 10.0, 55.0])   # K = 11 (padded to 16)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        p.set_logw(P["G"], P["YTilde"], 1.0)
+        for ls in (2, 0):
+            X, fmin, codes, info = p.theta_scan(thetas, linesearch=ls)
+            assert X.shape == (thetas.size, 20000)
+            for q, th in enumerate(thetas):
+                p.set_theta(th)
+                x1, f1, c1, i1 = p.opt_lbfgs(P["GInit"], linesearch=ls)
+                tol = 1e-8 if i1["iterations"] < 150 else 1e-4      # long delta-stopped runs are chaotic
+                assert codes[q] == c1, (th, ls, codes[q], c1)
+                assert rel(fmin[q], f1) < tol, (th, ls, fmin[q], f1, info["iterations"][q], i1)
+                if i1["iterations"] < 150:
+                    assert abs(int(info["iterations"][q]) - i1["iterations"]) <= 2
+                assert rel(p.objective(X[q]), fmin[q]) < 5e-13
+                if i1["iterations"] < 150:
+                    assert np.max(np.abs(_softmax(X[q]) - _softmax(x1))) < W_TOL
+            # identical thetas give identical results (planes do not interact)
+            assert fmin[2] == fmin[8] and np.array_equal(X[2], X[8])
+            assert fmin[4] == fmin[9] and np.array_equal(X[4], X[9])
+
+
+def test_theta_scan_against_reference_golden(oracle):
+    """theta = 10 plane of a scan reproduces the reference's liblbfgs end point stored in the golden file."""
+    import bioen_b200
+    d = load_golden("synthetic_M100xN20000")
+    P = oracle.synthetic_problem(int(d["M"]), int(d["N"]), seed=int(d["seed"]))
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        p.set_logw(P["G"], P["YTilde"], d["theta"])
+        for ls in (0, 2):
+            X, fmin, codes, info = p.theta_scan([d["theta"], 2 * d["theta"]], linesearch=ls)
+            assert codes[0] == d["logw_lbfgs%d_code" % ls]
+            assert rel(fmin[0], d["logw_lbfgs%d_fmin" % ls]) < F_TOL
+            assert np.max(np.abs(_softmax(X[0]) - _softmax(d["logw_lbfgs%d_x" % ls]))) < W_TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(7, 33, 1), (37, 5001, 8), (300, 1000, 9), (1000, 777, 32), (257, 4099, 24)])
+def test_theta_scan_ragged_shapes(oracle, M, N, K):
+    import bioen_b200
+    P = oracle.synthetic_problem(M, N, seed=M + N + K)
+    rng = np.random.default_rng(K)
+    G = 0.1 * rng.standard_normal(N)
+    thetas = np.geomspace(100.0, 1.0, K)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        p.set_logw(G, P["YTilde"], 1.0)
+        X, fmin, codes, info = p.theta_scan(thetas, x0=G, max_iterations=15)
+        for q in (0, K // 2, K - 1):
+            p.set_theta(thetas[q])
+            x1, f1, c1, i1 = p.opt_lbfgs(G, max_iterations=15)
+            assert codes[q] == c1 and rel(fmin[q], f1) < 1e-9, (q, codes[q], c1, fmin[q], f1)
+            fo, _ = oracle.logw_fg(X[q], G, P["yTilde"], P["YTilde"], thetas[q])
+            assert rel(fo, fmin[q]) < 1e-11 or codes[q] < 0
