@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimum", action="store_true")
     ap.add_argument("--unfused-forces", action="store_true", help="forces: four tile passes instead of two fused")
+    ap.add_argument("--theta-scan", type=int, default=0, metavar="K",
+                    help="BASELINE config 4: K theta values (log-spaced 1e3..1e-1) minimised together; prints the "
+                         "batched-evaluation line instead of the single-theta one")
     return ap.parse_args()
 
 
@@ -348,8 +351,66 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_theta_scan(args):
+    """BASELINE.json config 4: the L-curve -- K problems, one yTilde stream per pass for all of them."""
+    import torch
+    import bioen_b200
+    from bioen_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    M, N, K = args.m, args.n, args.theta_scan
+    a, YT = observations(M)
+    prob = bioen_b200.Problem(shape=(M, N), device=0)
+    prob.generate(SEED, 0, a, SIG_SIM / SIG_EXP)
+    prob.set_logw(np.zeros(N), YT, THETA)
+    thetas = np.geomspace(1e3, 1e-1, K)
+    rng = np.random.default_rng(SEED + 7)
+    X0 = np.ascontiguousarray(0.1 * rng.standard_normal((K, N)))
+    lib = _lib.load()
+    peak_tf = ctypes.c_double()
+    _lib.check(lib.bioen_b200_dmma_peak(0, ctypes.byref(peak_tf)), "dmma_peak")
+    ms, gemm_ms, launches = ctypes.c_float(), ctypes.c_float(), ctypes.c_longlong()
+    with ClockSampler(0) as clk:
+        _lib.check(lib.bioen_b200_time_scan_evals(prob._h, K, _lib.ptr(thetas), _lib.ptr(X0), args.warmup, args.steps,
+                                                  ctypes.byref(ms), ctypes.byref(gemm_ms), ctypes.byref(launches)),
+                   "time_scan_evals")
+    KP = (K + 7) // 8 * 8
+    flops = 2.0 * M * N * KP
+    ach = flops / (gemm_ms.value * 1e-3) / 1e12
+    hbm_peak, _ = measured_peak()
+    line = {
+        "metric": "theta_scan_problem_evals_per_s", "value": K * args.steps / (ms.value * 1e-3),
+        "unit": "f+g evaluations/s summed over K problems (logw, N=%d x M=%d each)" % (N, M), "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.value / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "theta L-curve scan, K=%d theta values batched, N=%d x M=%d, skinny fp64 GEMMs on "
+                               "tensor cores (DMMA)" % (K, N, M), "K": K, "l2": "inputs (%.1f GB) larger than L2"
+                                                                                 % (M * N * 8 / 1e9)},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
+                     "frac": ach / peak_tf.value, "traffic": None,
+                     "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 loop (no fp64 figure "
+                                    "in MEASURED_PEAKS.json)",
+                     "kernel": "batched_gemm_kernel (one pass over yTilde for all K)", "flops_per_launch": flops,
+                     "ms_per_launch": gemm_ms.value,
+                     "hbm_frac_same_launch": (M * N * 8.0) / (gemm_ms.value * 1e-3) / 1e9 / hbm_peak},
+        "gpu_launches": int(launches.value), "clocks": clk.summary(),
+    }
+    if not args.no_optimum:
+        t0 = time.perf_counter()
+        X, fmin, codes, info = prob.theta_scan(thetas, x0=np.zeros(N))
+        line["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "rounds": info["rounds"],
+                                   "codes": [int(c) for c in codes], "iterations": [int(i) for i in info["iterations"]],
+                                   "evaluations_total": int(info["evaluations"].sum()),
+                                   "fmin_first_last": [float(fmin[0]), float(fmin[-1])],
+                                   "includes": "K x N start vectors H2D, results D2H; yTilde resident"}
+    prob.close()
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
+    if args.theta_scan and args.impl != "reference":
+        return run_theta_scan(args)
     if args.impl == "reference":
         run_reference(args)
     else:

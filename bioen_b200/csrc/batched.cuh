@@ -47,6 +47,23 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
                  : "d"(a), "d"(b));
 }
 
+// register-resident DMMA loop: the fp64 tensor-core peak this GPU can actually deliver (bench.py's roofline
+// denominator for the batched GEMMs; MEASURED_PEAKS.json has no fp64 figure)
+__global__ void __launch_bounds__(256) k_dmma_peak(int iters, double* sink) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma_m8n8k4(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
 // position of element (index, k) inside a fragment-major B operand with KP = 8*NT problems
 __host__ __device__ __forceinline__ size_t frag_index(long long index, int k, int NT) {
     return ((size_t)(index >> 2) * NT + (k >> 3)) * 32 + (size_t)((k & 7) * 4 + (int)(index & 3));
@@ -626,6 +643,40 @@ class ThetaScan {
         C.sync();
     }
     const double* hs(int k) const { return h_scb + (size_t)k * SC_COUNT; }
+
+    // bench.py: time `steps` batched evaluations of all K problems at fresh points (x = xp + (k+1)*d with a tiny d)
+    void time_evals(const double* thetas, const double* x0_host, int warmup, int steps, float* ms, float* gemm_ms,
+                    long long* launches) {
+        KVec kv{};
+        for (int q = 0; q < KP; ++q) { kv.mask[q] = q < K; kv.theta[q] = q < K ? thetas[q] : 0.0; kv.stp[q] = 0.0; }
+        for (int q = 0; q < K; ++q) C.h2d(B.X + (size_t)q * ldn, x0_host + (size_t)q * n, n);
+        const dim3 gridv(vblocks, KP);
+        evaluate(kv, false);
+        kb_scale_copy<<<gridv, kVecThreads, 0, C.stream>>>(n, ldn, B.X, B.XP, 1.0, kv);
+        kb_scale_copy<<<gridv, kVecThreads, 0, C.stream>>>(n, ldn, B.Gr, B.D, -1e-9, kv);
+        auto one = [&](int i) {
+            for (int q = 0; q < K; ++q) kv.stp[q] = (double)(i + 1);
+            evaluate(kv, true);
+        };
+        for (int i = 0; i < warmup; ++i) one(i);
+        C.sync();
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        C.begin_pass_timing(steps * 2);
+        const long long k0 = C.kernels_launched;
+        CUDA_CHECK(cudaEventRecord(e0, C.stream));
+        for (int i = 0; i < steps; ++i) one(warmup + i);
+        CUDA_CHECK(cudaEventRecord(e1, C.stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float total = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&total, e0, e1));
+        *ms = total;
+        *launches = C.kernels_launched - k0;
+        *gemm_ms = C.end_pass_timing();
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
 
     // x0 / x_out: [K][n] host arrays.  Returns per-problem results (liblbfgs codes).
     std::vector<ScanResult> run(const double* thetas, const double* x0_host, double* x_host) {

@@ -430,6 +430,45 @@ int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int K, const double* thetas, cons
     });
 }
 
+int bioen_b200_time_scan_evals(bioen_b200_ctx* ctx, int K, const double* thetas, const double* x0_host, int warmup,
+                               int steps, float* ms, float* gemm_ms, long long* launches) {
+    return guarded("bioen_b200_time_scan_evals", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        ThetaScan scan(C, K, LbfgsParams());
+        scan.time_evals(thetas, x0_host, warmup, steps, ms, gemm_ms, launches);
+    });
+}
+
+int bioen_b200_dmma_peak(int device, double* tflops) {
+    return guarded("bioen_b200_dmma_peak", [&] {
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        DevBuf<double> sink;
+        sink.alloc(1);
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        const int iters = 20000, blocks = prop.multiProcessorCount * 4;
+        k_dmma_peak<<<blocks, 256>>>(100, sink.p);
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            CUDA_CHECK(cudaEventRecord(e0));
+            k_dmma_peak<<<blocks, 256>>>(iters, sink.p);
+            CUDA_CHECK(cudaEventRecord(e1));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float t = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+            best = std::min(best, t);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        // 8 warps * 8 mma * 512 flop per iteration per block
+        *tflops = (double)blocks * 8.0 * 8.0 * 512.0 * iters / (best * 1e-3) / 1e12;
+    });
+}
+
 int bioen_b200_nccl_unique_id(char id[128]) {
     return guarded("bioen_b200_nccl_unique_id", [&] { Comm::unique_id(id); });
 }

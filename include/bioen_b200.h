@@ -194,6 +194,13 @@ int bioen_b200_theta_scan(bioen_b200_ctx *ctx, int K, const double *thetas, cons
                           lbfgs_config_params config, visual_params visual, double *fmin, int *codes, int *info,
                           double *stats);
 
+/* bench.py: time `steps` batched f+g evaluations of K problems (CUDA events); *gemm_ms = mean duration of one
+ * skinny-GEMM launch.  bioen_b200_dmma_peak: fp64 tensor-core peak of the device, measured with a
+ * register-resident mma.sync.m8n8k4.f64 loop (the roofline denominator of the GEMMs). */
+int bioen_b200_time_scan_evals(bioen_b200_ctx *ctx, int K, const double *thetas, const double *x0_host, int warmup,
+                               int steps, float *ms, float *gemm_ms, long long *launches);
+int bioen_b200_dmma_peak(int device, double *tflops);
+
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);
