@@ -220,3 +220,50 @@ def find_optimum(GInit, G, y, yTilde, YTilde, theta, cfg, problem=None):
         print("fmin_final    = ", fmin_final)
         print("========================")
     return wopt, yopt, gopt, fmin_initial, fmin_final
+
+
+def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, problem=None):
+    """The theta series (L-curve) of the reference's callers -- the loop of bioen/analyze/procedure.py:62-83 and
+    of the ala5 notebook's run_theta_series -- on ONE resident copy of yTilde.  Not part of the reference API.
+
+    batched=True (minimizer 'lbfgs' only): up to 32 theta values are minimised together from GInit by lockstep
+    device L-BFGS machines whose evaluations are fp64 tensor-core skinny GEMMs (yTilde streamed once per pass
+    for all of them).  batched=False: one find_optimum per theta, warm-started from the previous optimum like
+    the reference's callers do.  Returns a list of find_optimum 5-tuples, one per theta, in input order.
+    """
+    check_params_logweights(GInit, G, y, yTilde, YTilde)
+    thetas = [float(t) for t in np.asarray(thetas, dtype=np.float64).ravel()]
+    own = problem is None
+    if own:
+        problem = Problem(yTilde)
+    out = []
+    try:
+        if batched and cfg["minimizer"].upper() in ("LIBLBFGS", "LBFGS"):
+            problem.set_logw(G, YTilde, thetas[0] if thetas else 0.0)
+            g0 = _lib.vec(GInit)
+            yprob = problem if y is yTilde else Problem(y)
+            try:
+                for lo in range(0, len(thetas), 32):
+                    chunk = thetas[lo:lo + 32]
+                    X, fmin, codes, _ = problem.theta_scan(chunk, x0=g0, verbose=cfg["verbose"], **_lbfgs_kwargs(cfg))
+                    for q, th in enumerate(chunk):
+                        if codes[q] not in LBFGS_OK:
+                            raise RuntimeError("{}, liblbfgs return code: {}:{}".format(
+                                "bioen_opt_lbfgs_logw", codes[q], lbfgs_strerror(codes[q])))
+                        problem.set_theta(th)
+                        fmin_initial = problem.objective(g0, LOGW)
+                        w, _ = problem.weights(X[q], LOGW)
+                        out.append((w.reshape(-1, 1), yprob.average(w), X[q].copy(), fmin_initial, float(fmin[q])))
+            finally:
+                if yprob is not problem:
+                    yprob.close()
+        else:
+            g = GInit
+            for th in thetas:
+                res = find_optimum(g, G, y, yTilde, YTilde, th, cfg, problem=problem)
+                out.append(res)
+                g = res[2].reshape(-1, 1)
+    finally:
+        if own:
+            problem.close()
+    return out

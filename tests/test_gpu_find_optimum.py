@@ -109,3 +109,24 @@ def test_theta_series_reuses_one_upload(oracle):
             assert rel(f1, r["fx"]) < tol, (theta, f1, r["fx"], r["iterations"], r["code"])
             assert abs(wopt.sum() - 1) < 1e-12
             GInit = gopt.reshape(-1, 1)
+
+
+def test_find_optimum_series_batched_and_sequential(oracle):
+    from bioen_b200 import optimize
+    P = oracle.synthetic_problem(60, 8000, seed=31)
+    cfg = _cfg("lbfgs", "", True)
+    thetas = [100.0, 30.0, 10.0]
+    batched = optimize.log_weights.find_optimum_series(P["GInit"], P["G"], P["y"], P["yTilde"], P["YTilde"], thetas,
+                                                       cfg, batched=True)
+    seq = optimize.log_weights.find_optimum_series(P["GInit"], P["G"], P["y"], P["yTilde"], P["YTilde"], thetas, cfg,
+                                                   batched=False)
+    assert len(batched) == len(seq) == 3
+    for th, b, s_ in zip(thetas, batched, seq):
+        wopt, yopt, gopt, f0, f1 = b
+        assert wopt.shape == (8000, 1) and yopt.shape == (60,) and gopt.shape == (8000,)
+        r = oracle.lbfgs(lambda v: oracle.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], th), P["GInit"])
+        assert rel(f1, r["fx"]) < 1e-8                                    # cold start = what the oracle ran
+        assert np.allclose(yopt, P["y"] @ wopt.ravel(), rtol=1e-12, atol=1e-12)
+        # the warm-started run (the reference callers' way) stops on the same `delta` criterion from another
+        # start point: same optimum to the reference's own 10 % bar, not digit for digit
+        assert rel(s_[4], f1) < 1e-2
