@@ -36,7 +36,11 @@ SEED = 12345
 SIG_EXP, SIG_SIM = 0.5, 1.0
 THETA = 10.0
 METRIC = "grad_evals_per_s"
-UNIT = "evals/s (f+g, logw, N=1e6 x M=1e3 per evaluation)"
+
+
+def unit(args):
+    return ("evals/s (one evaluation = objective + gradient of the %s method over an N=%d x M=%d block of yTilde; "
+            "summed over GPUs)" % (args.method, args.n, args.m))
 
 
 def parse():
@@ -45,8 +49,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=1000)
-    ap.add_argument("--n", type=int, default=1000000, help="structures PER GPU")
+    # long spellings: under torchrun a bare `--m` is swallowed by the launcher's own abbreviation matching
+    ap.add_argument("--m", "--observables", dest="m", type=int, default=1000)
+    ap.add_argument("--n", "--structures", dest="n", type=int, default=1000000, help="structures PER GPU")
     ap.add_argument("--method", default="logw", choices=["logw", "forces"])
     ap.add_argument("--cpu-cols", type=int, default=200000, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -192,14 +197,14 @@ def run_reference(args):
     t_wall = time.perf_counter()
     value, info = cpu_reference_evals(args.m, args.n, args.cpu_cols, steps, min(args.warmup, 2), args.method)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": unit(args), "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d, theta=%g"
                                % (args.method, args.n, args.m, THETA), "method": args.method},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+        "cpu_baseline": {"value": value, "unit": unit(args), "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": unit(args), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
     }
     print(json.dumps(line))
@@ -313,7 +318,7 @@ def run_b200(args):
     alg_bytes = float(M) * N * 8.0
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": unit(args), "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
@@ -330,7 +335,7 @@ def run_b200(args):
                      "kernel": "stream_pass_kernel (one pass over yTilde)", "bytes_per_launch": alg_bytes,
                      "ms_per_launch": pass_ms,
                      "step_frac": (2 * M * N * 8.0) / (ms / args.steps * 1e-3) / 1e9 / peak},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,
+        "e2e": {"value": e2e_value, "unit": unit(args), "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,
                 "api": "bioen_b200_eval (C ABI, pinned host vectors; yTilde resident after one upload)"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
@@ -340,10 +345,10 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, info = cpu_reference_evals(M, N, args.cpu_cols, 5, 1, args.method)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+            line["cpu_baseline"] = {"value": v, "unit": unit(args), "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"]}
         except Exception as e:  # the baseline is reported, never required for the GPU number
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+            line["cpu_baseline"] = {"value": None, "unit": unit(args), "cores": 0, "kind": "unavailable", "sample": str(e)}
     prob.close()
     if rank == 0:
         print(json.dumps(line))

@@ -284,17 +284,17 @@ class Context {
     }
     void prepare_fused() {
         if (!fused_eligible()) return;
-        if (!Yt.p) make_transposed();
+        ldt = (M + 1LL) & ~1LL;
         const long long row_bytes = ldt * 8;
         const long long smem_max = 232448 - 128;   // 227 KB opt-in limit minus our alignment slack
         f_team = false;
         if (ldt <= kTMaxLdt) {
             // team variant: T warps per structure, 8/T independent teams per CTA.  Measured at M = 1000:
             // T = 1 (eight independent warps) 1.28 ms per pass, T = 2 1.34 ms, T = 4 2.1 ms.
-            f_T = ldt <= 1024 ? 1 : ldt <= 2048 ? 2 : 4;
+            f_T = ldt <= 1024 ? 1 : ldt <= 2048 ? 2 : ldt <= 4096 ? 4 : 8;
             if (const char* e = getenv("BIOEN_B200_FUSED_T")) {
                 const int t = atoi(e);
-                if ((t == 1 || t == 2 || t == 4) && ldt <= 1024LL * t) f_T = t;
+                if ((t == 1 || t == 2 || t == 4 || t == 8) && ldt <= 1024LL * t) f_T = t;
             }
             const int teams = kTWarps / f_T;
             const long long need = (ldt + 64LL * f_T - 1) / (64LL * f_T);
@@ -310,15 +310,8 @@ class Context {
                 f_smem = (int)(teams * st * stage_bytes + fixed) + 128;
             }
         }
-        if (!f_team) {
-            f_C = (int)std::max(1LL, std::min((long long)kFCMax, (long long)kFSlabTarget / row_bytes));
-            const long long stage_bytes = ((long long)f_C * row_bytes + 127) & ~127LL;
-            f_stages = (int)std::max(2LL, std::min((long long)kFMaxStages, (long long)kFSmemBudget / stage_bytes));
-            const int need = (int)((ldt + 511) / 512);
-            f_KI = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
-            f_rows_per_cta = 1;
-            f_smem = (int)(f_stages * stage_bytes) + 2 * kFMaxStages * 8 + 2 * (kFConsumers / 32) * kFCMax * 8 + 128;
-        }
+        if (!f_team) return;   // does not fit shared memory (M > ~5500): the four-pass tile kernels are used
+        if (!Yt.p) make_transposed();
         f_nslab = ((long long)N + f_C - 1) / f_C;
         f_grid = (int)std::min<long long>(num_sms, f_nslab);
         f_chunk = (f_nslab + f_grid - 1) / f_grid;
@@ -328,13 +321,6 @@ class Context {
         flse.alloc((size_t)2 * f_rows);
         set_fused_attr();
         fused_ready = true;
-    }
-    template <int KI>
-    void set_fused_attr_ki() {
-        CUDA_CHECK(cudaFuncSetAttribute(fused_struct_pass<KI, kFusedSoftmaxAvg>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(fused_struct_pass<KI, kFusedGradient>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
     }
     template <int KI, int T>
     void set_team_attr() {
@@ -351,9 +337,12 @@ class Context {
         else if (f_T == 2 && f_KI == 4) { FN(4, 2); }             \
         else if (f_T == 2 && f_KI == 8) { FN(8, 2); }             \
         else if (f_T == 2) { FN(16, 2); }                         \
-        else if (f_KI == 4) { FN(4, 4); }                         \
-        else if (f_KI == 8) { FN(8, 4); }                         \
-        else { FN(16, 4); }                                       \
+        else if (f_T == 4 && f_KI == 4) { FN(4, 4); }             \
+        else if (f_T == 4 && f_KI == 8) { FN(8, 4); }             \
+        else if (f_T == 4) { FN(16, 4); }                         \
+        else if (f_KI == 4) { FN(4, 8); }                         \
+        else if (f_KI == 8) { FN(8, 8); }                         \
+        else { FN(16, 8); }                                       \
     } while (0)
     void set_fused_attr() {
         if (f_team) {
@@ -362,19 +351,12 @@ class Context {
 #undef BIOEN_SET_ATTR
             return;
         }
-        switch (f_KI) {
-            case 1: set_fused_attr_ki<1>(); break;
-            case 2: set_fused_attr_ki<2>(); break;
-            case 4: set_fused_attr_ki<4>(); break;
-            case 8: set_fused_attr_ki<8>(); break;
-            default: set_fused_attr_ki<16>(); break;
-        }
     }
     template <int KIND>
     void launch_fused(const double* bvec, const double* s0, const double* s1, double* xout) {
         const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
-        if (f_team) {
+        {
             TeamArgs a{};
             a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;
             a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta; a.xout = xout;
@@ -382,18 +364,6 @@ class Context {
 #define BIOEN_LAUNCH_TEAM(KI_, T_) fused_team_pass<KI_, T_, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a)
             BIOEN_TEAM_DISPATCH(BIOEN_LAUNCH_TEAM);
 #undef BIOEN_LAUNCH_TEAM
-        } else {
-            FusedArgs a{};
-            a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;
-            a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta; a.xout = xout;
-            a.part = fpart.p; a.ldp = Mpad; a.lse = flse.p;
-            switch (f_KI) {
-                case 1: fused_struct_pass<1, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
-                case 2: fused_struct_pass<2, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
-                case 4: fused_struct_pass<4, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
-                case 8: fused_struct_pass<8, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
-                default: fused_struct_pass<16, KIND><<<f_grid, kFThreads, f_smem, stream>>>(a); break;
-            }
         }
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
         CUDA_CHECK(cudaGetLastError());

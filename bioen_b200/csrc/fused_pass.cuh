@@ -10,21 +10,16 @@
 // In the reference's observable-major layout (M x N) the first reduction needs a whole COLUMN before the second
 // can start, and a column block of useful width does not fit in shared memory.  So the forces method keeps a
 // second, structure-major copy  Yt[j][i]  (N x ldt; the reference's own `yTildeT` cache, c_bioen.pyx:391-393,
-// made once on the device by k_transpose): now all M observables of a structure are contiguous, a "slab" of C
-// whole structures (~48 KB) is ONE 1-D bulk copy (cp.async.bulk, completion on an mbarrier), and both reductions
-// run out of the same shared-memory slab:
+// made once on the device by k_transpose): all M observables of a structure are contiguous, a slab of C whole
+// structures is ONE 1-D bulk copy (cp.async.bulk, completion on an mbarrier), and both reductions run on the
+// same copy of the data -- see fused_team_pass below.  HBM traffic: N*ldt*8 bytes per kernel, read exactly once.
+// All reductions are fixed-order: bit-reproducible run to run.
 //
-//   phase A   every thread owns a fixed set of observable pairs i (coefficients a_i, b_i live in registers for
-//             the whole kernel) and forms its part of the C dot products; warp shuffle + one named barrier give
-//             every warp the C column sums (lane c holds structure c)
-//   transform lane c turns its sum into the per-structure factor v_c (online softmax with a running max for
-//             F1, the E_j formula for F2); the per-structure inputs were prefetched before the slab arrived
-//   phase B   acc_i += (y_ci - b_i) v_c  for the thread's own observables; accumulators stay in registers over
-//             all slabs of the CTA and are written once, to the CTA's own row of `part`
-//
-// Persistent: one CTA per SM, producer warp + 8 consumer warps, ring of 3-8 slabs, equal contiguous chunks of
-// slabs per CTA.  All reductions are fixed-order: bit-reproducible run to run.  HBM traffic: N*ldt*8 bytes per
-// kernel, read exactly once.
+// History (measured at N = 1e6, M = 1e3, 8 GB per pass; 1.15 ms = the unfused tile kernel = HBM roofline):
+//   block-wide kernel, 8 warps per slab, two barriers per slab            2.35 ms   latency chain per slab
+//   teams + producer warp with 64-bit divisions in its loop               1.85 ms   producer-bound
+//   teams + division-free producer warp                                   1.34 ms   producer-bound (8 KB copies)
+//   teams feeding their own rings, inputs riding with the slab (this)     1.22 ms
 #pragma once
 #include <float.h>
 
@@ -32,200 +27,11 @@
 
 namespace bioen {
 
-constexpr int kFConsumers = 256;            // 8 consumer warps
-constexpr int kFThreads = kFConsumers + 32;  // + producer warp
-constexpr int kFCMax = 8;                   // structures per slab (<= 32: one lane per structure)
-constexpr int kFMaxStages = 8;
-constexpr int kFSlabTarget = 48 * 1024;
-constexpr int kFSmemBudget = 200 * 1024;
+constexpr int kFCMax = 8;                   // structures per slab
 constexpr int kFMinM = 256;                 // below this the thread mapping is mostly idle: use the tile kernels
-constexpr int kFMaxLdt = 8192;              // 16 pair-slots x 512 observables
+constexpr int kFMaxLdt = 8192;              // 16 pair-slots x 64 lanes x 8 warps
 
 enum FusedKind { kFusedSoftmaxAvg = 0, kFusedGradient = 1 };
-
-struct FusedArgs {
-    const double* Yt;      // N x ldt, structure-major, ldt even, pad column zero
-    long long ldt;
-    int M, N;
-    int C;                 // structures per slab
-    int stages;
-    long long nslab, chunk;
-    const double* ab;      // interleaved {a_i, *}: a_i = f_i (F1) or r_i (F2); zero padded
-    const double* b;       // F2: avg_i (zero padded); F1: unused
-    const double* s0;      // per structure: w0_j (F1) or w_j (F2)
-    const double* s1;      // F2: lr_j
-    double theta;
-    double* xout;          // F1: x_j
-    double* part;          // [gridDim.x][ldp] accumulators
-    long long ldp;
-    double* lse;           // F1: [gridDim.x][2] = running (max, sum) of the CTA
-};
-
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kFConsumers) : "memory"); }
-
-template <int KI, int KIND>
-__global__ void __launch_bounds__(kFThreads, 1) fused_struct_pass(const FusedArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // offset arithmetic on the extern array (not a uintptr_t round trip) keeps the shared address space known
-    // to the compiler: LDS instead of generic LD.E
-    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    const int slab_bytes = a.C * (int)a.ldt * 8;
-    const int stage_bytes = (slab_bytes + 127) & ~127;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
-    uint64_t* empty = full + kFMaxStages;
-    double* red = reinterpret_cast<double*>(empty + kFMaxStages);  // [2][8 warps][kFCMax]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long s_begin = (long long)blockIdx.x * a.chunk;
-    const long long s_end = (s_begin + a.chunk < a.nslab) ? s_begin + a.chunk : a.nslab;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kFConsumers / 32);
-        }
-        fence_barrier_init();
-    }
-    __syncthreads();
-
-    if (warp == kFConsumers / 32) {
-        // ------------------------------------------------------------------ producer: one bulk copy per slab
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 1;
-            for (long long s = s_begin; s < s_end; ++s) {
-                const long long j0 = s * a.C;
-                const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
-                const uint32_t bytes = (uint32_t)Cs * (uint32_t)a.ldt * 8u;
-                mbar_wait(&empty[stage], phase);
-                mbar_expect_tx(&full[stage], bytes);
-                bulk_load_1d(smem + (size_t)stage * stage_bytes, a.Yt + (size_t)j0 * a.ldt, bytes, &full[stage]);
-                if (++stage == a.stages) { stage = 0; phase ^= 1; }
-            }
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- consumers
-    const int t = threadIdx.x;  // 0..255
-    double2 areg[KI], breg[KI], acc[KI];
-    bool live[KI];
-#pragma unroll
-    for (int k = 0; k < KI; ++k) {
-        const int p = 2 * (t + kFConsumers * k);
-        live[k] = p < a.ldt;
-        areg[k] = make_double2(0.0, 0.0);
-        breg[k] = make_double2(0.0, 0.0);
-        acc[k] = make_double2(0.0, 0.0);
-        if (live[k]) {
-            areg[k] = make_double2(a.ab[2 * p], a.ab[2 * p + 2]);
-            if (KIND == kFusedGradient) breg[k] = make_double2(a.b[p], a.b[p + 1]);
-        }
-    }
-    double m_run = -DBL_MAX, S_run = 0.0;
-    int stage = 0;
-    uint32_t phase = 0;
-    int par = 0;
-
-    for (long long s = s_begin; s < s_end; ++s) {
-        const long long j0 = s * a.C;
-        const int Cs = (a.N - j0 < a.C) ? (int)(a.N - j0) : a.C;
-        // per-structure inputs of this slab: issued before the wait so their latency hides behind it
-        double q0 = 0.0, q1 = 0.0;
-        if (lane < Cs) {
-            q0 = __ldg(a.s0 + j0 + lane);
-            if (KIND == kFusedGradient) q1 = __ldg(a.s1 + j0 + lane);
-        }
-        mbar_wait(&full[stage], phase);
-        const double* slab = reinterpret_cast<const double*>(smem + (size_t)stage * stage_bytes);
-
-        // ---- phase A: partial dot products over this thread's observables
-        double p[kFCMax];
-#pragma unroll
-        for (int c = 0; c < kFCMax; ++c) {
-            p[c] = 0.0;
-            if (c < Cs) {
-#pragma unroll
-                for (int k = 0; k < KI; ++k) {
-                    if (live[k]) {
-                        const double2 y =
-                            *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + 2 * (t + kFConsumers * k));
-                        p[c] = fma(y.x, areg[k].x, p[c]);
-                        p[c] = fma(y.y, areg[k].y, p[c]);
-                    }
-                }
-            }
-        }
-        double* redp = red + par * (kFConsumers / 32) * kFCMax;
-#pragma unroll
-        for (int c = 0; c < kFCMax; ++c) {
-            if (c < Cs) {
-                const double v = warp_sum(p[c]);
-                if (lane == 0) redp[warp * kFCMax + c] = v;
-            }
-        }
-        consumer_barrier();
-        double cj = 0.0;
-        if (lane < Cs) {
-#pragma unroll
-            for (int w = 0; w < kFConsumers / 32; ++w) cj += redp[w * kFCMax + lane];
-        }
-        par ^= 1;
-
-        // ---- per-structure transform (lane c <-> structure c; every warp computes the same values)
-        double v;
-        if (KIND == kFusedSoftmaxAvg) {
-            const double mx = warp_max(lane < Cs ? cj : -DBL_MAX);
-            const double m_new = fmax(m_run, mx);
-            const double sc = exp(m_run - m_new);
-            v = (lane < Cs) ? q0 * exp(cj - m_new) : 0.0;
-            S_run = S_run * sc + warp_sum(v);
-            m_run = m_new;
-            if (sc != 1.0) {
-#pragma unroll
-                for (int k = 0; k < KI; ++k) { acc[k].x *= sc; acc[k].y *= sc; }
-            }
-            if (warp == 0 && lane < Cs) a.xout[j0 + lane] = cj;
-        } else {
-            v = (lane < Cs) ? ((1.0 + q1) * a.theta + cj) * q0 : 0.0;
-        }
-
-        // ---- phase B: accumulate the structures of the slab into this thread's observables
-#pragma unroll
-        for (int c = 0; c < kFCMax; ++c) {
-            if (c < Cs) {
-                const double vc = __shfl_sync(0xffffffffu, v, c);
-#pragma unroll
-                for (int k = 0; k < KI; ++k) {
-                    if (live[k]) {
-                        const double2 y =
-                            *reinterpret_cast<const double2*>(slab + (size_t)c * a.ldt + 2 * (t + kFConsumers * k));
-                        if (KIND == kFusedGradient) {
-                            acc[k].x = fma(y.x - breg[k].x, vc, acc[k].x);
-                            acc[k].y = fma(y.y - breg[k].y, vc, acc[k].y);
-                        } else {
-                            acc[k].x = fma(y.x, vc, acc[k].x);
-                            acc[k].y = fma(y.y, vc, acc[k].y);
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
-    }
-
-    double* out = a.part + (size_t)blockIdx.x * a.ldp;
-#pragma unroll
-    for (int k = 0; k < KI; ++k) {
-        if (live[k]) *reinterpret_cast<double2*>(out + 2 * (t + kFConsumers * k)) = acc[k];
-    }
-    if (KIND == kFusedSoftmaxAvg && t == 0) {
-        a.lse[2 * blockIdx.x] = m_run;
-        a.lse[2 * blockIdx.x + 1] = S_run;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Team variant (ldt <= 4096): the block-wide kernel above synchronises all 8 warps twice per slab and its
@@ -240,7 +46,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_struct_pass(const FusedArg
 constexpr int kTWarps = 8;                   // consumer warps per CTA
 constexpr int kTThreads = kTWarps * 32;      // no producer warp: every team feeds its own ring
 constexpr int kTMaxRing = 32;                // teams * stages
-constexpr int kTMaxLdt = 4096;
+constexpr int kTMaxLdt = 8192;               // T = 8: one team of all eight warps
 constexpr int kTAuxBytes = 256;              // per ring slot: two windows of <= 10 doubles (w0 | w, lr)
 
 struct TeamArgs {
