@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-cols", type=int, default=200000, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimum", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the host-matrix drop-in call (needs M*N*8 B of host RAM)")
     ap.add_argument("--unfused-forces", action="store_true", help="forces: four tile passes instead of two fused")
     ap.add_argument("--theta-scan", type=int, default=0, metavar="K",
                     help="BASELINE config 4: K theta values (log-spaced 1e3..1e-1) minimised together; prints the "
@@ -77,6 +78,25 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic(method, M, N):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed `ncu --set full`
+    capture of this same workload (profiles/), or None when the workload differs from the profiled one."""
+    if (M, N) != (1000, 1000000):
+        return None
+    name = "r1_ncu_full_stream_pass.csv" if method == "logw" else "r1_ncu_full_fused_team_pass.csv"
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
+            rows = list(csv.reader(fh))
+        hdr, units = rows[0], rows[1]
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        vals = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]] for r in rows[2:] if r]
+        return sum(vals) / len(vals)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -314,6 +334,29 @@ def run_b200(args):
                    "minimizer": "device L-BFGS (liblbfgs semantics, BioEn defaults: linesearch=2, past=10, "
                                 "delta=1e-6, epsilon=1e-6)", "includes": "x0 H2D + result D2H; yTilde resident"}
 
+    # ---- the reference-facing call with HOST buffers: bioen.optimize.ext.c_bioen.bioen_opt_lbfgs_* ------------
+    dropin = None
+    if world == 1 and not args.no_dropin and not args.no_optimum:
+        from bioen_b200 import optimize
+        from bioen_b200.optimize.ext import c_bioen
+        yT_host = prob.download()                       # the same matrix, now a pageable NumPy array
+        cfg = optimize.minimize.Parameters("lbfgs")
+        cfg["verbose"] = False
+        t0 = time.perf_counter()
+        with bioen_b200.Problem(yT_host, device=local):
+            upload_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if method == LOGW:
+            xo2, fmin2 = c_bioen.bioen_opt_lbfgs_logw(np.zeros(N), np.zeros(N), yT_host, YT, THETA, cfg)
+        else:
+            xo2, fmin2 = c_bioen.bioen_opt_lbfgs_forces(np.zeros(M), np.full(N, 1.0 / N), yT_host, YT, THETA, cfg)
+        total_s = time.perf_counter() - t0
+        dropin = {"api": "c_bioen.bioen_opt_lbfgs_%s (host NumPy arrays in, result out; = the reference's Cython entry)"
+                         % args.method, "seconds": total_s, "ytilde_upload_s": upload_s,
+                  "h2d_bytes": M * N * 8 + (N + M) * 8, "fmin": fmin2,
+                  "agrees_with_resident_run": bool(optimum and abs(fmin2 - optimum["fmin"]) <= 1e-8 * abs(fmin2))}
+        del yT_host
+
     peak, peak_src = measured_peak()
     alg_bytes = float(M) * N * 8.0
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
@@ -331,8 +374,11 @@ def run_b200(args):
             "generate_s": gen_s,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "stream_pass_kernel (one pass over yTilde)", "bytes_per_launch": alg_bytes,
+                     "frac": achieved / peak, "traffic": profiled_traffic(args.method, M, N),
+                     "traffic_source": "profiles/r1_ncu_full_*.csv (ncu --set full of this workload, mean per launch)",
+                     "peak_source": peak_src,
+                     "kernel": ("stream_pass_kernel" if method == LOGW or args.unfused_forces else "fused_team_pass")
+                               + " (one pass over yTilde)", "bytes_per_launch": alg_bytes,
                      "ms_per_launch": pass_ms,
                      "step_frac": (2 * M * N * 8.0) / (ms / args.steps * 1e-3) / 1e9 / peak},
         "e2e": {"value": e2e_value, "unit": unit(args), "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,
@@ -342,6 +388,8 @@ def run_b200(args):
     }
     if optimum:
         line["time_to_optimum"] = optimum
+    if dropin:
+        line["dropin_time_to_optimum"] = dropin
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, info = cpu_reference_evals(M, N, args.cpu_cols, 5, 1, args.method)

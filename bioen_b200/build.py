@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libbioen_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
-    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-diag-suppress", "550",
 ]
 
 

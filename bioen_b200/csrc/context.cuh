@@ -13,6 +13,9 @@
 // on one stream with no host synchronisation; the caller fetches sc[] when it needs numbers.
 #pragma once
 #include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "comm.cuh"
@@ -174,9 +177,68 @@ class Context {
         Yown.n = (size_t)M * ld;
         Y = Yown.p;
         if (ld != N) CUDA_CHECK(cudaMemsetAsync(Y, 0, (size_t)M * ld * sizeof(double), stream));
-        CUDA_CHECK(cudaMemcpy2DAsync(Y, ld * sizeof(double), host, ld_host * sizeof(double), (size_t)N * sizeof(double),
-                                     M, cudaMemcpyHostToDevice, stream));
+        sync();
+        const size_t total = (size_t)M * N * sizeof(double);
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const char* mode = getenv("BIOEN_B200_UPLOAD");   // "plain" forces one cudaMemcpy2D (diagnostics)
+        if (pinned || total < ((size_t)256 << 20) || (mode && !strcmp(mode, "plain"))) {
+            CUDA_CHECK(cudaMemcpy2DAsync(Y, ld * sizeof(double), host, ld_host * sizeof(double),
+                                         (size_t)N * sizeof(double), M, cudaMemcpyHostToDevice, stream));
+            sync();
+        } else {
+            upload_staged(host, ld_host);
+        }
         make_tensor_map();
+    }
+    // Large pageable source (a NumPy array): a plain cudaMemcpy is limited by the driver's single-threaded staging
+    // (~10 GB/s).  Here kUpThreads host threads copy row chunks into their own pinned double buffers and push them
+    // with async copies on their own streams, so the host memcpy and the PCIe transfer overlap and scale.
+    static constexpr int kUpThreads = 6;
+    void upload_staged(const double* host, size_t ld_host) {
+        const size_t row_bytes = (size_t)N * sizeof(double);
+        const size_t buf_bytes = std::max(row_bytes, (size_t)32 << 20);
+        const int rows_per_chunk = (int)std::max<size_t>(1, buf_bytes / row_bytes);
+        const int nchunks = (M + rows_per_chunk - 1) / rows_per_chunk;
+        int want = kUpThreads;
+        if (const char* e = getenv("BIOEN_B200_UPLOAD_THREADS")) want = std::max(1, atoi(e));
+        const int nthreads = std::min(want, nchunks);
+        std::vector<std::thread> pool;
+        std::vector<std::string> errors(nthreads);
+        for (int t = 0; t < nthreads; ++t) {
+            pool.emplace_back([&, t] {
+                try {
+                    CUDA_CHECK(cudaSetDevice(device));
+                    cudaStream_t st;
+                    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                    char* stage[2] = {nullptr, nullptr};
+                    cudaEvent_t done[2];
+                    for (int b = 0; b < 2; ++b) {
+                        CUDA_CHECK(cudaHostAlloc((void**)&stage[b], (size_t)rows_per_chunk * row_bytes, cudaHostAllocDefault));
+                        CUDA_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+                    }
+                    int use = 0;
+                    for (int c = t; c < nchunks; c += nthreads, use ^= 1) {
+                        const int r0 = c * rows_per_chunk, nr = std::min(rows_per_chunk, M - r0);
+                        CUDA_CHECK(cudaEventSynchronize(done[use]));   // the previous copy out of this buffer
+                        for (int r = 0; r < nr; ++r)
+                            memcpy(stage[use] + (size_t)r * row_bytes, host + (size_t)(r0 + r) * ld_host, row_bytes);
+                        CUDA_CHECK(cudaMemcpy2DAsync(Y + (size_t)r0 * ld, ld * sizeof(double), stage[use], row_bytes,
+                                                     row_bytes, nr, cudaMemcpyHostToDevice, st));
+                        CUDA_CHECK(cudaEventRecord(done[use], st));
+                    }
+                    CUDA_CHECK(cudaStreamSynchronize(st));
+                    for (int b = 0; b < 2; ++b) { cudaFreeHost(stage[b]); cudaEventDestroy(done[b]); }
+                    cudaStreamDestroy(st);
+                } catch (const std::exception& e) {
+                    errors[t] = e.what();
+                }
+            });
+        }
+        for (auto& th : pool) th.join();
+        for (auto& e : errors)
+            if (!e.empty()) throw CudaError(e);
     }
     // allocate an uninitialised device matrix (filled by the on-device generator)
     void alloc_matrix() {
