@@ -237,3 +237,32 @@ def test_theta_scan_ragged_shapes(oracle, M, N, K):
             assert codes[q] == c1 and rel(fmin[q], f1) < 1e-9, (q, codes[q], c1, fmin[q], f1)
             fo, _ = oracle.logw_fg(X[q], G, P["yTilde"], P["YTilde"], thetas[q])
             assert rel(fo, fmin[q]) < 1e-11 or codes[q] < 0
+
+
+def test_theta_scan_errors_and_chunking(oracle):
+    import bioen_b200
+    from bioen_b200 import optimize
+    P = oracle.synthetic_problem(20, 600, seed=3)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        with pytest.raises(RuntimeError, match="log-weights data not set"):
+            p.theta_scan([1.0, 2.0])
+        p.set_logw(P["G"], P["YTilde"], 1.0)
+        with pytest.raises(RuntimeError, match="1..32"):
+            p.theta_scan(np.ones(33))
+        # invalid liblbfgs parameters: every problem reports the parameter code, nothing is evaluated
+        X, fmin, codes, info = p.theta_scan([1.0, 2.0, 3.0], delta=-1.0)
+        assert list(codes) == [-1015] * 3 and info["rounds"] == 0
+        # a start point that already satisfies the convergence test
+        xo, fo, co, _ = p.opt_lbfgs(P["GInit"], epsilon=1e-10, delta=0.0, past=0)
+        X, fmin, codes, info = p.theta_scan([1.0], x0=xo, epsilon=1e-3)
+        assert codes[0] == 2 and rel(fmin[0], fo) < 1e-12
+    # more theta values than one batch holds: find_optimum_series chunks by 32
+    cfg = optimize.minimize.Parameters("lbfgs")
+    cfg["verbose"] = False
+    thetas = np.geomspace(100.0, 1.0, 35)
+    out = optimize.log_weights.find_optimum_series(P["GInit"], P["G"], P["y"], P["yTilde"], P["YTilde"], thetas, cfg)
+    assert len(out) == 35
+    f_final = np.array([o[4] for o in out])
+    assert np.all(np.diff(f_final) < 1e-9)          # the optimum decreases with theta
+    r = oracle.lbfgs(lambda v: oracle.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], thetas[33]), P["GInit"])
+    assert rel(out[33][4], r["fx"]) < 1e-8
