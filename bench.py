@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--method", default="logw", choices=["logw", "forces"])
     ap.add_argument("--cpu-cols", type=int, default=200000, help="columns of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --structures is the TOTAL N, split over the GPUs (default: weak, N per GPU)")
     ap.add_argument("--no-optimum", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the host-matrix drop-in call (needs M*N*8 B of host RAM)")
     ap.add_argument("--unfused-forces", action="store_true", help="forces: four tile passes instead of two fused")
@@ -252,7 +254,13 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    M, N = args.m, args.n
+    M = args.m
+    if args.strong:
+        from bioen_b200.dist import shard_bounds
+        lo, hi = shard_bounds(args.n, rank, world)
+        N, col0 = hi - lo, lo
+    else:
+        N, col0 = args.n, rank * args.n
     method = LOGW if args.method == "logw" else FORCES
     nvar = N if method == LOGW else M
     a, YT = observations(M)
@@ -265,11 +273,11 @@ def run_b200(args):
             _lib.check(_lib.load().bioen_b200_nccl_unique_id(raw), "nccl_unique_id")
             idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
         dist.broadcast(idbuf, 0)
-        prob.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world, N * world)
+        prob.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world, args.n if args.strong else N * world)
     t0 = time.perf_counter()
-    prob.generate(SEED, rank * N, a, SIG_SIM / SIG_EXP)      # this rank's columns of the global matrix
+    prob.generate(SEED, col0, a, SIG_SIM / SIG_EXP)          # this rank's columns of the global matrix
     gen_s = time.perf_counter() - t0
-    n_total = N * world
+    n_total = args.n if args.strong else N * world
     if method == LOGW:
         prob.set_logw(np.zeros(N), YT, THETA)
     else:
@@ -301,7 +309,8 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, pass_ms = float(t[0]), float(t[1])
-    value = world * args.steps / (ms * 1e-3)
+    units = 1 if args.strong else world     # weak: every rank adds one N-block per evaluation
+    value = units * args.steps / (ms * 1e-3)
 
     # ---- end to end: host vectors through the C ABI ------------------------------------------------------
     lib = _lib.load()
@@ -319,7 +328,7 @@ def run_b200(args):
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(te[0])
+    e2e_value = units * e2e_steps / float(te[0])
 
     # ---- time to optimum (device L-BFGS, BioEn defaults) -----------------------------------------------
     optimum = None
@@ -362,7 +371,8 @@ def run_b200(args):
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": unit(args), "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d per GPU (yTilde %.1f GB fp64 "

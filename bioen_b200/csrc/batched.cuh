@@ -640,7 +640,7 @@ class ThetaScan {
     }
     void fetch() {
         C.d2h(h_scb, scb.p, (size_t)KP * SC_COUNT);
-        C.sync();
+        C.spin_sync();
     }
     const double* hs(int k) const { return h_scb + (size_t)k * SC_COUNT; }
 

@@ -313,6 +313,9 @@ static int run_lbfgs_dev(bioen_b200_ctx* ctx, int method, double* x_dev, lbfgs_c
         info[2] = 0;
         info[3] = 0;
     }
+    if (opt.trace)
+        fprintf(stderr, "[bioen_b200 trace] lbfgs %.3f s wall: %d evals, GPU eval %.1f ms, GPU update+idle %.1f ms\n",
+                secs, opt.stats.evaluations, opt.stats.gpu_eval_ms, opt.stats.gpu_update_ms);
     if (visual.verbose) {
         printf("\t%s\n", lbfgs_strerror(ret));
         printf("\tConfig: m=%d and n=%d\n", C.M, C.N);

@@ -160,6 +160,7 @@ class Context {
     ~Context() {
         if (h_sc) cudaFreeHost(h_sc);
         for (cudaEvent_t e : pass_ev) cudaEventDestroy(e);
+        if (fetch_ev) cudaEventDestroy(fetch_ev);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 
@@ -708,9 +709,20 @@ class Context {
         d2d(avg_out_dev, msum.p, M);
     }
 
+    // the host reads the scalar file once per line-search trial: spin on an event instead of
+    // cudaStreamSynchronize, whose default scheduling may yield the CPU (milliseconds on a busy host)
+    cudaEvent_t fetch_ev = nullptr;
+    void spin_sync() {
+        if (!fetch_ev) CUDA_CHECK(cudaEventCreateWithFlags(&fetch_ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(fetch_ev, stream));
+        cudaError_t e;
+        while ((e = cudaEventQuery(fetch_ev)) == cudaErrorNotReady) {
+        }
+        CUDA_CHECK(e);
+    }
     void fetch_scalars() {
         d2h(h_sc, sc.p, SC_COUNT);
-        sync();
+        spin_sync();
     }
 };
 

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kTThreads, 1) fused_team_pass(const TeamArgs a
     // NOTE: index the extern array directly.  Rounding the base through uintptr_t makes the compiler lose the
     // shared address space and emit generic LD.E instead of LDS.  Bulk copies need 16-byte alignment only,
     // which the declaration guarantees.
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int slab_bytes = a.C * (int)a.ldt * 8;
     const int aux_off = (slab_bytes + 127) & ~127;       // per-structure inputs ride along with the slab
     const int stage_bytes = aux_off + kTAuxBytes;

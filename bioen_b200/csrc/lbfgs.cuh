@@ -71,6 +71,7 @@ struct LbfgsParams {  // lbfgs.h lbfgs_parameter_t with _defparam (lbfgs.c:113-1
 struct LbfgsStats {
     int iterations = 0, evaluations = 0;
     double seconds = 0.0;
+    double gpu_eval_ms = 0.0, gpu_update_ms = 0.0, host_wait_s = 0.0;   // BIOEN_B200_TRACE=1
 };
 
 inline int lbfgs_check_params(int n, const LbfgsParams& p) {  // lbfgs.c:286-364
@@ -179,6 +180,8 @@ class Lbfgs {
     LbfgsParams prm;
     int verbose = 0;
     LbfgsStats stats;
+    bool trace = false;                                   // BIOEN_B200_TRACE: GPU time of evaluations vs updates
+    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};
 
     DevBuf<double> store;  // g, xp, gp, d, s[m], y[m]
     double *x = nullptr, *g = nullptr, *xp = nullptr, *gp = nullptr, *d = nullptr;
@@ -195,6 +198,7 @@ class Lbfgs {
     // x_dev (device, n doubles): start point on entry, end point on exit.  Returns the liblbfgs code.
     int run(double* x_dev, double* fx_out) {
         x = x_dev;
+        trace = getenv("BIOEN_B200_TRACE") != nullptr;
         int ret = lbfgs_check_params(n, prm);
         if (ret) { *fx_out = 0.0; return ret; }
         const int m = prm.m;
@@ -270,8 +274,22 @@ class Lbfgs {
    private:
     // enqueue one f+g evaluation at x (= xp + stp*dir when xp_ given); dg direction optional
     void eval(const double* xp_, const double* dir, double stp, const double* ddir) {
+        if (trace) {
+            if (!tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+            cudaEventRecord(tev[2], C.stream);          // end of the previous update phase
+            if (stats.evaluations > 0) {
+                cudaEventSynchronize(tev[2]);
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, tev[0], tev[1]);
+                cudaEventElapsedTime(&b, tev[1], tev[2]);
+                stats.gpu_eval_ms += a;
+                stats.gpu_update_ms += b;
+            }
+            cudaEventRecord(tev[0], C.stream);
+        }
         if (forces) C.forces_eval(x, xp_, dir, stp, g, ddir);
         else C.logw_eval(x, xp_, dir, stp, g, ddir);
+        if (trace) cudaEventRecord(tev[1], C.stream);
         ++stats.evaluations;
     }
 

@@ -68,7 +68,7 @@ __host__ __device__ inline int pass_num_slots(long long run, long long L, long l
 template <int MODE, bool SUB>
 __global__ void __launch_bounds__(kPassThreads, 1)
     stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 128-byte align the ring by hand (dynamic smem base is only guaranteed 16-byte aligned)
     // offset arithmetic on the extern array (not a uintptr_t round trip) keeps the shared address space known
     // to the compiler: LDS instead of generic LD.E
