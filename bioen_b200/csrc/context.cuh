@@ -38,7 +38,11 @@ struct DevBuf {
         n = count;
         if (count) {
             CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
-            CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+            // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which does NOT
+            // order against our cudaStreamNonBlocking streams: without the wait below a kernel (or copy) that
+            // writes the fresh buffer can be overtaken by the zero fill (seen as rare, unreproducible test failures)
+            CUDA_CHECK(cudaMemsetAsync(p, 0, count * sizeof(T), cudaStreamLegacy));
+            CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
         }
     }
     void release() {

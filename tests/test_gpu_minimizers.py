@@ -264,5 +264,6 @@ def test_theta_scan_errors_and_chunking(oracle):
     assert len(out) == 35
     f_final = np.array([o[4] for o in out])
     assert np.all(np.diff(f_final) < 1e-9)          # the optimum decreases with theta
-    r = oracle.lbfgs(lambda v: oracle.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], thetas[33]), P["GInit"])
-    assert rel(out[33][4], r["fx"]) < 1e-8
+    for q in (2, 33):       # one plane of each chunk against the oracle's liblbfgs restatement
+        r = oracle.lbfgs(lambda v: oracle.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], thetas[q]), P["GInit"])
+        assert rel(out[q][4], r["fx"]) < (1e-8 if r["iterations"] < 150 else 1e-4), (q, out[q][4], r["fx"])
