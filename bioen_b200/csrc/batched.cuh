@@ -543,7 +543,7 @@ class ThetaScan {
         if (k < 1 || k > kBMaxK) throw std::invalid_argument("bioen_b200: theta scan batches 1..32 problems");
         if (C.nranks > 1) throw std::invalid_argument("bioen_b200: theta scan is single-GPU in this version");
         if (!C.have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
-        if (!C.Yt.p) C.make_transposed();
+        if (!C.yt_valid) C.make_transposed();
         ldn = ((long long)n + 63) & ~63LL;
         const int m = prm.m;
         planes.alloc((size_t)5 * KP * ldn);

@@ -122,9 +122,33 @@ int bioen_b200_device_count(void) {
     return n;
 }
 
+// Small problems: creating a context (two dozen allocations, pinned memory, a stream) costs ~10 ms, more than a
+// whole minimisation at the ala5 size (M = 28, N = 5e4).  The last destroyed small context of a thread is kept and
+// handed out again for the same shape; nothing of the previous problem survives (reset_for_reuse), callers upload
+// their data as usual, so the stateless entry points stay stateless.
+namespace {
+constexpr size_t kCacheMaxBytes = (size_t)256 << 20;
+struct CtxCache {
+    bioen_b200_ctx* ctx = nullptr;
+    ~CtxCache() { delete ctx; }
+};
+thread_local CtxCache g_cache;
+}  // namespace
+
 bioen_b200_ctx* bioen_b200_create(int m, int n, int device) {
     bioen_b200_ctx* ctx = nullptr;
-    guarded("bioen_b200_create", [&] { ctx = new bioen_b200_ctx(m, n, device); });
+    guarded("bioen_b200_create", [&] {
+        bioen_b200_ctx* c = g_cache.ctx;
+        if (c && c->C.M == m && c->C.N == n && c->C.device == device) {
+            g_cache.ctx = nullptr;
+            CUDA_CHECK(cudaSetDevice(device));
+            c->C.reset_for_reuse();
+            c->comm.reset();
+            ctx = c;
+            return;
+        }
+        ctx = new bioen_b200_ctx(m, n, device);
+    });
     return ctx;
 }
 
@@ -132,6 +156,12 @@ void bioen_b200_destroy(bioen_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->C.device);
     cudaStreamSynchronize(ctx->C.stream);
+    const size_t bytes = (size_t)ctx->C.M * (size_t)ctx->C.N * sizeof(double);
+    if (bytes <= kCacheMaxBytes && !ctx->comm) {
+        delete g_cache.ctx;
+        g_cache.ctx = ctx;
+        return;
+    }
     delete ctx;
 }
 
@@ -607,17 +637,13 @@ namespace {
 struct TempProblem {
     bioen_b200_ctx* ctx = nullptr;
     TempProblem(int m, int n, const double* yTilde) {
-        ctx = new bioen_b200_ctx(m, n, 0);
+        ctx = bioen_b200_create(m, n, 0);
+        if (!ctx) throw std::runtime_error(g_last_error);
         if (yTilde) {
             ctx->C.upload_matrix(yTilde, (size_t)n);
         }
     }
-    ~TempProblem() {
-        if (ctx) {
-            cudaStreamSynchronize(ctx->C.stream);
-            delete ctx;
-        }
-    }
+    ~TempProblem() { bioen_b200_destroy(ctx); }
 };
 }  // namespace
 

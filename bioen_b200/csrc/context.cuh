@@ -45,6 +45,11 @@ struct DevBuf {
             CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
         }
     }
+    // keep the allocation when the size is unchanged (contents are left as they are: callers that rely on zero
+    // padding only ever write the unpadded part)
+    void ensure(size_t count) {
+        if (count != n || !p) alloc(count);
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -102,7 +107,7 @@ class Context {
     long long ldt = 0, f_nslab = 0, f_chunk = 0;
     int f_C = 0, f_stages = 0, f_grid = 0, f_KI = 0, f_smem = 0, f_T = 1, f_rows = 0, f_rows_per_cta = 1;
     bool f_team = false;
-    bool fused_ready = false;
+    bool fused_ready = false, yt_valid = false;
     bool allow_fused = true;   // bioen_b200_set_option: 0 forces the four-pass tile kernels
     double theta = 0.0;
     bool have_logw = false, have_forces = false;
@@ -168,6 +173,20 @@ class Context {
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 
+    // forget the problem but keep every allocation (stateless reference entry points reuse a cached context)
+    void reset_for_reuse() {
+        sync();
+        have_logw = have_forces = false;
+        fused_ready = false;
+        yt_valid = false;
+        allow_fused = true;
+        comm = nullptr;
+        nranks = 1;
+        N_total = N;
+        Y = nullptr;
+        passes_launched = kernels_launched = 0;
+        pass_timing = false;
+    }
     void set_comm(Comm* c) {
         comm = c;
         nranks = c ? c->nranks : 1;
@@ -177,9 +196,11 @@ class Context {
     // ---- matrix -------------------------------------------------------------------------------
     void upload_matrix(const double* host, size_t ld_host) {
         ld = round_up(N, 16);
-        Yown.release();
-        CUDA_CHECK(cudaMalloc(&Yown.p, (size_t)M * ld * sizeof(double)));
-        Yown.n = (size_t)M * ld;
+        if (Yown.n != (size_t)M * ld || !Yown.p) {
+            Yown.release();
+            CUDA_CHECK(cudaMalloc(&Yown.p, (size_t)M * ld * sizeof(double)));
+            Yown.n = (size_t)M * ld;
+        }
         Y = Yown.p;
         if (ld != N) CUDA_CHECK(cudaMemsetAsync(Y, 0, (size_t)M * ld * sizeof(double), stream));
         sync();
@@ -279,7 +300,7 @@ class Context {
             throw CudaError(buf);
         }
         fused_ready = false;   // the structure-major copy (if any) belongs to the previous matrix
-        Yt.release();
+        yt_valid = false;
         // a matrix that fits in L2 with room to spare is kept there between the two passes
         evict_first = ((double)M * (double)ld * 8.0 > 80.0e6) ? 1 : 0;
     }
@@ -301,9 +322,9 @@ class Context {
 
     // logw: reference log-weights G (this rank's slice); log s0 = log sum_j exp(G_j) over ALL ranks
     void set_logw(const double* G_host, bool on_device = false) {
-        Gv.alloc(N);
+        Gv.ensure(Npad + 8);
         if (on_device) d2d(Gv.p, G_host, N); else h2d(Gv.p, G_host, N);
-        aux_n.alloc(Npad);  // scratch x for the lse of G
+        aux_n.ensure(Npad + 8);  // scratch x for the lse of G
         d2d(aux_n.p, Gv.p, N);
         launch_lse(aux_n.p, nullptr, nullptr, 0.0, nullptr, false);
         gather_lse();
@@ -324,10 +345,10 @@ class Context {
     }
     // forces: reference weights w0 (this rank's slice)
     void set_forces(const double* w0_host, bool on_device = false) {
-        Gv.alloc(Npad + 8);      // holds w0
+        Gv.ensure(Npad + 8);      // holds w0
         if (on_device) d2d(Gv.p, w0_host, N); else h2d(Gv.p, w0_host, N);
-        aux_n.alloc(Npad + 8);   // x_j, later E_j (zero padded: it feeds the row pass)
-        aux_n2.alloc(Npad + 8);  // lr_j
+        aux_n.ensure(Npad + 8);   // x_j, later E_j (zero padded: it feeds the row pass)
+        aux_n2.ensure(Npad + 8);  // lr_j
         have_forces = true;
         if (allow_fused && Y && !fused_ready) prepare_fused();
     }
@@ -341,9 +362,12 @@ class Context {
     void make_transposed() {
         if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         ldt = (M + 1LL) & ~1LL;
-        Yt.release();
-        CUDA_CHECK(cudaMalloc(&Yt.p, (size_t)N * ldt * sizeof(double)));
-        Yt.n = (size_t)N * ldt;
+        if (Yt.n != (size_t)N * ldt || !Yt.p) {
+            Yt.release();
+            CUDA_CHECK(cudaMalloc(&Yt.p, (size_t)N * ldt * sizeof(double)));
+            Yt.n = (size_t)N * ldt;
+        }
+        yt_valid = true;
         dim3 grid((unsigned)((N + 31) / 32), (unsigned)((ldt + 31) / 32));
         k_transpose<<<grid, 256, 0, stream>>>(Y, ld, M, N, Yt.p, ldt);
         CUDA_CHECK(cudaGetLastError());
@@ -378,14 +402,14 @@ class Context {
             }
         }
         if (!f_team) return;   // does not fit shared memory (M > ~5500): the four-pass tile kernels are used
-        if (!Yt.p) make_transposed();
+        if (!yt_valid) make_transposed();
         f_nslab = ((long long)N + f_C - 1) / f_C;
         f_grid = (int)std::min<long long>(num_sms, f_nslab);
         f_chunk = (f_nslab + f_grid - 1) / f_grid;
         f_grid = (int)((f_nslab + f_chunk - 1) / f_chunk);
         f_rows = f_grid * f_rows_per_cta;
-        fpart.alloc((size_t)f_rows * Mpad);
-        flse.alloc((size_t)2 * f_rows);
+        fpart.ensure((size_t)f_rows * Mpad);
+        flse.ensure((size_t)2 * f_rows);
         set_fused_attr();
         fused_ready = true;
     }
