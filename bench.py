@@ -425,16 +425,22 @@ def run_theta_scan(args):
     a, YT = observations(M)
     prob = bioen_b200.Problem(shape=(M, N), device=0)
     prob.generate(SEED, 0, a, SIG_SIM / SIG_EXP)
-    prob.set_logw(np.zeros(N), YT, THETA)
+    forces = args.method == "forces"
+    meth = 1 if forces else 0
+    nvar = M if forces else N
+    if forces:
+        prob.set_forces(np.full(N, 1.0 / N), YT, THETA)
+    else:
+        prob.set_logw(np.zeros(N), YT, THETA)
     thetas = np.geomspace(1e3, 1e-1, K)
     rng = np.random.default_rng(SEED + 7)
-    X0 = np.ascontiguousarray(0.1 * rng.standard_normal((K, N)))
+    X0 = np.ascontiguousarray((1e-3 if forces else 0.1) * rng.standard_normal((K, nvar)))
     lib = _lib.load()
     peak_tf = ctypes.c_double()
     _lib.check(lib.bioen_b200_dmma_peak(0, ctypes.byref(peak_tf)), "dmma_peak")
     ms, gemm_ms, launches = ctypes.c_float(), ctypes.c_float(), ctypes.c_longlong()
     with ClockSampler(0) as clk:
-        _lib.check(lib.bioen_b200_time_scan_evals(prob._h, K, _lib.ptr(thetas), _lib.ptr(X0), args.warmup, args.steps,
+        _lib.check(lib.bioen_b200_time_scan_evals(prob._h, meth, K, _lib.ptr(thetas), _lib.ptr(X0), args.warmup, args.steps,
                                                   ctypes.byref(ms), ctypes.byref(gemm_ms), ctypes.byref(launches)),
                    "time_scan_evals")
     KP = (K + 7) // 8 * 8
@@ -443,11 +449,11 @@ def run_theta_scan(args):
     hbm_peak, _ = measured_peak()
     line = {
         "metric": "theta_scan_problem_evals_per_s", "value": K * args.steps / (ms.value * 1e-3),
-        "unit": "f+g evaluations/s summed over K problems (logw, N=%d x M=%d each)" % (N, M), "n_gpus": 1,
+        "unit": "f+g evaluations/s summed over K problems (%s, N=%d x M=%d each)" % (args.method, N, M), "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.value / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "theta L-curve scan, K=%d theta values batched, N=%d x M=%d, skinny fp64 GEMMs on "
-                               "tensor cores (DMMA)" % (K, N, M), "K": K, "l2": "inputs (%.1f GB) larger than L2"
+        "config": {"workload": "theta L-curve scan (%s method), K=%d theta values batched, N=%d x M=%d, skinny fp64 "
+                               "GEMMs on tensor cores (DMMA)" % (args.method, K, N, M), "K": K, "method": args.method, "l2": "inputs (%.1f GB) larger than L2"
                                                                                  % (M * N * 8 / 1e9)},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
                      "frac": ach / peak_tf.value, "traffic": None,
@@ -460,7 +466,7 @@ def run_theta_scan(args):
     }
     if not args.no_optimum:
         t0 = time.perf_counter()
-        X, fmin, codes, info = prob.theta_scan(thetas, x0=np.zeros(N))
+        X, fmin, codes, info = prob.theta_scan(thetas, x0=np.zeros(nvar))
         line["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "rounds": info["rounds"],
                                    "codes": [int(c) for c in codes], "iterations": [int(i) for i in info["iterations"]],
                                    "evaluations_total": int(info["evaluations"].sum()),

@@ -84,9 +84,9 @@ SIGNATURES = {
     "bioen_b200_forces_from_weights": (C.c_int, [_vp, _dp, _dp, _dp]),
     "bioen_b200_opt_lbfgs": (C.c_int, [_vp, C.c_int, _dp, _dp, lbfgs_config_params, visual_params, _dp, _ip]),
     "bioen_b200_opt_gsl": (C.c_int, [_vp, C.c_int, _dp, _dp, gsl_config_params, visual_params, _dp, _ip]),
-    "bioen_b200_theta_scan": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, lbfgs_config_params, visual_params, _dp, _ip,
-                                        _ip, _dp]),
-    "bioen_b200_time_scan_evals": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int, C.POINTER(C.c_float),
+    "bioen_b200_theta_scan": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, lbfgs_config_params, visual_params, _dp,
+                                        _ip, _ip, _dp]),
+    "bioen_b200_time_scan_evals": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "bioen_b200_dmma_peak": (C.c_int, [C.c_int, _dp]),
     "bioen_b200_nccl_unique_id": (C.c_int, [C.c_char_p]),

@@ -204,8 +204,15 @@ struct BatchBufs {
     double* partials;           // [KP][pstride]
     unsigned int* ticket;       // [KP]
     long long pstride;
-    const double* G;            // shared reference log-weights
+    const double* G;            // shared reference log-weights (logw) / reference weights w0 (forces)
     const double* Yobs;
+    // forces scan only: the variables are M-dimensional planes; these are the structure-axis work planes
+    int nN = 0;                 // structures
+    long long ldN = 0;
+    double *Xn = nullptr, *LR = nullptr, *Tn = nullptr;   // [KP][ldN]: x_j = (Yt f)_j, log(w_j/w0_j), t_j
+    double* Ff = nullptr;       // fragment-major forces (index = i)
+    double* avgk = nullptr;     // [KP][ldo]
+    long long ldo = 0;
 };
 
 __global__ void __launch_bounds__(kVecThreads) kb_update_lse(const BatchBufs b, const KVec p, int move) {
@@ -433,6 +440,180 @@ __global__ void __launch_bounds__(kVecThreads) kb_twoloop(const BatchBufs b, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// forces method, batched (c_bioen_kernels_forces.c:43-76 for K problems at once).  The variables f_k are
+// M-dimensional planes; one batched evaluation is four skinny GEMMs:
+//   X = Yt.F  ->  softmax with prior weights  ->  avg = Y.W  ->  T = Yt.R  ->  E  ->  grad = Y.E - avg*sum(E)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kbf_prepare(const BatchBufs b, const KVec p, int move) {
+    const int k = blockIdx.x;
+    if (!p.mask[k]) return;
+    __shared__ double red[32];
+    double* x = b.X + (size_t)k * b.ldn;
+    const double* xp = b.XP + (size_t)k * b.ldn;
+    const double* d = b.D + (size_t)k * b.ldn;
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < b.n; i += blockDim.x) {
+        double xi = x[i];
+        if (move) { xi = fma(p.stp[k], d[i], xp[i]); x[i] = xi; }
+        b.Ff[frag_index(i, k, b.NT)] = xi;
+        v[0] = fma(xi, xi, v[0]);
+    }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) b.scb[(size_t)k * SC_COUNT + SC_XNORM2] = v[0];
+}
+
+__global__ void __launch_bounds__(kVecThreads) kbf_lse(const BatchBufs b, const KVec p) {
+    const int k = blockIdx.y;
+    if (!p.mask[k]) return;
+    __shared__ double red[3 * 32];
+    __shared__ bool is_last;
+    const double* x = b.Xn + (size_t)k * b.ldN;
+    double m = -DBL_MAX, s = 0.0, dummy = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < b.nN; j += gridDim.x * blockDim.x) {
+        const double v = x[j], pw = b.G[j];
+        if (v > m) { s = s * exp(m - v) + pw; m = v; }
+        else s += pw * exp(v - m);
+    }
+    double* partials = b.partials + (size_t)k * b.pstride;
+    block_lse(m, s, dummy, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x * 2 + 0] = m;
+        partials[blockIdx.x * 2 + 1] = s;
+        __threadfence();
+        is_last = (atomicAdd(b.ticket + k, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        m = -DBL_MAX; s = 0.0; dummy = 0.0;
+        for (unsigned q = threadIdx.x; q < gridDim.x; q += blockDim.x)
+            lse_merge(m, s, __ldcg(&partials[q * 2]), __ldcg(&partials[q * 2 + 1]));
+        block_lse(m, s, dummy, red);
+        if (threadIdx.x == 0) {
+            double* sc = b.scb + (size_t)k * SC_COUNT;
+            sc[SC_GMAX] = m;
+            sc[SC_S] = s;
+            b.ticket[k] = 0;
+        }
+    }
+}
+
+// weights (fragment-major), guarded log ratio, KL   (c_bioen_kernels_forces.c:156-171, 246-274)
+__global__ void __launch_bounds__(kVecThreads) kbf_weights(const BatchBufs b, const KVec p) {
+    const int k = blockIdx.y;
+    if (!p.mask[k]) return;
+    __shared__ double red[32];
+    double* sc = b.scb + (size_t)k * SC_COUNT;
+    const double M = sc[SC_GMAX], inv = 1.0 / sc[SC_S], logS = log(sc[SC_S]);
+    const double* x = b.Xn + (size_t)k * b.ldN;
+    double* lrp = b.LR + (size_t)k * b.ldN;
+    double v[1] = {0.0};
+    const int nq = (b.nN + 3) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        double w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            double w = 0.0;
+            if (j < b.nN) {
+                const double xj = x[j], w0 = b.G[j];
+                w = inv * (w0 * exp(xj - M));
+                const double lr = (w >= DBL_MIN && w0 >= DBL_MIN) ? (xj - M - logS) : 0.0;
+                lrp[j] = lr;
+                v[0] = fma(lr, w, v[0]);
+            }
+            w4[e] = w;
+        }
+        double* dst = b.Wf + ((size_t)q * b.NT + (k >> 3)) * 32 + (k & 7) * 4;
+        *reinterpret_cast<double2*>(dst) = make_double2(w4[0], w4[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(w4[2], w4[3]);
+    }
+    grid_sum<1>(v, b.partials + (size_t)k * b.pstride, b.ticket + k, red, [=](const double(&t)[1]) { sc[SC_KL] = t[0]; });
+}
+
+// avg, r (fragment-major), chi^2, objective = theta KL + chi^2   (one block per problem)
+__global__ void __launch_bounds__(1024) kbf_finalize(const BatchBufs b, const KVec p, int m, int nseg) {
+    const int k = blockIdx.x;
+    if (!p.mask[k]) return;
+    __shared__ double red[32];
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nseg; ++q) s += b.avgp[((size_t)q * b.KP + k) * b.ldo + i];
+        b.avgk[(size_t)k * b.ldo + i] = s;
+        const double r = s - b.Yobs[i];
+        b.Rf[frag_index(i, k, b.NT)] = r;
+        v[0] = fma(r, r, v[0]);
+    }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) {
+        double* sc = b.scb + (size_t)k * SC_COUNT;
+        const double chi2 = 0.5 * v[0], prior = sc[SC_KL] * p.theta[k];
+        sc[SC_CHI2] = chi2;
+        sc[SC_PRIOR] = prior;
+        sc[SC_F] = prior + chi2;
+    }
+}
+
+// E_j = (theta (1 + lr_j) + t_j) w_j in fragment-major order, and sum_j E_j   (kernels_forces.c:321-328)
+__global__ void __launch_bounds__(kVecThreads) kbf_E(const BatchBufs b, const KVec p) {
+    const int k = blockIdx.y;
+    if (!p.mask[k]) return;
+    __shared__ double red[32];
+    double* sc = b.scb + (size_t)k * SC_COUNT;
+    const double M = sc[SC_GMAX], inv = 1.0 / sc[SC_S], theta = p.theta[k];
+    const double* x = b.Xn + (size_t)k * b.ldN;
+    const double* lrp = b.LR + (size_t)k * b.ldN;
+    const double* t = b.Tn + (size_t)k * b.ldN;
+    double v[1] = {0.0};
+    const int nq = (b.nN + 3) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        double e4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * q + e;
+            double E = 0.0;
+            if (j < b.nN) {
+                const double w = inv * (b.G[j] * exp(x[j] - M));
+                E = ((1.0 + lrp[j]) * theta + t[j]) * w;
+                v[0] += E;
+            }
+            e4[e] = E;
+        }
+        double* dst = b.Wf + ((size_t)q * b.NT + (k >> 3)) * 32 + (k & 7) * 4;
+        *reinterpret_cast<double2*>(dst) = make_double2(e4[0], e4[1]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(e4[2], e4[3]);
+    }
+    grid_sum<1>(v, b.partials + (size_t)k * b.pstride, b.ticket + k, red,
+                [=](const double(&t)[1]) { sc[SC_TMP0 + 1] = t[0]; });
+}
+
+// grad_i = sum_j y_ij E_j - avg_i sum_j E_j, plus grad.d and ||grad||^2   (one block per problem)
+__global__ void __launch_bounds__(1024) kbf_grad(const BatchBufs b, const KVec p, int m, int nseg) {
+    const int k = blockIdx.x;
+    if (!p.mask[k]) return;
+    __shared__ double red[2 * 32];
+    double* sc = b.scb + (size_t)k * SC_COUNT;
+    const double sumE = sc[SC_TMP0 + 1];
+    double* gr = b.Gr + (size_t)k * b.ldn;
+    const double* d = b.D + (size_t)k * b.ldn;
+    double v[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nseg; ++q) s += b.avgp[((size_t)q * b.KP + k) * b.ldo + i];
+        const double gv = s - b.avgk[(size_t)k * b.ldo + i] * sumE;
+        gr[i] = gv;
+        v[0] = fma(gv, d[i], v[0]);
+        v[1] = fma(gv, gv, v[1]);
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) {
+        sc[SC_DG] = v[0];
+        sc[SC_GNORM2] = v[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // line searches of liblbfgs as resumable state machines: prepare() -> step to evaluate, update(f, dg) -> verdict
 // (same arithmetic and order of tests as Lbfgs::linesearch_* in lbfgs.cuh / lbfgs.c:645-1001)
 // ------------------------------------------------------------------------------------------------
@@ -525,11 +706,14 @@ struct ScanResult {
 class ThetaScan {
    public:
     Context& C;
-    const int K, KP, NT, n;
+    const bool forces;          // false: log-weights (variables = N planes), true: forces (variables = M planes)
+    const int K, KP, NT, n;     // n = dimension of the variables
+    const int NN, MM;           // structures, observables
     LbfgsParams prm;
     int verbose = 0;
-    long long ldn;
-    DevBuf<double> planes, hist, Wf, Rf, avgp, scb, partials;
+    long long ldn, ldN;
+    DevBuf<double> planes, hist, Wf, Rf, avgp, scb, partials, nplanes, Ff, avgk;
+    int vblocksN = 1;
     DevBuf<unsigned int> ticket;
     double* h_scb = nullptr;
     BatchBufs B{};
@@ -538,36 +722,40 @@ class ThetaScan {
     int vblocks;
     long long rounds = 0, gemm_launches = 0;
 
-    ThetaScan(Context& ctx, int k, const LbfgsParams& p)
-        : C(ctx), K(k), KP((k + 7) & ~7), NT(((k + 7) & ~7) / 8), n(ctx.N), prm(p) {
+    ThetaScan(Context& ctx, int k, const LbfgsParams& p, bool is_forces = false)
+        : C(ctx), forces(is_forces), K(k), KP((k + 7) & ~7), NT(((k + 7) & ~7) / 8),
+          n(is_forces ? ctx.M : ctx.N), NN(ctx.N), MM(ctx.M), prm(p) {
         if (k < 1 || k > kBMaxK) throw std::invalid_argument("bioen_b200: theta scan batches 1..32 problems");
         if (C.nranks > 1) throw std::invalid_argument("bioen_b200: theta scan is single-GPU in this version");
-        if (!C.have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
+        if (!forces && !C.have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
+        if (forces && !C.have_forces) throw std::logic_error("bioen_b200: forces data not set");
         if (!C.yt_valid) C.make_transposed();
         ldn = ((long long)n + 63) & ~63LL;
+        ldN = ((long long)NN + 63) & ~63LL;
         const int m = prm.m;
         planes.alloc((size_t)5 * KP * ldn);
         hist.alloc((size_t)2 * m * KP * ldn);
-        const long long nq = ((long long)n + 15) / 16 * 16;           // indices padded to whole GEMM tiles
-        const long long mq = ((long long)C.M + 15) / 16 * 16;
+        const long long nq = ((long long)NN + 15) / 16 * 16;          // indices padded to whole GEMM tiles
+        const long long mq = ((long long)MM + 15) / 16 * 16;
         Wf.alloc((size_t)nq * KP);
         Rf.alloc((size_t)mq * KP);
         scb.alloc((size_t)KP * SC_COUNT);
         vblocks = std::max(1, std::min((n + kVecThreads - 1) / kVecThreads, C.num_sms * 2));
-        const long long pstride = (long long)vblocks * 4 + 16;
+        vblocksN = std::max(1, std::min((NN + kVecThreads - 1) / kVecThreads, C.num_sms * 2));
+        const long long pstride = (long long)std::max(vblocks, vblocksN) * 4 + 16;
         partials.alloc((size_t)KP * pstride);
         ticket.alloc(KP);
         CUDA_CHECK(cudaHostAlloc(&h_scb, (size_t)KP * SC_COUNT * sizeof(double), cudaHostAllocDefault));
         // GEMM geometry
-        gRow.rows = C.M; gRow.kdim = n; gRow.RB = (C.M + kGRows - 1) / kGRows; gRow.ktiles = (n + kGKdim - 1) / kGKdim;
+        gRow.rows = MM; gRow.kdim = NN; gRow.RB = (MM + kGRows - 1) / kGRows; gRow.ktiles = (NN + kGKdim - 1) / kGKdim;
         gRow.S = std::max(1, std::min(gRow.ktiles, C.num_sms / gRow.RB));
         gRow.tps = (gRow.ktiles + gRow.S - 1) / gRow.S;
         gRow.S = (gRow.ktiles + gRow.tps - 1) / gRow.tps;
         gRow.KP = KP; gRow.ldo = ((long long)C.M + 3) & ~3LL; gRow.evict_first = C.evict_first;
         avgp.alloc((size_t)gRow.S * KP * gRow.ldo);
         gRow.B = Wf.p; gRow.out = avgp.p;
-        gCol.rows = n; gCol.kdim = C.M; gCol.RB = (n + kGRows - 1) / kGRows; gCol.ktiles = (C.M + kGKdim - 1) / kGKdim;
-        gCol.S = 1; gCol.tps = gCol.ktiles; gCol.KP = KP; gCol.ldo = ldn; gCol.evict_first = C.evict_first;
+        gCol.rows = NN; gCol.kdim = MM; gCol.RB = (NN + kGRows - 1) / kGRows; gCol.ktiles = (MM + kGKdim - 1) / kGKdim;
+        gCol.S = 1; gCol.tps = gCol.ktiles; gCol.KP = KP; gCol.ldo = ldN; gCol.evict_first = C.evict_first;
         gCol.B = Rf.p;
         B.n = n; B.K = K; B.KP = KP; B.NT = NT; B.ldn = ldn;
         B.X = planes.p; B.Gr = B.X + (size_t)KP * ldn; B.XP = B.Gr + (size_t)KP * ldn;
@@ -575,14 +763,22 @@ class ThetaScan {
         B.S = hist.p; B.Yv = hist.p + (size_t)m * KP * ldn;
         B.Wf = Wf.p; B.Rf = Rf.p; B.avgp = avgp.p; B.scb = scb.p; B.partials = partials.p; B.ticket = ticket.p;
         B.pstride = pstride; B.G = C.Gv.p; B.Yobs = C.Yobs.p;
-        gCol.out = B.Gr;
-        make_map(&tmapRow, C.Y, (cuuint64_t)n, (cuuint64_t)C.M, (cuuint64_t)C.ld);
-        make_map(&tmapCol, C.Yt.p, (cuuint64_t)C.M, (cuuint64_t)n, (cuuint64_t)C.ldt);
+        gCol.out = B.Gr;          // logw: the column pass writes straight into the gradient planes (ldn == ldN)
+        if (forces) {
+            nplanes.alloc((size_t)3 * KP * ldN);
+            Ff.alloc((size_t)mq * KP);
+            avgk.alloc((size_t)KP * gRow.ldo);
+            B.nN = NN; B.ldN = ldN; B.Xn = nplanes.p; B.LR = B.Xn + (size_t)KP * ldN; B.Tn = B.LR + (size_t)KP * ldN;
+            B.Ff = Ff.p; B.avgk = avgk.p;
+        }
+        B.ldo = gRow.ldo;
+        make_map(&tmapRow, C.Y, (cuuint64_t)NN, (cuuint64_t)MM, (cuuint64_t)C.ld);
+        make_map(&tmapCol, C.Yt.p, (cuuint64_t)MM, (cuuint64_t)NN, (cuuint64_t)C.ldt);
         set_attr();
         // log s0 is a property of G: copy it into every problem's scalar row
         std::vector<double> row((size_t)KP * SC_COUNT, 0.0);
         double logs0 = 0.0;
-        C.d2h(&logs0, C.sc.p + SC_LOGS0, 1);
+        if (!forces) C.d2h(&logs0, C.sc.p + SC_LOGS0, 1);
         C.sync();
         for (int q = 0; q < KP; ++q) row[(size_t)q * SC_COUNT + SC_LOGS0] = logs0;
         C.h2d(scb.p, row.data(), row.size());
@@ -628,6 +824,25 @@ class ThetaScan {
 
     // one batched f+g evaluation of the masked problems; move: x = xp + stp*d first
     void evaluate(const KVec& kv, bool move) {
+        if (forces) {
+            const dim3 gridN(vblocksN, KP);
+            GemmArgs g = gCol;
+            kbf_prepare<<<KP, 256, 0, C.stream>>>(B, kv, move ? 1 : 0);
+            g.B = Ff.p; g.out = B.Xn;
+            launch_gemm(tmapCol, g);                                   // x_j = sum_i f_i y_ij
+            kbf_lse<<<gridN, kVecThreads, 0, C.stream>>>(B, kv);
+            kbf_weights<<<gridN, kVecThreads, 0, C.stream>>>(B, kv);
+            launch_gemm(tmapRow, gRow);                                // avg_i
+            kbf_finalize<<<KP, 1024, 0, C.stream>>>(B, kv, MM, gRow.S);
+            g.B = Rf.p; g.out = B.Tn;
+            launch_gemm(tmapCol, g);                                   // t_j = sum_i r_i y_ij
+            kbf_E<<<gridN, kVecThreads, 0, C.stream>>>(B, kv);
+            launch_gemm(tmapRow, gRow);                                // sum_j y_ij E_j
+            kbf_grad<<<KP, 1024, 0, C.stream>>>(B, kv, MM, gRow.S);
+            CUDA_CHECK(cudaGetLastError());
+            C.kernels_launched += 6;
+            return;
+        }
         const dim3 gridv(vblocks, KP);
         kb_update_lse<<<gridv, kVecThreads, 0, C.stream>>>(B, kv, move ? 1 : 0);
         kb_weights<<<gridv, kVecThreads, 0, C.stream>>>(B, kv);

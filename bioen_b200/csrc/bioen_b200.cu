@@ -432,14 +432,15 @@ int bioen_b200_opt_gsl(bioen_b200_ctx* ctx, int method, const double* x0_host, d
     return ret;
 }
 
-int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int K, const double* thetas, const double* x0_host, double* x_host,
+int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int method, int K, const double* thetas, const double* x0_host,
+                          double* x_host,
                           lbfgs_config_params config, visual_params visual, double* fmin, int* codes, int* info,
                           double* stats) {
     return guarded("bioen_b200_theta_scan", [&] {
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         const auto t0 = std::chrono::steady_clock::now();
-        ThetaScan scan(C, K, to_params(config));
+        ThetaScan scan(C, K, to_params(config), method == BIOEN_B200_FORCES);
         scan.verbose = (int)visual.verbose;
         const std::vector<ScanResult> res = scan.run(thetas, x0_host, x_host);
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -463,12 +464,12 @@ int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int K, const double* thetas, cons
     });
 }
 
-int bioen_b200_time_scan_evals(bioen_b200_ctx* ctx, int K, const double* thetas, const double* x0_host, int warmup,
-                               int steps, float* ms, float* gemm_ms, long long* launches) {
+int bioen_b200_time_scan_evals(bioen_b200_ctx* ctx, int method, int K, const double* thetas, const double* x0_host,
+                               int warmup, int steps, float* ms, float* gemm_ms, long long* launches) {
     return guarded("bioen_b200_time_scan_evals", [&] {
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
-        ThetaScan scan(C, K, LbfgsParams());
+        ThetaScan scan(C, K, LbfgsParams(), method == BIOEN_B200_FORCES);
         scan.time_evals(thetas, x0_host, warmup, steps, ms, gemm_ms, launches);
     });
 }

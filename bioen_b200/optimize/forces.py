@@ -8,9 +8,9 @@ import numpy as np
 
 from . import common
 from .ext import c_bioen
-from .log_weights import _minimize_on_device, _run_scipy
+from .log_weights import _lbfgs_kwargs, _minimize_on_device, _run_scipy
 from .. import _lib
-from ..problem import FORCES, Problem
+from ..problem import FORCES, LBFGS_OK, Problem, lbfgs_strerror
 
 
 # ---- synthetic "generic data" generators (forces.py:19-68) -------------------------------------------------
@@ -153,3 +153,56 @@ def find_optimum(forcesInit, w0, y, yTilde, YTilde, theta, cfg, problem=None):
         print("fmin_final    = ", fmin_final)
         print("========================")
     return wopt, yopt, forces_opt, fmin_initial, fmin_final, chiSqr, S
+
+
+def find_optimum_series(forcesInit, w0, y, yTilde, YTilde, thetas, cfg, batched=True, problem=None):
+    """The theta series (L-curve) of the reference's callers (bioen/analyze/procedure.py:62-83; the ala5 notebook
+    runs exactly this with the forces method and liblbfgs) on ONE resident copy of yTilde.  Not in the reference API.
+
+    batched=True (minimizer 'lbfgs'): up to 32 theta values are minimised together from forcesInit (lockstep
+    device L-BFGS, four tensor-core GEMMs per batched evaluation).  batched=False: one find_optimum per theta,
+    warm-started from the previous optimum.  Returns a list of find_optimum 7-tuples in input order.
+    """
+    check_params_forces(forcesInit, w0, y, yTilde, YTilde)
+    thetas = [float(t) for t in np.asarray(thetas, dtype=np.float64).ravel()]
+    own = problem is None
+    if own:
+        problem = Problem(yTilde)
+    out = []
+    try:
+        if batched and cfg["minimizer"].upper() in ("LIBLBFGS", "LBFGS"):
+            problem.set_forces(w0, YTilde, thetas[0] if thetas else 0.0)
+            f0 = _lib.vec(forcesInit)
+            w0v, Yv = _lib.vec(w0), _lib.vec(YTilde)
+            yprob = problem if y is yTilde else Problem(y)
+            try:
+                for lo in range(0, len(thetas), 32):
+                    chunk = thetas[lo:lo + 32]
+                    X, fmin, codes, _ = problem.theta_scan(chunk, x0=f0, method=FORCES, verbose=cfg["verbose"],
+                                                           **_lbfgs_kwargs(cfg))
+                    for q, th in enumerate(chunk):
+                        if codes[q] not in LBFGS_OK:
+                            raise RuntimeError("{}, liblbfgs return code: {}:{}".format(
+                                "bioen_opt_lbfgs_forces", codes[q], lbfgs_strerror(codes[q])))
+                        problem.set_theta(th)
+                        fmin_initial = problem.objective(f0, FORCES)
+                        w, _ = problem.weights(X[q], FORCES)
+                        yavg = problem.average(w)
+                        ind = w > 0
+                        S = float(np.log(w[ind] / w0v[ind]) @ w[ind])
+                        r = yavg - Yv
+                        out.append((w.reshape(-1, 1), yavg if y is yTilde else yprob.average(w), X[q].copy(),
+                                    fmin_initial, float(fmin[q]), 0.5 * float(r @ r), S))
+            finally:
+                if yprob is not problem:
+                    yprob.close()
+        else:
+            f = forcesInit
+            for th in thetas:
+                res = find_optimum(f, w0, y, yTilde, YTilde, th, cfg, problem=problem)
+                out.append(res)
+                f = res[2].reshape(-1, 1)
+    finally:
+        if own:
+            problem.close()
+    return out

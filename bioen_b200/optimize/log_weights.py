@@ -245,7 +245,7 @@ def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, 
             try:
                 for lo in range(0, len(thetas), 32):
                     chunk = thetas[lo:lo + 32]
-                    X, fmin, codes, _ = problem.theta_scan(chunk, x0=g0, verbose=cfg["verbose"], **_lbfgs_kwargs(cfg))
+                    X, fmin, codes, _ = problem.theta_scan(chunk, x0=g0, method=LOGW, verbose=cfg["verbose"], **_lbfgs_kwargs(cfg))
                     for q, th in enumerate(chunk):
                         if codes[q] not in LBFGS_OK:
                             raise RuntimeError("{}, liblbfgs return code: {}:{}".format(

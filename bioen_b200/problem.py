@@ -205,27 +205,31 @@ class Problem:
             raise RuntimeError("bioen_b200_opt_gsl failed: " + _lib.last_error())
         return x, fmin.value, code, dict(iterations=info[0], gradient_evaluations=info[1], f_only_evaluations=info[2])
 
-    def theta_scan(self, thetas, x0=None, verbose=0, **cfg):
-        """Minimise the log-weights problem for up to 32 theta values TOGETHER (lockstep L-BFGS, batched fp64
-        tensor-core evaluations).  x0: (n,) shared start or (K, n).  Returns (X (K, n), fmin (K,), codes (K,),
-        info dict).  Call set_logw first (its theta is ignored)."""
+    def theta_scan(self, thetas, x0=None, method=None, verbose=0, **cfg):
+        """Minimise the problem for up to 32 theta values TOGETHER (lockstep L-BFGS, batched fp64 tensor-core
+        evaluations).  x0: (n,) shared start or (K, n), n = N for log-weights, M for forces.  Returns
+        (X (K, n), fmin (K,), codes (K,), info dict).  Call set_logw / set_forces first (their theta is ignored)."""
+        method = self.method if method is None else method
+        if method is None:
+            raise RuntimeError("theta_scan: log-weights data not set / forces data not set (call set_logw or "
+                               "set_forces first)")
+        n = self._dim(method)
         thetas = _lib.vec(thetas)
         K = thetas.size
         if x0 is None:
-            x0 = np.zeros(self.n)
+            x0 = np.zeros(n)
         x0 = np.asarray(x0, dtype=np.float64)
-        X0 = np.ascontiguousarray(np.broadcast_to(x0.reshape(-1, self.n) if x0.size != self.n else
-                                                  x0.reshape(1, self.n), (K, self.n)))
+        X0 = np.ascontiguousarray(np.broadcast_to(x0.reshape(-1, n) if x0.size != n else x0.reshape(1, n), (K, n)))
         p = dict(LBFGS_DEFAULTS)
         p.update(cfg)
         c = _lib.lbfgs_config_params(**{k: p[k] for k, _ in _lib.lbfgs_config_params._fields_})
         v = _lib.visual_params(0, int(bool(verbose)))
-        X = np.empty((K, self.n), dtype=np.float64)
+        X = np.empty((K, n), dtype=np.float64)
         fmin = np.empty(K, dtype=np.float64)
         codes = (C.c_int * K)()
         info = (C.c_int * (2 * K))()
         stats = np.zeros(4, dtype=np.float64)
-        _lib.check(self._lib.bioen_b200_theta_scan(self._h, K, _lib.ptr(thetas), _lib.ptr(X0), _lib.ptr(X), c, v,
+        _lib.check(self._lib.bioen_b200_theta_scan(self._h, method, K, _lib.ptr(thetas), _lib.ptr(X0), _lib.ptr(X), c, v,
                                                    _lib.ptr(fmin), codes, info, _lib.ptr(stats)), "theta_scan")
         return X, fmin, np.array(codes[:]), dict(iterations=np.array(info[0::2]), evaluations=np.array(info[1::2]),
                                                  rounds=int(stats[0]), gemm_launches=int(stats[1]),

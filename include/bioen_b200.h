@@ -184,21 +184,23 @@ int bioen_b200_opt_lbfgs(bioen_b200_ctx *ctx, int method, const double *x0_host,
 int bioen_b200_opt_gsl(bioen_b200_ctx *ctx, int method, const double *x0_host, double *x_host,
                        gsl_config_params config, visual_params visual, double *fmin, int info[4]);
 
-/* theta scan (L-curve): K <= 32 log-weights problems that differ only in theta (and start point) minimised together
- * by K lockstep L-BFGS machines; every evaluation streams yTilde once for all K (fp64 tensor-core skinny GEMMs).
- * Requires bioen_b200_set_logw (its theta is ignored).  x0_host / x_host: [K][n] row-major; fmin[K]; codes[K]
+/* theta scan (L-curve): K <= 32 problems of one method that differ only in theta (and start point) minimised
+ * together by K lockstep L-BFGS machines; every pass streams yTilde once for all K (fp64 tensor-core skinny GEMMs:
+ * two per evaluation for BIOEN_B200_LOGW, four for BIOEN_B200_FORCES).  Requires bioen_b200_set_logw /
+ * bioen_b200_set_forces (their theta is ignored).  x0_host / x_host: [K][n] row-major, n = N (logw) or M (forces);
+ * fmin[K]; codes[K]
  * (liblbfgs return codes); info[2K] = {iterations, evaluations} per problem; stats[4] = {lockstep rounds, GEMM
  * launches, seconds, 0}.  The reference's counterpart is the Python loop over theta in
  * bioen/analyze/procedure.py:62-83. */
-int bioen_b200_theta_scan(bioen_b200_ctx *ctx, int K, const double *thetas, const double *x0_host, double *x_host,
-                          lbfgs_config_params config, visual_params visual, double *fmin, int *codes, int *info,
+int bioen_b200_theta_scan(bioen_b200_ctx *ctx, int method, int K, const double *thetas, const double *x0_host,
+                          double *x_host, lbfgs_config_params config, visual_params visual, double *fmin, int *codes, int *info,
                           double *stats);
 
 /* bench.py: time `steps` batched f+g evaluations of K problems (CUDA events); *gemm_ms = mean duration of one
  * skinny-GEMM launch.  bioen_b200_dmma_peak: fp64 tensor-core peak of the device, measured with a
  * register-resident mma.sync.m8n8k4.f64 loop (the roofline denominator of the GEMMs). */
-int bioen_b200_time_scan_evals(bioen_b200_ctx *ctx, int K, const double *thetas, const double *x0_host, int warmup,
-                               int steps, float *ms, float *gemm_ms, long long *launches);
+int bioen_b200_time_scan_evals(bioen_b200_ctx *ctx, int method, int K, const double *thetas, const double *x0_host,
+                               int warmup, int steps, float *ms, float *gemm_ms, long long *launches);
 int bioen_b200_dmma_peak(int device, double *tflops);
 
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */

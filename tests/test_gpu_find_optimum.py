@@ -130,3 +130,23 @@ def test_find_optimum_series_batched_and_sequential(oracle):
         # the warm-started run (the reference callers' way) stops on the same `delta` criterion from another
         # start point: same optimum to the reference's own 10 % bar, not digit for digit
         assert rel(s_[4], f1) < 1e-2
+
+
+def test_forces_find_optimum_series(oracle):
+    from bioen_b200 import optimize
+    P = oracle.synthetic_problem(28, 6000, seed=41)            # the ala5 shape class: few observables, many structures
+    cfg = _cfg("lbfgs", "", True)
+    thetas = np.geomspace(100.0, 1.0, 40)                      # two batches
+    out = optimize.forces.find_optimum_series(P["forces_init"], P["w0"], P["y"], P["yTilde"], P["YTilde"], thetas, cfg)
+    assert len(out) == 40
+    for q in (0, 20, 39):
+        wopt, yopt, fopt, f0, f1, chi2, S = out[q]
+        assert wopt.shape == (6000, 1) and yopt.shape == (28,) and fopt.shape == (28,)
+        r = oracle.lbfgs(lambda v: oracle.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], thetas[q]), np.zeros(28))
+        assert rel(f1, r["fx"]) < (1e-8 if r["iterations"] < 150 else 1e-4)
+        assert rel(thetas[q] * S + chi2, f1) < 1e-9
+        assert np.allclose(yopt, P["y"] @ wopt.ravel(), rtol=1e-12, atol=1e-12)
+    seq = optimize.forces.find_optimum_series(P["forces_init"], P["w0"], P["y"], P["yTilde"], P["YTilde"], thetas[:3],
+                                              cfg, batched=False)
+    for a, b in zip(seq, out[:3]):
+        assert rel(a[4], b[4]) < 1e-6
