@@ -99,7 +99,6 @@ __global__ void __launch_bounds__(256) k_generate(double* Y, long long ld, int m
     }
 }
 
-// x <- x + eps*dir on the device (time_evals: no two timed steps evaluate the same point)
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------------

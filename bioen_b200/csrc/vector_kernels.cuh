@@ -512,20 +512,6 @@ __global__ void __launch_bounds__(kVecThreads)
     }
 }
 
-__global__ void __launch_bounds__(kVecThreads) k_max_abs(int n, const double* x, double* out) {
-    // single block, small or rarely used
-    __shared__ double red[32];
-    double m = 0.0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmax(m, fabs(x[j]));
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
-        out[0] = m;
-    }
-}
-
 // L-BFGS: s = x - xp, y = g - gp, ys = y.s, yy = y.y; then xp <- x, gp <- g for the next iteration
 //     (liblbfgs lbfgs.c:543-555 and 462-463)
 struct PairArgs {

@@ -188,8 +188,7 @@ int bioen_b200_opt_gsl(bioen_b200_ctx *ctx, int method, const double *x0_host, d
  * together by K lockstep L-BFGS machines; every pass streams yTilde once for all K (fp64 tensor-core skinny GEMMs:
  * two per evaluation for BIOEN_B200_LOGW, four for BIOEN_B200_FORCES).  Requires bioen_b200_set_logw /
  * bioen_b200_set_forces (their theta is ignored).  x0_host / x_host: [K][n] row-major, n = N (logw) or M (forces);
- * fmin[K]; codes[K]
- * (liblbfgs return codes); info[2K] = {iterations, evaluations} per problem; stats[4] = {lockstep rounds, GEMM
+ * fmin[K]; codes[K] (liblbfgs return codes); info[2K] = {iterations, evaluations} per problem; stats[4] = {lockstep rounds, GEMM
  * launches, seconds, 0}.  The reference's counterpart is the Python loop over theta in
  * bioen/analyze/procedure.py:62-83. */
 int bioen_b200_theta_scan(bioen_b200_ctx *ctx, int method, int K, const double *thetas, const double *x0_host,
