@@ -614,6 +614,50 @@ __global__ void __launch_bounds__(1024) kbf_grad(const BatchBufs b, const KVec p
 }
 
 // ------------------------------------------------------------------------------------------------
+// N-sharded scan (one process per GPU): per-problem scalars that are sums over the structure axis are packed
+// into a contiguous buffer, all-reduced with ONE NCCL call, and unpacked; the (max, sum-exp) pairs are
+// all-gathered and merged.  slot < 0: that problem contributes nothing (finished / masked).
+// ------------------------------------------------------------------------------------------------
+struct KSlotTab {
+    int n;                          // rows used (<= 4)
+    signed char row[4];             // unpack: which buffer row feeds entry r (pack: r itself)
+    signed char slot[4][kBMaxK];
+};
+
+__global__ void kb_pack(const double* scb, double* buf, const KSlotTab t, int KP) {
+    const int k = threadIdx.x, r = blockIdx.x;
+    if (k >= KP || r >= t.n) return;
+    const int sl = t.slot[r][k];
+    buf[r * KP + k] = sl >= 0 ? scb[(size_t)k * SC_COUNT + sl] : 0.0;
+}
+
+__global__ void kb_unpack(double* scb, const double* buf, const KSlotTab t, int KP) {
+    const int k = threadIdx.x, r = blockIdx.x;
+    if (k >= KP || r >= t.n) return;
+    const int sl = t.slot[r][k];
+    if (sl >= 0) scb[(size_t)k * SC_COUNT + sl] = buf[t.row[r] * KP + k];
+}
+
+// merge the ranks' (max, sum-exp) pairs: lse_all[rank][2][KP] -> sc[k][SC_GMAX], sc[k][SC_S]
+__global__ void kb_lse_merge(double* scb, const double* lse_all, int nranks, int KP, const KVec p) {
+    const int k = threadIdx.x;
+    if (k >= KP || !p.mask[k]) return;
+    double m = lse_all[k], s = lse_all[KP + k];
+    for (int r = 1; r < nranks; ++r) lse_merge(m, s, lse_all[(size_t)r * 2 * KP + k], lse_all[(size_t)r * 2 * KP + KP + k]);
+    scb[(size_t)k * SC_COUNT + SC_GMAX] = m;
+    scb[(size_t)k * SC_COUNT + SC_S] = s;
+}
+
+// out[k][i] = sum over the reduction segments of the row-GEMM partials (the buffer that is all-reduced)
+__global__ void __launch_bounds__(256) kb_reduce_avg(const double* avgp, double* out, int m, int nseg, int KP, long long ldo) {
+    const int k = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double s = 0.0;
+    for (int q = 0; q < nseg; ++q) s += avgp[((size_t)q * KP + k) * ldo + i];
+    out[(size_t)k * ldo + i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // line searches of liblbfgs as resumable state machines: prepare() -> step to evaluate, update(f, dg) -> verdict
 // (same arithmetic and order of tests as Lbfgs::linesearch_* in lbfgs.cuh / lbfgs.c:645-1001)
 // ------------------------------------------------------------------------------------------------
@@ -712,8 +756,9 @@ class ThetaScan {
     LbfgsParams prm;
     int verbose = 0;
     long long ldn, ldN;
-    DevBuf<double> planes, hist, Wf, Rf, avgp, scb, partials, nplanes, Ff, avgk;
+    DevBuf<double> planes, hist, Wf, Rf, avgp, scb, partials, nplanes, Ff, avgk, redbuf, lsebuf, lse_all;
     int vblocksN = 1;
+    bool reduce = false;        // N sharded over ranks
     DevBuf<unsigned int> ticket;
     double* h_scb = nullptr;
     BatchBufs B{};
@@ -726,7 +771,6 @@ class ThetaScan {
         : C(ctx), forces(is_forces), K(k), KP((k + 7) & ~7), NT(((k + 7) & ~7) / 8),
           n(is_forces ? ctx.M : ctx.N), NN(ctx.N), MM(ctx.M), prm(p) {
         if (k < 1 || k > kBMaxK) throw std::invalid_argument("bioen_b200: theta scan batches 1..32 problems");
-        if (C.nranks > 1) throw std::invalid_argument("bioen_b200: theta scan is single-GPU in this version");
         if (!forces && !C.have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
         if (forces && !C.have_forces) throw std::logic_error("bioen_b200: forces data not set");
         if (!C.yt_valid) C.make_transposed();
@@ -772,6 +816,12 @@ class ThetaScan {
             B.Ff = Ff.p; B.avgk = avgk.p;
         }
         B.ldo = gRow.ldo;
+        reduce = C.nranks > 1;
+        if (reduce) {
+            redbuf.alloc((size_t)KP * gRow.ldo + 4 * KP);
+            lsebuf.alloc((size_t)2 * KP);
+            lse_all.alloc((size_t)C.nranks * 2 * KP);
+        }
         make_map(&tmapRow, C.Y, (cuuint64_t)NN, (cuuint64_t)MM, (cuuint64_t)C.ld);
         make_map(&tmapCol, C.Yt.p, (cuuint64_t)MM, (cuuint64_t)NN, (cuuint64_t)C.ldt);
         set_attr();
@@ -822,8 +872,51 @@ class ThetaScan {
         ++C.kernels_launched;
     }
 
+    // ---- collectives of the sharded scan (no-ops on one GPU) -----------------------------------------------
+    static KSlotTab tab_uniform(std::initializer_list<int> slots, const KVec& kv) {
+        KSlotTab t{};
+        t.n = (int)slots.size();
+        int r = 0;
+        for (int sl : slots) {
+            t.row[r] = (signed char)r;
+            for (int q = 0; q < kBMaxK; ++q) t.slot[r][q] = kv.mask[q] ? (signed char)sl : (signed char)-1;
+            ++r;
+        }
+        return t;
+    }
+    void allreduce_tab(const KSlotTab& t, double* buf) {
+        kb_pack<<<t.n, kBMaxK, 0, C.stream>>>(scb.p, buf, t, KP);
+        C.comm->allreduce_sum(buf, (size_t)t.n * KP, C.stream);
+        kb_unpack<<<t.n, kBMaxK, 0, C.stream>>>(scb.p, buf, t, KP);
+    }
+    void merge_lse(const KVec& kv) {
+        if (!reduce) return;
+        const KSlotTab t = tab_uniform({SC_GMAX, SC_S}, kv);
+        kb_pack<<<2, kBMaxK, 0, C.stream>>>(scb.p, lsebuf.p, t, KP);
+        C.comm->allgather(lsebuf.p, lse_all.p, (size_t)2 * KP, C.stream);
+        kb_lse_merge<<<1, kBMaxK, 0, C.stream>>>(scb.p, lse_all.p, C.nranks, KP, kv);
+    }
+    // segments of the row GEMM -> one [KP][ldo] array, all-reduced together with `tail` per-problem scalars;
+    // returns the BatchBufs view the finalising kernel should read (nseg = 1)
+    BatchBufs reduce_rows(const KVec& kv, std::initializer_list<int> tail, int& nseg) {
+        BatchBufs v = B;
+        nseg = gRow.S;
+        if (!reduce) return v;
+        const dim3 g((MM + 255) / 256, KP);
+        kb_reduce_avg<<<g, 256, 0, C.stream>>>(avgp.p, redbuf.p, MM, gRow.S, KP, gRow.ldo);
+        const KSlotTab t = tab_uniform(tail, kv);
+        double* tailbuf = redbuf.p + (size_t)KP * gRow.ldo;
+        kb_pack<<<t.n, kBMaxK, 0, C.stream>>>(scb.p, tailbuf, t, KP);
+        C.comm->allreduce_sum(redbuf.p, (size_t)KP * gRow.ldo + (size_t)t.n * KP, C.stream);
+        kb_unpack<<<t.n, kBMaxK, 0, C.stream>>>(scb.p, tailbuf, t, KP);
+        v.avgp = redbuf.p;
+        nseg = 1;
+        return v;
+    }
+
     // one batched f+g evaluation of the masked problems; move: x = xp + stp*d first
     void evaluate(const KVec& kv, bool move) {
+        int nseg = 0;
         if (forces) {
             const dim3 gridN(vblocksN, KP);
             GemmArgs g = gCol;
@@ -831,25 +924,37 @@ class ThetaScan {
             g.B = Ff.p; g.out = B.Xn;
             launch_gemm(tmapCol, g);                                   // x_j = sum_i f_i y_ij
             kbf_lse<<<gridN, kVecThreads, 0, C.stream>>>(B, kv);
+            merge_lse(kv);
             kbf_weights<<<gridN, kVecThreads, 0, C.stream>>>(B, kv);
             launch_gemm(tmapRow, gRow);                                // avg_i
-            kbf_finalize<<<KP, 1024, 0, C.stream>>>(B, kv, MM, gRow.S);
+            {
+                const BatchBufs v = reduce_rows(kv, {SC_KL}, nseg);
+                kbf_finalize<<<KP, 1024, 0, C.stream>>>(v, kv, MM, nseg);
+            }
             g.B = Rf.p; g.out = B.Tn;
             launch_gemm(tmapCol, g);                                   // t_j = sum_i r_i y_ij
             kbf_E<<<gridN, kVecThreads, 0, C.stream>>>(B, kv);
             launch_gemm(tmapRow, gRow);                                // sum_j y_ij E_j
-            kbf_grad<<<KP, 1024, 0, C.stream>>>(B, kv, MM, gRow.S);
+            {
+                const BatchBufs v = reduce_rows(kv, {SC_TMP0 + 1}, nseg);
+                kbf_grad<<<KP, 1024, 0, C.stream>>>(v, kv, MM, nseg);
+            }
             CUDA_CHECK(cudaGetLastError());
             C.kernels_launched += 6;
             return;
         }
         const dim3 gridv(vblocks, KP);
         kb_update_lse<<<gridv, kVecThreads, 0, C.stream>>>(B, kv, move ? 1 : 0);
+        merge_lse(kv);
         kb_weights<<<gridv, kVecThreads, 0, C.stream>>>(B, kv);
         launch_gemm(tmapRow, gRow);
-        kb_finalize<<<KP, 1024, 0, C.stream>>>(B, kv, C.M, gRow.S, gRow.ldo);
+        {
+            const BatchBufs v = reduce_rows(kv, {SC_TMP0, SC_GBAR, SC_CAPGBAR, SC_XNORM2}, nseg);
+            kb_finalize<<<KP, 1024, 0, C.stream>>>(v, kv, C.M, nseg, gRow.ldo);
+        }
         launch_gemm(tmapCol, gCol);
         kb_grad<<<gridv, kVecThreads, 0, C.stream>>>(B, kv);
+        if (reduce) allreduce_tab(tab_uniform({SC_DG, SC_GNORM2}, kv), redbuf.p);
         CUDA_CHECK(cudaGetLastError());
         C.kernels_launched += 4;
     }
@@ -1010,6 +1115,23 @@ class ThetaScan {
             }
             if (any_upd) {
                 kb_pair<<<gridv, kVecThreads, 0, C.stream>>>(B, upd);
+                if (reduce && !forces) {
+                    // y.s and y.y are sums over the structure axis; the ring copy ys[slot] follows the reduced value
+                    KSlotTab t{};
+                    t.n = 3;
+                    t.row[0] = 0; t.row[1] = 1; t.row[2] = 0;
+                    for (int q = 0; q < kBMaxK; ++q) {
+                        const bool on = q < K && upd.mask[q];
+                        t.slot[0][q] = on ? (signed char)SC_YS : (signed char)-1;
+                        t.slot[1][q] = on ? (signed char)SC_YY : (signed char)-1;
+                        t.slot[2][q] = on ? (signed char)(SC_YS0 + upd.slot[q]) : (signed char)-1;
+                    }
+                    KSlotTab pk = t;
+                    pk.n = 2;
+                    kb_pack<<<2, kBMaxK, 0, C.stream>>>(scb.p, redbuf.p, pk, KP);
+                    C.comm->allreduce_sum(redbuf.p, (size_t)2 * KP, C.stream);
+                    kb_unpack<<<3, kBMaxK, 0, C.stream>>>(scb.p, redbuf.p, t, KP);
+                }
                 // two-loop recursion (lbfgs.c:572-598) as 2*bound+1 fused steps per problem
                 for (int t = 0; t <= 2 * maxbound; ++t) {
                     KStep st{};
@@ -1051,6 +1173,14 @@ class ThetaScan {
                         }
                     }
                     kb_twoloop<<<gridv, kVecThreads, 0, C.stream>>>(B, st);
+                    if (reduce && !forces) {
+                        KSlotTab t{};
+                        t.n = 1;
+                        t.row[0] = 0;
+                        for (int q = 0; q < kBMaxK; ++q)
+                            t.slot[0][q] = (q < K && st.op[q] && st.v_kind[q]) ? st.out[q] : (signed char)-1;
+                        allreduce_tab(t, redbuf.p);
+                    }
                 }
                 CUDA_CHECK(cudaGetLastError());
             }

@@ -122,6 +122,17 @@ class ShardedProblem:
             return self._gather(x), fmin, code, info
         return self.p.opt_gsl(x0, **cfg)
 
+    def theta_scan(self, thetas, x0=None, **cfg):
+        """Batched theta scan on the sharded problem; X planes are gathered to full length for log-weights."""
+        if self.p.method == LOGW:
+            if x0 is not None:
+                x0 = np.asarray(x0, dtype=np.float64)
+                x0 = x0[..., self.lo:self.hi] if x0.shape[-1] == self.n_total else x0
+            X, fmin, codes, info = self.p.theta_scan(thetas, x0=x0, method=LOGW, **cfg)
+            X = np.stack([self._gather(X[q]) for q in range(X.shape[0])])
+            return X, fmin, codes, info
+        return self.p.theta_scan(thetas, x0=x0, method=FORCES, **cfg)
+
     def close(self):
         self.p.close()
 

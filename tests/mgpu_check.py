@@ -12,6 +12,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import bioen_b200  # noqa: E402
 from bioen_b200 import dist as D  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
@@ -65,6 +66,23 @@ def main():
         r = O.lbfgs(lambda v: O.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], theta), P["forces_init"])
         tol = 1e-7 if r["iterations"] < 150 else 1e-4
         assert code == r["code"] and rel(fmin, r["fx"]) < tol, ("forces lbfgs", M, N, code, r["code"], fmin, r["fx"])
+        # batched theta scan on the sharded problem against the same scan on one GPU holding the whole matrix
+        thetas = np.array([100.0, 30.0, 10.0, 3.0, 55.0])
+        with bioen_b200.Problem(P["yTilde"], device=local) as whole:
+            sp.set_logw(P["G"], P["YTilde"], 1.0)
+            whole.set_logw(P["G"], P["YTilde"], 1.0)
+            Xs, fs, cs, _ = sp.theta_scan(thetas, max_iterations=40)
+            Xw, fw, cw, _ = whole.theta_scan(thetas, max_iterations=40)
+            assert list(cs) == list(cw), ("scan logw codes", M, N, cs, cw)
+            assert np.max(np.abs(fs - fw) / np.abs(fw)) < 1e-9, ("scan logw fmin", M, N, fs, fw)
+            assert np.max(np.abs(Xs - Xw)) < 1e-6 * max(1.0, np.max(np.abs(Xw)))
+            sp.set_forces(w0, P["YTilde"], 1.0)
+            whole.set_forces(w0, P["YTilde"], 1.0)
+            Xs, fs, cs, _ = sp.theta_scan(thetas, max_iterations=25)
+            Xw, fw, cw, _ = whole.theta_scan(thetas, max_iterations=25)
+            noise = {-998, -1001, -1000, -999, -996}       # line search at rounding level (large theta), see tests
+            assert all(a == b or a in noise or b in noise for a, b in zip(cs, cw)), ("scan forces codes", M, N, cs, cw)
+            assert np.max(np.abs(fs - fw) / np.abs(fw)) < 1e-9, ("scan forces fmin", M, N, fs, fw)
         sp.close()
         if rank == 0:
             print("mgpu_check ok: M=%d N=%d world=%d" % (M, N, world), flush=True)
