@@ -415,65 +415,103 @@ def run_b200(args):
 
 
 def run_theta_scan(args):
-    """BASELINE.json config 4: the L-curve -- K problems, one yTilde stream per pass for all of them."""
+    """BASELINE.json config 4: the L-curve -- K problems, one yTilde stream per pass for all of them.  With
+    N > 1 GPUs the structure axis is sharded (N per GPU, weak scaling) and the per-problem scalars are all-reduced."""
     import torch
+    import torch.distributed as dist
     import bioen_b200
     from bioen_b200 import _lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torchrun for N>1)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     M, N, K = args.m, args.n, args.theta_scan
+    n_total = N * world
     a, YT = observations(M)
-    prob = bioen_b200.Problem(shape=(M, N), device=0)
-    prob.generate(SEED, 0, a, SIG_SIM / SIG_EXP)
+    prob = bioen_b200.Problem(shape=(M, N), device=local)
+    lib = _lib.load()
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            raw = ctypes.create_string_buffer(128)
+            _lib.check(lib.bioen_b200_nccl_unique_id(raw), "nccl_unique_id")
+            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        prob.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world, n_total)
+    prob.generate(SEED, rank * N, a, SIG_SIM / SIG_EXP)
     forces = args.method == "forces"
     meth = 1 if forces else 0
     nvar = M if forces else N
     if forces:
-        prob.set_forces(np.full(N, 1.0 / N), YT, THETA)
+        prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
     else:
         prob.set_logw(np.zeros(N), YT, THETA)
     thetas = np.geomspace(1e3, 1e-1, K)
-    rng = np.random.default_rng(SEED + 7)
+    rng = np.random.default_rng(SEED + 7 + (0 if forces else rank))
     X0 = np.ascontiguousarray((1e-3 if forces else 0.1) * rng.standard_normal((K, nvar)))
-    lib = _lib.load()
     peak_tf = ctypes.c_double()
-    _lib.check(lib.bioen_b200_dmma_peak(0, ctypes.byref(peak_tf)), "dmma_peak")
+    _lib.check(lib.bioen_b200_dmma_peak(local, ctypes.byref(peak_tf)), "dmma_peak")
     ms, gemm_ms, launches = ctypes.c_float(), ctypes.c_float(), ctypes.c_longlong()
-    with ClockSampler(0) as clk:
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    with ClockSampler(local) as clk:
         _lib.check(lib.bioen_b200_time_scan_evals(prob._h, meth, K, _lib.ptr(thetas), _lib.ptr(X0), args.warmup, args.steps,
                                                   ctypes.byref(ms), ctypes.byref(gemm_ms), ctypes.byref(launches)),
                    "time_scan_evals")
+    barrier()
+    t = torch.tensor([ms.value, gemm_ms.value], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms, g_ms = float(t[0]), float(t[1])
     KP = (K + 7) // 8 * 8
     flops = 2.0 * M * N * KP
-    ach = flops / (gemm_ms.value * 1e-3) / 1e12
+    ach = flops / (g_ms * 1e-3) / 1e12
     hbm_peak, _ = measured_peak()
     line = {
-        "metric": "theta_scan_problem_evals_per_s", "value": K * args.steps / (ms.value * 1e-3),
-        "unit": "f+g evaluations/s summed over K problems (%s, N=%d x M=%d each)" % (args.method, N, M), "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.value / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "theta L-curve scan (%s method), K=%d theta values batched, N=%d x M=%d, skinny fp64 "
-                               "GEMMs on tensor cores (DMMA)" % (args.method, K, N, M), "K": K, "method": args.method, "l2": "inputs (%.1f GB) larger than L2"
-                                                                                 % (M * N * 8 / 1e9)},
+        "metric": "theta_scan_problem_evals_per_s", "value": world * K * args.steps / (tot_ms * 1e-3),
+        "unit": "f+g evaluations/s of N=%d x M=%d blocks, summed over K problems and GPUs (%s)" % (N, M, args.method),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "theta L-curve scan (%s method), K=%d theta values batched, N=%d x M=%d per GPU, skinny "
+                               "fp64 GEMMs on tensor cores (DMMA)" % (args.method, K, N, M), "K": K,
+                   "method": args.method, "n_total": n_total,
+                   "l2": "inputs (%.1f GB) larger than L2" % (M * N * 8 / 1e9)},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
                      "frac": ach / peak_tf.value, "traffic": None,
                      "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 loop (no fp64 figure "
                                     "in MEASURED_PEAKS.json)",
                      "kernel": "batched_gemm_kernel (one pass over yTilde for all K)", "flops_per_launch": flops,
-                     "ms_per_launch": gemm_ms.value,
-                     "hbm_frac_same_launch": (M * N * 8.0) / (gemm_ms.value * 1e-3) / 1e9 / hbm_peak},
+                     "ms_per_launch": g_ms,
+                     "hbm_frac_same_launch": (M * N * 8.0) / (g_ms * 1e-3) / 1e9 / hbm_peak},
         "gpu_launches": int(launches.value), "clocks": clk.summary(),
     }
     if not args.no_optimum:
+        barrier()
         t0 = time.perf_counter()
-        X, fmin, codes, info = prob.theta_scan(thetas, x0=np.zeros(nvar))
+        X, fmin, codes, info = prob.theta_scan(thetas, x0=np.zeros(nvar), method=meth)
+        barrier()
         line["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "rounds": info["rounds"],
                                    "codes": [int(c) for c in codes], "iterations": [int(i) for i in info["iterations"]],
                                    "evaluations_total": int(info["evaluations"].sum()),
                                    "fmin_first_last": [float(fmin[0]), float(fmin[-1])],
-                                   "includes": "K x N start vectors H2D, results D2H; yTilde resident"}
+                                   "includes": "K x n start vectors H2D, results D2H; yTilde resident"}
     prob.close()
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
