@@ -229,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": unit(args), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -409,7 +409,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": None, "unit": unit(args), "cores": 0, "kind": "unavailable", "sample": str(e)}
     prob.close()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -509,13 +509,31 @@ def run_theta_scan(args):
                                    "includes": "K x n start vectors H2D, results D2H; yTilde resident"}
     prob.close()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, liblbfgs-style progress prints) goes to stderr;
+    the one JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.theta_scan and args.impl != "reference":
         return run_theta_scan(args)
     if args.impl == "reference":

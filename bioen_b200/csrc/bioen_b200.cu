@@ -46,7 +46,17 @@ int guarded(const char* where, F&& body) {
         // leave no sticky error behind in the runtime
         cudaGetLastError();
         return 1;
+    } catch (...) {
+        set_error(where, std::runtime_error("unknown C++ exception"));
+        cudaGetLastError();
+        return 1;
     }
+}
+
+// device used by the reference-compatible (part 1) entry points, which have no device argument
+int default_device() {
+    if (const char* e = getenv("BIOEN_B200_DEVICE")) return atoi(e);
+    return 0;
 }
 const double kNaN = std::numeric_limits<double>::quiet_NaN();
 }  // namespace
@@ -637,7 +647,7 @@ namespace {
 struct TempProblem {
     bioen_b200_ctx* ctx = nullptr;
     TempProblem(int m, int n, const double* yTilde) {
-        ctx = bioen_b200_create(m, n, 0);
+        ctx = bioen_b200_create(m, n, default_device());
         if (!ctx) throw std::runtime_error(g_last_error);
         if (yTilde) {
             ctx->C.upload_matrix(yTilde, (size_t)n);

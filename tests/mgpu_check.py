@@ -61,6 +61,12 @@ def main():
         # ~500-iteration bfgs2 runs are chaotic: the oracle's own C and NumPy evaluators end 1.7e-6 apart
         tol = 1e-7 if r["iterations"] < 150 else 1e-4
         assert code == r["code"] and rel(fmin, r["fx"]) < tol, ("gsl", M, N, code, r["code"], fmin, r["fx"])
+        if M == 37:   # the other GSL state machines on the sharded log-weights vector (N-vector dots all-reduced)
+            for alg, algid in (("conjugate_fr", 0), ("conjugate_pr", 1), ("bfgs", 3), ("steepest_descent", 4)):
+                x, fmin, code, info = sp.opt_gsl(P["GInit"], algorithm=algid, max_iterations=12)
+                r = O.gsl_minimize(lambda v: O.logw_fg(v, P["G"], P["yTilde"], P["YTilde"], theta), P["GInit"],
+                                   algorithm=alg, max_iterations=12)
+                assert code == r["code"] and rel(fmin, r["fx"]) < 1e-7, ("gsl " + alg, code, r["code"], fmin, r["fx"])
         sp.set_forces(P["w0"], P["YTilde"], theta)
         x, fmin, code, info = sp.opt_lbfgs(P["forces_init"])
         r = O.lbfgs(lambda v: O.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], theta), P["forces_init"])
