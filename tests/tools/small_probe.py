@@ -1,7 +1,7 @@
 """Diagnostic (GPU box): fixed overheads at the ala5 size (M=28, N=50001)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bioen_b200
 from bioen_b200 import optimize
 from bioen_b200.optimize.ext import c_bioen
