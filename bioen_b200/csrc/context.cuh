@@ -101,6 +101,7 @@ class Context {
     DevBuf<double> partialA, partialB, ab, avg, msum, Yobs, w, aux_n, aux_n2, Gv, sc, red_partials, lse_all;
     DevBuf<unsigned int> ticket;
     double* h_sc = nullptr;  // pinned
+    double* h_stp = nullptr; // pinned: step length of the next graph-replayed trial
 
     // structure-major copy + geometry of the fused two-pass forces kernels (fused_pass.cuh)
     DevBuf<double> Yt, fpart, flse;
@@ -155,7 +156,8 @@ class Context {
         red_partials.alloc((size_t)std::max(vec_blocks_n, vec_blocks_m) * 4 + 16);
         ticket.alloc(4);
         lse_all.alloc(2 * 64);
-        CUDA_CHECK(cudaHostAlloc(&h_sc, SC_COUNT * sizeof(double), cudaHostAllocDefault));
+        CUDA_CHECK(cudaHostAlloc(&h_sc, (SC_COUNT + 8) * sizeof(double), cudaHostAllocDefault));
+        h_stp = h_sc + SC_COUNT;
         CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kRowPass, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
         CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kRowPass, true>,
@@ -468,9 +470,9 @@ class Context {
         if (nranks > 1) comm->allreduce_sum(msum.p, M + ntail, stream);
     }
     void forces_eval_fused(double* x, const double* xp, const double* d, double stp, double* grad,
-                           const double* ddir) {
+                           const double* ddir, const double* stp_dev = nullptr) {
         {
-            ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p};
+            ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p, stp_dev};
             k_forces_update<<<1, 1024, 0, stream>>>(a);
             ++kernels_launched;
         }
@@ -514,9 +516,10 @@ class Context {
     // ---- kernel launch helpers ---------------------------------------------------------------------
     const double* lse_pairs() const { return nranks > 1 ? lse_all.p : sc.p + SC_LSE_MAX; }
 
-    void launch_lse(double* x, const double* xp, const double* d, double stp, const double* w0, bool from_col) {
+    void launch_lse(double* x, const double* xp, const double* d, double stp, const double* w0, bool from_col,
+                    const double* stp_dev = nullptr) {
         LseArgs a{};
-        a.n = N; a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.w0 = w0;
+        a.n = N; a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev; a.w0 = w0;
         a.col_partial = from_col ? partialB.p : nullptr;
         a.col_ld = Npad; a.col_L = nRT; a.col_chunk = chunk;
         a.write_xnorm = from_col ? 0 : 1;
@@ -591,9 +594,10 @@ class Context {
     // ---- log-weights evaluation (c_bioen_kernels_logw.c:525-561) ------------------------------------------
     // x (device, N): evaluated point; when xp != nullptr it is first formed as xp + stp*d.
     // grad == nullptr -> objective only (one pass over Y).  ddir: optional direction for sc[SC_DG].
-    void logw_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir) {
+    void logw_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir,
+                   const double* stp_dev = nullptr) {
         if (!have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
-        launch_lse(x, xp, d, stp, nullptr, false);
+        launch_lse(x, xp, d, stp, nullptr, false, stp_dev);
         gather_lse();
         {
             LogwWeightsArgs a{};
@@ -630,14 +634,15 @@ class Context {
     // ---- forces evaluation (c_bioen_kernels_forces.c:43-76) ----------------------------------------------
     // x (device, M): forces; formed as xp + stp*d when xp != nullptr.  The M-dimensional state is replicated
     // on every rank.  grad == nullptr -> objective only (two passes over Y).
-    void forces_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir) {
+    void forces_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir,
+                     const double* stp_dev = nullptr) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         if (fused_ready && allow_fused) {
-            forces_eval_fused(x, xp, d, stp, grad, ddir);
+            forces_eval_fused(x, xp, d, stp, grad, ddir, stp_dev);
             return;
         }
         {
-            ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p};
+            ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p, stp_dev};
             k_forces_update<<<1, 1024, 0, stream>>>(a);
             ++kernels_launched;
         }
@@ -680,7 +685,7 @@ class Context {
     }
     // weights only (the reference's _get_weights_from_forces): leaves normalised w in `w`
     void forces_weights_only(double* x) {
-        ForcesUpdateArgs u{M, x, nullptr, nullptr, 0.0, ab.p, sc.p};
+        ForcesUpdateArgs u{M, x, nullptr, nullptr, 0.0, ab.p, sc.p, nullptr};
         k_forces_update<<<1, 1024, 0, stream>>>(u);
         launch_pass<kColPass, false>(nullptr, nullptr);
         launch_lse(aux_n.p, nullptr, nullptr, 0.0, Gv.p, true);
