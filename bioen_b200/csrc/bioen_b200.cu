@@ -352,6 +352,9 @@ static int run_lbfgs_dev(bioen_b200_ctx* ctx, int method, double* x_dev, lbfgs_c
         info[2] = 0;
         info[3] = 0;
     }
+    if (opt.use_graphs && getenv("BIOEN_B200_GRAPH_TRACE"))
+        fprintf(stderr, "[bioen_b200 graphs] %.4f s wall, %d evals: host time inside cudaGraphLaunch %.2f ms, waiting %.2f ms\n",
+                secs, opt.stats.evaluations, opt.stats.gpu_eval_ms, 1e3 * opt.stats.host_wait_s);
     if (opt.trace)
         fprintf(stderr, "[bioen_b200 trace] lbfgs %.3f s wall: %d evals, GPU eval %.1f ms, GPU update+idle %.1f ms\n",
                 secs, opt.stats.evaluations, opt.stats.gpu_eval_ms, opt.stats.gpu_update_ms);

@@ -105,6 +105,7 @@ class Context {
 
     // structure-major copy + geometry of the fused two-pass forces kernels (fused_pass.cuh)
     DevBuf<double> Yt, fpart, flse;
+    DevBuf<double> lbfgs_store;   // g, xp, gp, d, s[m], y[m] of the device L-BFGS (lbfgs.cuh)
     long long ldt = 0, f_nslab = 0, f_chunk = 0;
     int f_C = 0, f_stages = 0, f_grid = 0, f_KI = 0, f_smem = 0, f_T = 1, f_rows = 0, f_rows_per_cta = 1;
     bool f_team = false;

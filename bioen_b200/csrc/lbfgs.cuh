@@ -13,6 +13,7 @@
 // With N sharded across GPUs the vector kernels see the local slice and the raw dot products are
 // all-reduced in-stream (forces: the M-dimensional state is replicated, nothing to reduce).
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <map>
@@ -198,7 +199,6 @@ class Lbfgs {
         for (auto& e : tev) if (e) cudaEventDestroy(e);
     }
 
-    DevBuf<double> store;  // g, xp, gp, d, s[m], y[m]
     double *x = nullptr, *g = nullptr, *xp = nullptr, *gp = nullptr, *d = nullptr;
     std::vector<double*> S, Yv;
     int vec_blocks;
@@ -224,8 +224,10 @@ class Lbfgs {
         if (ret) { *fx_out = 0.0; return ret; }
         const int m = prm.m;
         const size_t np = ((size_t)n + 15) & ~(size_t)15;
-        store.alloc(np * (4 + 2 * (size_t)m));
-        g = store.p; xp = g + np; gp = xp + np; d = gp + np;
+        // the work vectors live in the context and are reused by the next minimisation of the same size (every
+        // vector is written before it is read, so no clearing is needed)
+        C.lbfgs_store.ensure(np * (4 + 2 * (size_t)m));
+        g = C.lbfgs_store.p; xp = g + np; gp = xp + np; d = gp + np;
         S.resize(m); Yv.resize(m);
         for (int i = 0; i < m; ++i) { S[i] = d + np * (1 + i); Yv[i] = d + np * (1 + m + i); }
         std::vector<double> pf(prm.past > 0 ? prm.past : 0);
@@ -351,9 +353,14 @@ class Lbfgs {
             }
             if (g_trial) {
                 *C.h_stp = stp;
+                const auto t0 = std::chrono::steady_clock::now();
                 CUDA_CHECK(cudaGraphLaunch(g_trial, C.stream));
+                const auto t1 = std::chrono::steady_clock::now();
                 C.kernels_launched += g_trial_kernels;
                 C.spin_sync();
+                const auto t2 = std::chrono::steady_clock::now();
+                stats.host_wait_s += std::chrono::duration<double>(t2 - t1).count();
+                stats.gpu_eval_ms += 1e3 * std::chrono::duration<double>(t1 - t0).count();   // host time in launch
                 ++stats.evaluations;
                 return;
             }
