@@ -143,8 +143,10 @@ class Context {
         };
         slotsA = slots(nCB);
         slotsB = slots(nRT);
-        vec_blocks_n = std::min((N + kVecThreads - 1) / kVecThreads, num_sms * 4);
-        vec_blocks_m = std::min((M + kVecThreads - 1) / kVecThreads, num_sms * 4);
+        int vb = 4;   // resident 256-thread blocks per SM for the O(N) kernels (measured: 2, 8, 16 are no faster)
+        if (const char* e = getenv("BIOEN_B200_VEC_BLOCKS")) vb = std::max(1, atoi(e));
+        vec_blocks_n = std::min((N + kVecThreads - 1) / kVecThreads, num_sms * vb);
+        vec_blocks_m = std::min((M + kVecThreads - 1) / kVecThreads, num_sms * vb);
 
         partialA.alloc((size_t)slotsA * Mpad);
         partialB.alloc((size_t)slotsB * Npad);
