@@ -302,3 +302,21 @@ def test_theta_scan_forces_matches_single_runs(oracle, M, N, K):
             r = oracle.lbfgs(lambda v: oracle.forces_fg(v, w0, P["yTilde"], P["YTilde"], thetas[K - 1]), np.zeros(M),
                              linesearch=ls)
             assert rel(fmin[K - 1], r["fx"]) < (1e-8 if r["iterations"] < 150 else 1e-4)
+
+
+def test_minimiser_bit_reproducibility():
+    """The reference's test_{logw,forces}_reproducibility.py: GSL bfgs2 repeated many times must give the same
+    fmin and x to the last bit (its slow/reproducible OpenMP mode).  Device reductions are fixed-order, so the
+    same holds here for every minimiser."""
+    import bioen_b200
+    for name in ("data_potra_part_2_logw_M205xN10", "data_forces_M64xN64"):
+        d = load_golden(name)
+        with bioen_b200.Problem(d["yTilde"]) as p:
+            x0 = _setup(p, d)
+            x_ref, f_ref, c_ref, _ = p.opt_gsl(x0)
+            xl_ref, fl_ref, cl_ref, _ = p.opt_lbfgs(x0)
+            for _ in range(40):
+                x, f, c, _ = p.opt_gsl(x0)
+                assert f == f_ref and c == c_ref and np.array_equal(x, x_ref)
+                x, f, c, _ = p.opt_lbfgs(x0)
+                assert f == fl_ref and c == cl_ref and np.array_equal(x, xl_ref)
