@@ -108,7 +108,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    # BIOEN_B200_LIB: load another build of the library (kernel experiments); default = the in-tree build
+    return os.environ.get("BIOEN_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):
