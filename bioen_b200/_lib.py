@@ -89,6 +89,8 @@ SIGNATURES = {
     "bioen_b200_time_scan_evals": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "bioen_b200_dmma_peak": (C.c_int, [C.c_int, _dp]),
+    "bioen_b200_selftest_linesearch": (C.c_int, [lbfgs_config_params, C.c_double, C.c_double, C.c_double,
+                                                 C.CFUNCTYPE(None, C.c_double, _dp, _dp), _dp, _dp, _ip]),
     "bioen_b200_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "bioen_b200_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_longlong]),
     "bioen_b200_set_logw_dev": (C.c_int, [_vp, _vp, _dp, C.c_double]),

@@ -657,91 +657,6 @@ __global__ void __launch_bounds__(256) kb_reduce_avg(const double* avgp, double*
     out[(size_t)k * ldo + i] = s;
 }
 
-// ------------------------------------------------------------------------------------------------
-// line searches of liblbfgs as resumable state machines: prepare() -> step to evaluate, update(f, dg) -> verdict
-// (same arithmetic and order of tests as Lbfgs::linesearch_* in lbfgs.cuh / lbfgs.c:645-1001)
-// ------------------------------------------------------------------------------------------------
-struct LineSearchState {
-    const LbfgsParams* prm = nullptr;
-    int count = 0;
-    double finit = 0, dginit = 0, stp = 0;
-    // More-Thuente
-    int brackt = 0, stage1 = 1, uinfo = 0;
-    double width = 0, prev_width = 0, stx = 0, sty = 0, fx = 0, fy = 0, dgx = 0, dgy = 0, stmin = 0, stmax = 0;
-
-    void start(const LbfgsParams& p, double f, double dg, double step) {
-        prm = &p; count = 0; finit = f; dginit = dg; stp = step;
-        brackt = 0; stage1 = 1; uinfo = 0;
-        width = p.max_step - p.min_step; prev_width = 2.0 * width;
-        stx = sty = 0.0; fx = fy = f; dgx = dgy = dg;
-    }
-    void set_slope(double dg) { dginit = dg; dgx = dgy = dg; }
-    // step length of the next trial
-    double prepare() {
-        if (prm->linesearch != 0) return stp;
-        if (brackt) { stmin = std::fmin(stx, sty); stmax = std::fmax(stx, sty); }
-        else { stmin = stx; stmax = stp + 4.0 * (stp - stx); }
-        if (stp < prm->min_step) stp = prm->min_step;
-        if (prm->max_step < stp) stp = prm->max_step;
-        if ((brackt && ((stp <= stmin || stmax <= stp) || prm->max_linesearch <= count + 1 || uinfo != 0)) ||
-            (brackt && (stmax - stmin <= prm->xtol * stmax)))
-            stp = stx;
-        return stp;
-    }
-    // 0: another trial needed (stp updated); > 0: accepted after that many trials; < 0: liblbfgs error code
-    int update(double f, double dg) {
-        const LbfgsParams& p = *prm;
-        ++count;
-        if (p.linesearch != 0) {
-            const double dgtest = p.ftol * dginit;
-            double w;
-            if (f > finit + stp * dgtest) {
-                w = 0.5;
-            } else {
-                if (p.linesearch == 1) return count;
-                if (dg < p.wolfe * dginit) {
-                    w = 2.1;
-                } else {
-                    if (p.linesearch == 2) return count;
-                    if (dg > -p.wolfe * dginit) w = 0.5;
-                    else return count;
-                }
-            }
-            if (stp < p.min_step) return LBFGSERR_MINIMUMSTEP;
-            if (stp > p.max_step) return LBFGSERR_MAXIMUMSTEP;
-            if (p.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
-            stp *= w;
-            return 0;
-        }
-        const double dgtest = p.ftol * dginit;
-        const double ftest1 = finit + stp * dgtest;
-        if (brackt && ((stp <= stmin || stmax <= stp) || uinfo != 0)) return LBFGSERR_ROUNDING_ERROR;
-        if (stp == p.max_step && f <= ftest1 && dg <= dgtest) return LBFGSERR_MAXIMUMSTEP;
-        if (stp == p.min_step && (ftest1 < f || dgtest <= dg)) return LBFGSERR_MINIMUMSTEP;
-        if (brackt && (stmax - stmin) <= p.xtol * stmax) return LBFGSERR_WIDTHTOOSMALL;
-        if (p.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
-        if (f <= ftest1 && std::fabs(dg) <= p.gtol * (-dginit)) return count;
-        if (stage1 && f <= ftest1 && std::fmin(p.ftol, p.gtol) * dginit <= dg) stage1 = 0;
-        if (stage1 && ftest1 < f && f <= fx) {
-            double fm = f - stp * dgtest, fxm = fx - stx * dgtest, fym = fy - sty * dgtest;
-            double dgm = dg - dgtest, dgxm = dgx - dgtest, dgym = dgy - dgtest;
-            uinfo = mt::update(stx, fxm, dgxm, sty, fym, dgym, stp, fm, dgm, stmin, stmax, brackt);
-            fx = fxm + stx * dgtest;
-            fy = fym + sty * dgtest;
-            dgx = dgxm + dgtest;
-            dgy = dgym + dgtest;
-        } else {
-            uinfo = mt::update(stx, fx, dgx, sty, fy, dgy, stp, f, dg, stmin, stmax, brackt);
-        }
-        if (brackt) {
-            if (0.66 * prev_width <= std::fabs(sty - stx)) stp = stx + 0.5 * (sty - stx);
-            prev_width = width;
-            width = std::fabs(sty - stx);
-        }
-        return 0;
-    }
-};
-
 struct ScanResult {
     int code = 0, iterations = 0, evaluations = 0;
     double fmin = 0.0;

@@ -515,6 +515,31 @@ int bioen_b200_dmma_peak(int device, double* tflops) {
     });
 }
 
+// host-only: the line-search state machine on a caller-supplied 1-D function (CPU tests of the host logic)
+int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, double dginit, double stp0,
+                                   void (*phi)(double stp, double* f, double* dg), double* stp_out, double* f_out,
+                                   int* ntrials) {
+    const LbfgsParams prm = to_params(config);
+    if (stp0 <= 0.) return LBFGSERR_INVALIDPARAMETERS;
+    if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+    LineSearchState ls;
+    ls.start(prm, finit, dginit, stp0);
+    int n = 0;
+    for (;;) {
+        const double stp = ls.prepare();
+        double f = 0.0, dg = 0.0;
+        phi(stp, &f, &dg);
+        ++n;
+        const int verdict = ls.update(f, dg);
+        if (verdict != 0) {
+            if (stp_out) *stp_out = stp;
+            if (f_out) *f_out = f;
+            if (ntrials) *ntrials = n;
+            return verdict;
+        }
+    }
+}
+
 int bioen_b200_nccl_unique_id(char id[128]) {
     return guarded("bioen_b200_nccl_unique_id", [&] { Comm::unique_id(id); });
 }

@@ -174,6 +174,92 @@ inline int update(double& x, double& fx, double& dx, double& y, double& fy, doub
 }
 }  // namespace mt
 
+// ------------------------------------------------------------------------------------------------
+// line searches of liblbfgs as resumable state machines: prepare() -> step to evaluate, update(f, dg) -> verdict
+// (the arithmetic and order of tests of lbfgs.c:645-734 and 812-1001).  Used by the single-problem driver below,
+// by the lockstep theta scan (batched.cuh), and -- host-only -- by the CPU test hook bioen_b200_selftest_linesearch.
+// ------------------------------------------------------------------------------------------------
+struct LineSearchState {
+    const LbfgsParams* prm = nullptr;
+    int count = 0;
+    double finit = 0, dginit = 0, stp = 0;
+    // More-Thuente
+    int brackt = 0, stage1 = 1, uinfo = 0;
+    double width = 0, prev_width = 0, stx = 0, sty = 0, fx = 0, fy = 0, dgx = 0, dgy = 0, stmin = 0, stmax = 0;
+
+    void start(const LbfgsParams& p, double f, double dg, double step) {
+        prm = &p; count = 0; finit = f; dginit = dg; stp = step;
+        brackt = 0; stage1 = 1; uinfo = 0;
+        width = p.max_step - p.min_step; prev_width = 2.0 * width;
+        stx = sty = 0.0; fx = fy = f; dgx = dgy = dg;
+    }
+    void set_slope(double dg) { dginit = dg; dgx = dgy = dg; }
+    // step length of the next trial
+    double prepare() {
+        if (prm->linesearch != 0) return stp;
+        if (brackt) { stmin = std::fmin(stx, sty); stmax = std::fmax(stx, sty); }
+        else { stmin = stx; stmax = stp + 4.0 * (stp - stx); }
+        if (stp < prm->min_step) stp = prm->min_step;
+        if (prm->max_step < stp) stp = prm->max_step;
+        if ((brackt && ((stp <= stmin || stmax <= stp) || prm->max_linesearch <= count + 1 || uinfo != 0)) ||
+            (brackt && (stmax - stmin <= prm->xtol * stmax)))
+            stp = stx;
+        return stp;
+    }
+    // 0: another trial needed (stp updated); > 0: accepted after that many trials; < 0: liblbfgs error code
+    int update(double f, double dg) {
+        const LbfgsParams& p = *prm;
+        ++count;
+        if (p.linesearch != 0) {
+            const double dgtest = p.ftol * dginit;
+            double w;
+            if (f > finit + stp * dgtest) {
+                w = 0.5;
+            } else {
+                if (p.linesearch == 1) return count;
+                if (dg < p.wolfe * dginit) {
+                    w = 2.1;
+                } else {
+                    if (p.linesearch == 2) return count;
+                    if (dg > -p.wolfe * dginit) w = 0.5;
+                    else return count;
+                }
+            }
+            if (stp < p.min_step) return LBFGSERR_MINIMUMSTEP;
+            if (stp > p.max_step) return LBFGSERR_MAXIMUMSTEP;
+            if (p.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
+            stp *= w;
+            return 0;
+        }
+        const double dgtest = p.ftol * dginit;
+        const double ftest1 = finit + stp * dgtest;
+        if (brackt && ((stp <= stmin || stmax <= stp) || uinfo != 0)) return LBFGSERR_ROUNDING_ERROR;
+        if (stp == p.max_step && f <= ftest1 && dg <= dgtest) return LBFGSERR_MAXIMUMSTEP;
+        if (stp == p.min_step && (ftest1 < f || dgtest <= dg)) return LBFGSERR_MINIMUMSTEP;
+        if (brackt && (stmax - stmin) <= p.xtol * stmax) return LBFGSERR_WIDTHTOOSMALL;
+        if (p.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
+        if (f <= ftest1 && std::fabs(dg) <= p.gtol * (-dginit)) return count;
+        if (stage1 && f <= ftest1 && std::fmin(p.ftol, p.gtol) * dginit <= dg) stage1 = 0;
+        if (stage1 && ftest1 < f && f <= fx) {
+            double fm = f - stp * dgtest, fxm = fx - stx * dgtest, fym = fy - sty * dgtest;
+            double dgm = dg - dgtest, dgxm = dgx - dgtest, dgym = dgy - dgtest;
+            uinfo = mt::update(stx, fxm, dgxm, sty, fym, dgym, stp, fm, dgm, stmin, stmax, brackt);
+            fx = fxm + stx * dgtest;
+            fy = fym + sty * dgtest;
+            dgx = dgxm + dgtest;
+            dgy = dgym + dgtest;
+        } else {
+            uinfo = mt::update(stx, fx, dgx, sty, fy, dgy, stp, f, dg, stmin, stmax, brackt);
+        }
+        if (brackt) {
+            if (0.66 * prev_width <= std::fabs(sty - stx)) stp = stx + 0.5 * (sty - stx);
+            prev_width = width;
+            width = std::fabs(sty - stx);
+        }
+        return 0;
+    }
+};
+
 class Lbfgs {
    public:
     Context& C;
@@ -251,8 +337,7 @@ class Lbfgs {
 
         int k = 1, end = 0;
         for (;;) {
-            int ls = (prm.linesearch == 0) ? linesearch_morethuente(fx, step, dginit, dginit_known)
-                                           : linesearch_backtracking(fx, step, dginit, dginit_known);
+            int ls = linesearch(fx, step, dginit, dginit_known);
             if (ls < 0) {
                 // revert to the previous point (lbfgs.c:475-481)
                 C.d2d(x, xp, n);
@@ -441,100 +526,27 @@ class Lbfgs {
         }
     }
 
-    // lbfgs.c:645-734.  On success h_sc holds the scalars of the accepted point.
-    int linesearch_backtracking(double& f, double& stp, double& dginit, bool& dginit_known) {
+    // one line search (lbfgs.c:645-734 backtracking, 812-1001 More-Thuente) driven by LineSearchState: every
+    // trial is one f+g evaluation on the device and one 512-byte read-back.  On success h_sc holds the scalars
+    // of the accepted point.
+    int linesearch(double& f, double& stp, double& dginit, bool& dginit_known) {
         const double* h = C.h_sc;
-        int count = 0;
-        const double dec = 0.5, inc = 2.1;
         if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
-        if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
-        const double finit = f;
         if (!dginit_known) {
             // g.d of the new direction was left in the scalar file by the last two-loop kernel
             C.fetch_scalars();
             dginit = h[SC_DGINIT];
             dginit_known = true;
-            if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
         }
+        if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+        LineSearchState ls;
+        ls.start(prm, f, dginit, stp);
         for (;;) {
+            stp = ls.prepare();
             trial(stp);
-            const double dgtest = prm.ftol * dginit;
             f = h[SC_F];
-            ++count;
-            double width;
-            if (f > finit + stp * dgtest) {
-                width = dec;
-            } else {
-                if (prm.linesearch == 1) return count;
-                const double dg = h[SC_DG];
-                if (dg < prm.wolfe * dginit) {
-                    width = inc;
-                } else {
-                    if (prm.linesearch == 2) return count;
-                    if (dg > -prm.wolfe * dginit) width = dec;
-                    else return count;
-                }
-            }
-            if (stp < prm.min_step) return LBFGSERR_MINIMUMSTEP;
-            if (stp > prm.max_step) return LBFGSERR_MAXIMUMSTEP;
-            if (prm.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
-            stp *= width;
-        }
-    }
-
-    // lbfgs.c:812-1001
-    int linesearch_morethuente(double& f, double& stp, double& dginit, bool& dginit_known) {
-        const double* h = C.h_sc;
-        int count = 0, brackt = 0, stage1 = 1, uinfo = 0;
-        if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
-        if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
-        const double finit = f;
-        if (!dginit_known) {
-            C.fetch_scalars();
-            dginit = h[SC_DGINIT];
-            dginit_known = true;
-            if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
-        }
-        double width = prm.max_step - prm.min_step, prev_width = 2.0 * width;
-        double stx = 0., sty = 0., fx = finit, fy = finit, dgx = dginit, dgy = dginit;
-        double stmin, stmax;
-        for (;;) {
-            if (brackt) { stmin = std::fmin(stx, sty); stmax = std::fmax(stx, sty); }
-            else { stmin = stx; stmax = stp + 4.0 * (stp - stx); }
-            if (stp < prm.min_step) stp = prm.min_step;
-            if (prm.max_step < stp) stp = prm.max_step;
-            if ((brackt && ((stp <= stmin || stmax <= stp) || prm.max_linesearch <= count + 1 || uinfo != 0)) ||
-                (brackt && (stmax - stmin <= prm.xtol * stmax)))
-                stp = stx;
-            trial(stp);
-            const double dgtest = prm.ftol * dginit;
-            f = h[SC_F];
-            double dg = h[SC_DG];
-            const double ftest1 = finit + stp * dgtest;
-            ++count;
-            if (brackt && ((stp <= stmin || stmax <= stp) || uinfo != 0)) return LBFGSERR_ROUNDING_ERROR;
-            if (stp == prm.max_step && f <= ftest1 && dg <= dgtest) return LBFGSERR_MAXIMUMSTEP;
-            if (stp == prm.min_step && (ftest1 < f || dgtest <= dg)) return LBFGSERR_MINIMUMSTEP;
-            if (brackt && (stmax - stmin) <= prm.xtol * stmax) return LBFGSERR_WIDTHTOOSMALL;
-            if (prm.max_linesearch <= count) return LBFGSERR_MAXIMUMLINESEARCH;
-            if (f <= ftest1 && std::fabs(dg) <= prm.gtol * (-dginit)) return count;
-            if (stage1 && f <= ftest1 && std::fmin(prm.ftol, prm.gtol) * dginit <= dg) stage1 = 0;
-            if (stage1 && ftest1 < f && f <= fx) {
-                double fm = f - stp * dgtest, fxm = fx - stx * dgtest, fym = fy - sty * dgtest;
-                double dgm = dg - dgtest, dgxm = dgx - dgtest, dgym = dgy - dgtest;
-                uinfo = mt::update(stx, fxm, dgxm, sty, fym, dgym, stp, fm, dgm, stmin, stmax, brackt);
-                fx = fxm + stx * dgtest;
-                fy = fym + sty * dgtest;
-                dgx = dgxm + dgtest;
-                dgy = dgym + dgtest;
-            } else {
-                uinfo = mt::update(stx, fx, dgx, sty, fy, dgy, stp, f, dg, stmin, stmax, brackt);
-            }
-            if (brackt) {
-                if (0.66 * prev_width <= std::fabs(sty - stx)) stp = stx + 0.5 * (sty - stx);
-                prev_width = width;
-                width = std::fabs(sty - stx);
-            }
+            const int verdict = ls.update(f, h[SC_DG]);
+            if (verdict != 0) return verdict;
         }
     }
 };

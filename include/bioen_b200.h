@@ -202,6 +202,13 @@ int bioen_b200_time_scan_evals(bioen_b200_ctx *ctx, int method, int K, const dou
                                int warmup, int steps, float *ms, float *gemm_ms, long long *launches);
 int bioen_b200_dmma_peak(int device, double *tflops);
 
+/* host-only test hook (no GPU needed): runs the liblbfgs line search selected by config (More-Thuente or one of
+ * the three backtracking variants, lbfgs.c:645-1001) on the 1-D function phi(stp) -> (f, df/dstp).  Returns the
+ * liblbfgs verdict (> 0: number of trials on success, < 0: error code). */
+int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, double dginit, double stp0,
+                                   void (*phi)(double stp, double *f, double *dg), double *stp_out, double *f_out,
+                                   int *ntrials);
+
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);
