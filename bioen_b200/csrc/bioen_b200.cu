@@ -540,6 +540,12 @@ int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, dou
     }
 }
 
+// host-only: the interpolation step of GSL's Fletcher line minimisation (linear_minimize.c:25-128)
+double bioen_b200_selftest_interpolate(double a, double fa, double fpa, double b, double fb, double fpb, double xmin,
+                                       double xmax, int order) {
+    return fletcher::interpolate(a, fa, fpa, b, fb, fpb, xmin, xmax, order);
+}
+
 int bioen_b200_nccl_unique_id(char id[128]) {
     return guarded("bioen_b200_nccl_unique_id", [&] { Comm::unique_id(id); });
 }

@@ -209,6 +209,10 @@ int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, dou
                                    void (*phi)(double stp, double *f, double *dg), double *stp_out, double *f_out,
                                    int *ntrials);
 
+/* host-only test hook: quadratic / cubic interpolation of GSL's Fletcher line minimisation (linear_minimize.c) */
+double bioen_b200_selftest_interpolate(double a, double fa, double fpa, double b, double fb, double fpb, double xmin,
+                                       double xmax, int order);
+
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);

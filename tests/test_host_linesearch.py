@@ -77,3 +77,20 @@ def test_linesearch_rejects_ascent_direction_and_bad_step():
     cb = CB(lambda t, f, dg: None)
     assert lib.bioen_b200_selftest_linesearch(cfg, 1.0, +0.5, 1.0, cb, None, None, None) == -994   # INCREASEGRADIENT
     assert lib.bioen_b200_selftest_linesearch(cfg, 1.0, -0.5, 0.0, cb, None, None, None) == -995   # INVALIDPARAMETERS
+
+
+def test_fletcher_interpolation_matches_gsl_restatement(oracle):
+    """gsl_min.cuh fletcher::interpolate (the bracketing / sectioning step of vector_bfgs2's line search) against
+    the oracle's restatement of linear_minimize.c, including the NaN-derivative (quadratic) branch."""
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    for _ in range(400):
+        a, b = sorted(rng.uniform(-2, 5, 2))
+        fa, fb = rng.uniform(-3, 3, 2)
+        fpa = rng.uniform(-4, 0.5)
+        fpb = rng.uniform(-4, 4) if rng.random() < 0.7 else float("nan")
+        lo, hi = sorted(rng.uniform(a - 1, b + 2, 2))
+        for order in (2, 3):
+            want = oracle._interpolate(a, fa, fpa, b, fb, fpb, lo, hi, order)
+            got = lib.bioen_b200_selftest_interpolate(a, fa, fpa, b, fb, fpb, lo, hi, order)
+            assert got == want or (math.isnan(got) and math.isnan(want)), (a, fa, fpa, b, fb, fpb, lo, hi, order)
