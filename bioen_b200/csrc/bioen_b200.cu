@@ -189,6 +189,21 @@ int bioen_b200_adopt_ytilde(bioen_b200_ctx* ctx, double* yTilde_dev, size_t ld) 
     });
 }
 
+int bioen_b200_upload_rows(bioen_b200_ctx* ctx, int row0, int nrows, const double* rows_host, size_t ld) {
+    return guarded("bioen_b200_upload_rows", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        if (!C.Y) C.alloc_matrix();
+        if (row0 < 0 || nrows < 0 || row0 + nrows > C.M) throw std::invalid_argument("bioen_b200: rows out of range");
+        if (ld < (size_t)C.N) throw std::invalid_argument("bioen_b200: row stride smaller than N");
+        CUDA_CHECK(cudaMemcpy2DAsync(C.Y + (size_t)row0 * C.ld, C.ld * sizeof(double), rows_host, ld * sizeof(double),
+                                     (size_t)C.N * sizeof(double), nrows, cudaMemcpyHostToDevice, C.stream));
+        C.sync();
+        C.fused_ready = false;     // any structure-major copy is stale now
+        C.yt_valid = false;
+    });
+}
+
 int bioen_b200_alloc_ytilde(bioen_b200_ctx* ctx) {
     return guarded("bioen_b200_alloc_ytilde", [&] {
         CUDA_CHECK(cudaSetDevice(ctx->C.device));

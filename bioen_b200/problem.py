@@ -78,6 +78,15 @@ class Problem:
         """Use a matrix already on the device (e.g. a torch tensor's data_ptr()); caller keeps ownership."""
         _lib.check(self._lib.bioen_b200_adopt_ytilde(self._h, C.c_void_p(int(dev_ptr)), int(ld)), "adopt_ytilde")
 
+    def upload_rows(self, row0, rows):
+        """Chunked upload: rows[row0 : row0 + len(rows)] of yTilde (2-d, n columns).  For `Problem(shape=...)`
+        objects whose matrix arrives block by block (e.g. read from disk); call before set_logw / set_forces."""
+        blk = _lib.mat(rows)
+        if blk.ndim != 2 or blk.shape[1] != self.n:
+            raise ValueError("rows must be a (k, n) block")
+        _lib.check(self._lib.bioen_b200_upload_rows(self._h, int(row0), blk.shape[0], _lib.ptr(blk), self.n),
+                   "upload_rows")
+
     def generate(self, seed, col_offset, ytrue_over_sigma, inv_sigma):
         a = _lib.vec(ytrue_over_sigma)
         if a.size != self.m:

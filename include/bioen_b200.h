@@ -150,6 +150,10 @@ void bioen_b200_destroy(bioen_b200_ctx *ctx);
  * (even row stride, 16-byte aligned base; the caller keeps ownership) */
 int bioen_b200_upload_ytilde(bioen_b200_ctx *ctx, const double *yTilde_host, size_t ld);
 int bioen_b200_adopt_ytilde(bioen_b200_ctx *ctx, double *yTilde_dev, size_t ld);
+/* chunked upload: copy rows [row0, row0+nrows) of yTilde from host memory (row stride ld doubles).  The device
+ * matrix is allocated on the first call; a matrix larger than host memory can be streamed from disk block by block.
+ * Call before bioen_b200_set_logw / bioen_b200_set_forces. */
+int bioen_b200_upload_rows(bioen_b200_ctx *ctx, int row0, int nrows, const double *rows_host, size_t ld);
 /* allocate a zeroed device matrix for bioen_b200_generate_ytilde */
 int bioen_b200_alloc_ytilde(bioen_b200_ctx *ctx);
 /* copy the block [row0, row0+nrows) x [col0, col0+ncols) of the resident matrix to out_host (row-major, dense) */

@@ -215,3 +215,21 @@ def test_forces_fused_minimiser_and_reproducibility(oracle):
         for _ in range(3):
             f, g = p.objective_and_gradient(x)
             assert f == f0 and np.array_equal(g, g0)
+
+
+def test_chunked_upload_equals_full_upload(oracle):
+    import bioen_b200
+    P = oracle.synthetic_problem(45, 3003, seed=6)
+    g1 = 0.2 * np.random.default_rng(1).standard_normal(3003)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        p.set_logw(P["G"], P["YTilde"], 4.0)
+        want = p.objective_and_gradient(g1)
+    with bioen_b200.Problem(shape=(45, 3003)) as p:
+        for r0 in range(0, 45, 16):
+            p.upload_rows(r0, P["yTilde"][r0:r0 + 16])
+        assert np.array_equal(p.download(), P["yTilde"])
+        p.set_logw(P["G"], P["YTilde"], 4.0)
+        got = p.objective_and_gradient(g1)
+        with pytest.raises(RuntimeError, match="out of range"):
+            p.upload_rows(40, P["yTilde"][:16])
+    assert got[0] == want[0] and np.array_equal(got[1], want[1])
