@@ -6,4 +6,4 @@
 """
 __version__ = "0.1.0"
 
-from .problem import Problem, device_count  # noqa: F401
+from .problem import Problem, device_count, pinned_empty  # noqa: F401

@@ -73,6 +73,8 @@ SIGNATURES = {
     "bioen_b200_upload_ytilde": (C.c_int, [_vp, _dp, C.c_size_t]),
     "bioen_b200_adopt_ytilde": (C.c_int, [_vp, _vp, C.c_size_t]),
     "bioen_b200_upload_rows": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_size_t]),
+    "bioen_b200_host_alloc": (_vp, [C.c_size_t]),
+    "bioen_b200_host_free": (None, [_vp]),
     "bioen_b200_alloc_ytilde": (C.c_int, [_vp]),
     "bioen_b200_download_ytilde": (C.c_int, [_vp, C.c_int, C.c_int, C.c_longlong, C.c_longlong, _dp]),
     "bioen_b200_set_logw": (C.c_int, [_vp, _dp, _dp, C.c_double]),

@@ -204,6 +204,16 @@ int bioen_b200_upload_rows(bioen_b200_ctx* ctx, int row0, int nrows, const doubl
     });
 }
 
+void* bioen_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    guarded("bioen_b200_host_alloc", [&] { CUDA_CHECK(cudaHostAlloc(&p, bytes, cudaHostAllocPortable)); });
+    return p;
+}
+
+void bioen_b200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int bioen_b200_alloc_ytilde(bioen_b200_ctx* ctx) {
     return guarded("bioen_b200_alloc_ytilde", [&] {
         CUDA_CHECK(cudaSetDevice(ctx->C.device));

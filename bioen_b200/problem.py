@@ -32,6 +32,30 @@ def gsl_strerror(code):
     return _lib.load().bioen_gsl_error(int(code)).decode()
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            _lib.load().bioen_b200_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """NumPy array in page-locked host memory (freed with the array): fill yTilde into it and the upload runs as one
+    asynchronous copy at PCIe speed instead of being staged through pageable memory."""
+    shape = tuple(int(v) for v in np.atleast_1d(shape))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = _lib.load().bioen_b200_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise RuntimeError("bioen_b200_host_alloc failed: " + _lib.last_error())
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+    buf._bioen_owner = _PinnedOwner(ptr)     # the ctypes buffer is the base of every NumPy view: freed with the last one
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 class Problem:
     """yTilde (m x n, this rank's columns when sharded) resident on one GPU."""
 

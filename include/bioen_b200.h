@@ -154,6 +154,10 @@ int bioen_b200_adopt_ytilde(bioen_b200_ctx *ctx, double *yTilde_dev, size_t ld);
  * matrix is allocated on the first call; a matrix larger than host memory can be streamed from disk block by block.
  * Call before bioen_b200_set_logw / bioen_b200_set_forces. */
 int bioen_b200_upload_rows(bioen_b200_ctx *ctx, int row0, int nrows, const double *rows_host, size_t ld);
+/* page-locked host memory: matrices and vectors that live in it are uploaded by plain asynchronous copies at PCIe
+ * speed (bioen_b200_upload_ytilde detects it); NULL on failure */
+void *bioen_b200_host_alloc(size_t bytes);
+void bioen_b200_host_free(void *p);
 /* allocate a zeroed device matrix for bioen_b200_generate_ytilde */
 int bioen_b200_alloc_ytilde(bioen_b200_ctx *ctx);
 /* copy the block [row0, row0+nrows) x [col0, col0+ncols) of the resident matrix to out_host (row-major, dense) */

@@ -233,3 +233,21 @@ def test_chunked_upload_equals_full_upload(oracle):
         with pytest.raises(RuntimeError, match="out of range"):
             p.upload_rows(40, P["yTilde"][:16])
     assert got[0] == want[0] and np.array_equal(got[1], want[1])
+
+
+def test_pinned_host_arrays(oracle):
+    import gc
+    import bioen_b200
+    P = oracle.synthetic_problem(20, 1500, seed=2)
+    yp = bioen_b200.pinned_empty((20, 1500))
+    yp[:] = P["yTilde"]
+    g1 = 0.1 * np.random.default_rng(0).standard_normal(1500)
+    with bioen_b200.Problem(yp) as p:
+        p.set_logw(P["G"], P["YTilde"], 2.0)
+        f, g = p.objective_and_gradient(g1)
+    fo, go = oracle.logw_fg(g1, P["G"], P["yTilde"], P["YTilde"], 2.0)
+    assert rel(f, fo) < TOL and grad_err(g, go) < TOL
+    view = yp[3:5]
+    del yp
+    gc.collect()
+    assert np.array_equal(view, P["yTilde"][3:5])      # the pinned block lives as long as any view of it
