@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""The reference's ala5 notebook workflow (examples/ala5_optimize/ala5-bioen.ipynb: a series of confidence
+parameters theta, forces method, liblbfgs) on synthetic generic data of the same shape, with bioen_b200.
+
+    python examples/theta_series.py [--structures 50001] [--observables 28] [--thetas 40]
+
+Shows the three ways to run a theta series:
+  1. the reference's own pattern: one find_optimum per theta, warm-started (works unchanged after the import swap)
+  2. the same on one resident copy of yTilde (problem=...)
+  3. the batched scan: all thetas minimised together
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bioen_b200  # noqa: E402
+from bioen_b200 import optimize  # noqa: E402   (reference: `from bioen import optimize`)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--structures", type=int, default=50001)
+    ap.add_argument("--observables", type=int, default=28)
+    ap.add_argument("--thetas", type=int, default=40)
+    ap.add_argument("--method", default="forces", choices=["forces", "log_weights"])
+    args = ap.parse_args()
+    N, M = args.structures, args.observables
+
+    # synthetic "generic data" as in bioen/optimize/forces.py:19-68
+    np.random.seed(12345)
+    YTrue = np.random.normal(0.0, 1.0, M)
+    sig_exp = np.full(M, 0.5)
+    YObs, YTilde = optimize.forces.gen_synthetic_data(M, N, YTrue, sig_exp)
+    y, yTilde = optimize.forces.gen_sythetic_ensemble(M, N, YTrue, sig_exp, 1.0)
+    YTilde = YTilde[None, :]
+    w0 = np.full((N, 1), 1.0 / N)
+    thetas = np.geomspace(1e3, 1e-1, args.thetas)
+
+    cfg = optimize.minimize.Parameters("lbfgs")
+    cfg["verbose"] = False
+
+    if args.method == "forces":
+        mod, x0 = optimize.forces, optimize.forces.init_forces(M)
+        call = lambda x, th, **kw: mod.find_optimum(x, w0, y, yTilde, YTilde, th, cfg, **kw)
+        series = lambda **kw: mod.find_optimum_series(x0, w0, y, yTilde, YTilde, thetas, cfg, **kw)
+    else:
+        mod = optimize.log_weights
+        G = mod.getGs(w0)
+        x0 = G.copy()
+        call = lambda x, th, **kw: mod.find_optimum(x, G, y, yTilde, YTilde, th, cfg, **kw)
+        series = lambda **kw: mod.find_optimum_series(x0, G, y, yTilde, YTilde, thetas, cfg, **kw)
+
+    t0 = time.perf_counter()
+    x, f1 = x0, []
+    for th in thetas:                                   # 1. the reference's loop, unchanged
+        res = call(x, th)
+        x = res[2].reshape(-1, 1)
+        f1.append(res[4])
+    t1 = time.perf_counter()
+    with bioen_b200.Problem(yTilde) as P:               # 2. one upload for the whole series
+        x, f2 = x0, []
+        for th in thetas:
+            res = call(x, th, problem=P)
+            x = res[2].reshape(-1, 1)
+            f2.append(res[4])
+    t2 = time.perf_counter()
+    out = series()                                      # 3. batched scan (cold start for every theta)
+    t3 = time.perf_counter()
+    f3 = [o[4] for o in out]
+
+    print("%d thetas, %s method, N=%d, M=%d" % (len(thetas), args.method, N, M))
+    print("  1. find_optimum per theta (upload each time) : %.3f s" % (t1 - t0))
+    print("  2. find_optimum per theta, resident problem  : %.3f s" % (t2 - t1))
+    print("  3. batched find_optimum_series               : %.3f s" % (t3 - t2))
+    print("  theta = %g: fmin %.8f / %.8f / %.8f" % (thetas[0], f1[0], f2[0], f3[0]))
+    print("  theta = %g: fmin %.8f / %.8f / %.8f" % (thetas[-1], f1[-1], f2[-1], f3[-1]))
+    assert np.allclose(f1, f2, rtol=1e-9)
+    assert np.allclose(f1, f3, rtol=1e-2)               # warm vs cold start: same optimum to the reference's bar
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
