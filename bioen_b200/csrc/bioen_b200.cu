@@ -137,9 +137,12 @@ int bioen_b200_device_count(void) {
 // their data as usual, so the stateless entry points stay stateless.
 namespace {
 constexpr size_t kCacheMaxBytes = (size_t)256 << 20;
+constexpr int kCacheSlots = 2;     // find_optimum holds two problems of one shape at a time (yTilde and y)
 struct CtxCache {
-    bioen_b200_ctx* ctx = nullptr;
-    ~CtxCache() { delete ctx; }
+    bioen_b200_ctx* ctx[kCacheSlots] = {nullptr, nullptr};
+    ~CtxCache() {
+        for (auto*& c : ctx) { delete c; c = nullptr; }
+    }
 };
 thread_local CtxCache g_cache;
 }  // namespace
@@ -147,14 +150,16 @@ thread_local CtxCache g_cache;
 bioen_b200_ctx* bioen_b200_create(int m, int n, int device) {
     bioen_b200_ctx* ctx = nullptr;
     guarded("bioen_b200_create", [&] {
-        bioen_b200_ctx* c = g_cache.ctx;
-        if (c && c->C.M == m && c->C.N == n && c->C.device == device) {
-            g_cache.ctx = nullptr;
-            CUDA_CHECK(cudaSetDevice(device));
-            c->C.reset_for_reuse();
-            c->comm.reset();
-            ctx = c;
-            return;
+        for (auto*& c : g_cache.ctx) {
+            if (c && c->C.M == m && c->C.N == n && c->C.device == device) {
+                bioen_b200_ctx* hit = c;
+                c = nullptr;
+                CUDA_CHECK(cudaSetDevice(device));
+                hit->C.reset_for_reuse();
+                hit->comm.reset();
+                ctx = hit;
+                return;
+            }
         }
         ctx = new bioen_b200_ctx(m, n, device);
     });
@@ -167,8 +172,12 @@ void bioen_b200_destroy(bioen_b200_ctx* ctx) {
     cudaStreamSynchronize(ctx->C.stream);
     const size_t bytes = (size_t)ctx->C.M * (size_t)ctx->C.N * sizeof(double);
     if (bytes <= kCacheMaxBytes && !ctx->comm) {
-        delete g_cache.ctx;
-        g_cache.ctx = ctx;
+        for (auto*& c : g_cache.ctx) {
+            if (!c) { c = ctx; return; }
+        }
+        delete g_cache.ctx[0];                 // both slots taken: drop the older one
+        g_cache.ctx[0] = g_cache.ctx[1];
+        g_cache.ctx[1] = ctx;
         return;
     }
     delete ctx;

@@ -155,13 +155,14 @@ def find_optimum(forcesInit, w0, y, yTilde, YTilde, theta, cfg, problem=None):
     return wopt, yopt, forces_opt, fmin_initial, fmin_final, chiSqr, S
 
 
-def find_optimum_series(forcesInit, w0, y, yTilde, YTilde, thetas, cfg, batched=True, problem=None):
+def find_optimum_series(forcesInit, w0, y, yTilde, YTilde, thetas, cfg, batched=True, problem=None, strict=True):
     """The theta series (L-curve) of the reference's callers (bioen/analyze/procedure.py:62-83; the ala5 notebook
     runs exactly this with the forces method and liblbfgs) on ONE resident copy of yTilde.  Not in the reference API.
 
     batched=True (minimizer 'lbfgs'): up to 32 theta values are minimised together from forcesInit (lockstep
     device L-BFGS, four tensor-core GEMMs per batched evaluation).  batched=False: one find_optimum per theta,
-    warm-started from the previous optimum.  Returns a list of find_optimum 7-tuples in input order.
+    warm-started from the previous optimum.  Returns a list of find_optimum 7-tuples in input order.  strict=False:
+    a theta whose minimisation ends with a liblbfgs error code yields None instead of raising RuntimeError.
     """
     check_params_forces(forcesInit, w0, y, yTilde, YTilde)
     thetas = [float(t) for t in np.asarray(thetas, dtype=np.float64).ravel()]
@@ -182,6 +183,9 @@ def find_optimum_series(forcesInit, w0, y, yTilde, YTilde, thetas, cfg, batched=
                                                            **_lbfgs_kwargs(cfg))
                     for q, th in enumerate(chunk):
                         if codes[q] not in LBFGS_OK:
+                            if not strict:
+                                out.append(None)
+                                continue
                             raise RuntimeError("{}, liblbfgs return code: {}:{}".format(
                                 "bioen_opt_lbfgs_forces", codes[q], lbfgs_strerror(codes[q])))
                         problem.set_theta(th)
@@ -199,7 +203,13 @@ def find_optimum_series(forcesInit, w0, y, yTilde, YTilde, thetas, cfg, batched=
         else:
             f = forcesInit
             for th in thetas:
-                res = find_optimum(f, w0, y, yTilde, YTilde, th, cfg, problem=problem)
+                try:
+                    res = find_optimum(f, w0, y, yTilde, YTilde, th, cfg, problem=problem)
+                except RuntimeError:
+                    if strict:
+                        raise
+                    out.append(None)      # as a caller of the reference would: skip, keep the last good start
+                    continue
                 out.append(res)
                 f = res[2].reshape(-1, 1)
     finally:

@@ -222,14 +222,16 @@ def find_optimum(GInit, G, y, yTilde, YTilde, theta, cfg, problem=None):
     return wopt, yopt, gopt, fmin_initial, fmin_final
 
 
-def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, problem=None):
+def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, problem=None, strict=True):
     """The theta series (L-curve) of the reference's callers -- the loop of bioen/analyze/procedure.py:62-83 and
     of the ala5 notebook's run_theta_series -- on ONE resident copy of yTilde.  Not part of the reference API.
 
     batched=True (minimizer 'lbfgs' only): up to 32 theta values are minimised together from GInit by lockstep
     device L-BFGS machines whose evaluations are fp64 tensor-core skinny GEMMs (yTilde streamed once per pass
     for all of them).  batched=False: one find_optimum per theta, warm-started from the previous optimum like
-    the reference's callers do.  Returns a list of find_optimum 5-tuples, one per theta, in input order.
+    the reference's callers do.  Returns a list of find_optimum 5-tuples, one per theta, in input order.  strict=False: a theta whose
+    minimisation ends with a liblbfgs error code (the reference raises RuntimeError and discards the result; at
+    large theta the line search can fail at rounding level, code -998) yields None instead of raising.
     """
     check_params_logweights(GInit, G, y, yTilde, YTilde)
     thetas = [float(t) for t in np.asarray(thetas, dtype=np.float64).ravel()]
@@ -248,6 +250,9 @@ def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, 
                     X, fmin, codes, _ = problem.theta_scan(chunk, x0=g0, method=LOGW, verbose=cfg["verbose"], **_lbfgs_kwargs(cfg))
                     for q, th in enumerate(chunk):
                         if codes[q] not in LBFGS_OK:
+                            if not strict:
+                                out.append(None)
+                                continue
                             raise RuntimeError("{}, liblbfgs return code: {}:{}".format(
                                 "bioen_opt_lbfgs_logw", codes[q], lbfgs_strerror(codes[q])))
                         problem.set_theta(th)
@@ -260,7 +265,13 @@ def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, 
         else:
             g = GInit
             for th in thetas:
-                res = find_optimum(g, G, y, yTilde, YTilde, th, cfg, problem=problem)
+                try:
+                    res = find_optimum(g, G, y, yTilde, YTilde, th, cfg, problem=problem)
+                except RuntimeError:
+                    if strict:
+                        raise
+                    out.append(None)      # as a caller of the reference would: skip, keep the last good start
+                    continue
                 out.append(res)
                 g = res[2].reshape(-1, 1)
     finally:
