@@ -90,3 +90,19 @@ def test_compute_fails_loudly_without_gpu():
         c_bioen.bioen_log_posterior_logw(np.zeros(5), np.zeros(5), np.zeros(5), y, np.zeros(3), 1.0)
     with pytest.raises(RuntimeError):
         c_bioen.grad_bioen_log_posterior_forces(np.zeros(3), np.full(5, 0.2), y, np.zeros(3), 1.0)
+
+
+def test_plain_c_program_compiles_and_links_against_the_header(tmp_path):
+    """include/bioen_b200.h is valid C (not only C++) and every symbol the demo uses resolves in the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    _lib.load()
+    exe = tmp_path / "c_abi_demo"
+    libdir = os.path.dirname(_lib.library_path())
+    res = subprocess.run([gcc, "-O1", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", str(exe), "-L", libdir, "-lbioen_b200",
+                          "-lm", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
