@@ -77,9 +77,15 @@ class Problem:
         self.method = None
         self.nranks = 1
         if yTilde is not None:
-            _lib.check(self._lib.bioen_b200_upload_ytilde(self._h, _lib.ptr(yT), self.n), "upload_ytilde")
+            _lib.check(self._lib.bioen_b200_upload_ytilde(self._ctx, _lib.ptr(yT), self.n), "upload_ytilde")
 
     # ---- lifetime -----------------------------------------------------------------------------------
+    @property
+    def _ctx(self):
+        if not getattr(self, "_h", None):
+            raise RuntimeError("bioen_b200.Problem: used after close()")
+        return self._h
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.bioen_b200_destroy(self._h)
@@ -100,7 +106,7 @@ class Problem:
     # ---- data ---------------------------------------------------------------------------------------
     def adopt(self, dev_ptr, ld):
         """Use a matrix already on the device (e.g. a torch tensor's data_ptr()); caller keeps ownership."""
-        _lib.check(self._lib.bioen_b200_adopt_ytilde(self._h, C.c_void_p(int(dev_ptr)), int(ld)), "adopt_ytilde")
+        _lib.check(self._lib.bioen_b200_adopt_ytilde(self._ctx, C.c_void_p(int(dev_ptr)), int(ld)), "adopt_ytilde")
 
     def upload_rows(self, row0, rows):
         """Chunked upload: rows[row0 : row0 + len(rows)] of yTilde (2-d, n columns).  For `Problem(shape=...)`
@@ -108,21 +114,21 @@ class Problem:
         blk = _lib.mat(rows)
         if blk.ndim != 2 or blk.shape[1] != self.n:
             raise ValueError("rows must be a (k, n) block")
-        _lib.check(self._lib.bioen_b200_upload_rows(self._h, int(row0), blk.shape[0], _lib.ptr(blk), self.n),
+        _lib.check(self._lib.bioen_b200_upload_rows(self._ctx, int(row0), blk.shape[0], _lib.ptr(blk), self.n),
                    "upload_rows")
 
     def generate(self, seed, col_offset, ytrue_over_sigma, inv_sigma):
         a = _lib.vec(ytrue_over_sigma)
         if a.size != self.m:
             raise ValueError("ytrue_over_sigma must have m entries")
-        _lib.check(self._lib.bioen_b200_generate_ytilde(self._h, int(seed), int(col_offset), _lib.ptr(a),
+        _lib.check(self._lib.bioen_b200_generate_ytilde(self._ctx, int(seed), int(col_offset), _lib.ptr(a),
                                                         float(inv_sigma)), "generate_ytilde")
 
     def download(self, row0=0, nrows=None, col0=0, ncols=None):
         nrows = self.m - row0 if nrows is None else nrows
         ncols = self.n - col0 if ncols is None else ncols
         out = np.empty((nrows, ncols), dtype=np.float64)
-        _lib.check(self._lib.bioen_b200_download_ytilde(self._h, row0, nrows, col0, ncols, _lib.ptr(out)),
+        _lib.check(self._lib.bioen_b200_download_ytilde(self._ctx, row0, nrows, col0, ncols, _lib.ptr(out)),
                    "download_ytilde")
         return out
 
@@ -130,25 +136,25 @@ class Problem:
         G, Y = _lib.vec(G), _lib.vec(YTilde)
         if G.size != self.n or Y.size != self.m:
             raise ValueError("G must have n and YTilde m entries")
-        _lib.check(self._lib.bioen_b200_set_logw(self._h, _lib.ptr(G), _lib.ptr(Y), float(theta)), "set_logw")
+        _lib.check(self._lib.bioen_b200_set_logw(self._ctx, _lib.ptr(G), _lib.ptr(Y), float(theta)), "set_logw")
         self.method = LOGW
 
     def set_forces(self, w0, YTilde, theta):
         w0, Y = _lib.vec(w0), _lib.vec(YTilde)
         if w0.size != self.n or Y.size != self.m:
             raise ValueError("w0 must have n and YTilde m entries")
-        _lib.check(self._lib.bioen_b200_set_forces(self._h, _lib.ptr(w0), _lib.ptr(Y), float(theta)), "set_forces")
+        _lib.check(self._lib.bioen_b200_set_forces(self._ctx, _lib.ptr(w0), _lib.ptr(Y), float(theta)), "set_forces")
         self.method = FORCES
 
     def set_option(self, option, value):
         """Tuning switches of include/bioen_b200.h (1 = fused two-pass forces kernels, default on)."""
-        _lib.check(self._lib.bioen_b200_set_option(self._h, int(option), int(value)), "set_option")
+        _lib.check(self._lib.bioen_b200_set_option(self._ctx, int(option), int(value)), "set_option")
 
     def set_theta(self, theta):
-        self._lib.bioen_b200_set_theta(self._h, float(theta))
+        self._lib.bioen_b200_set_theta(self._ctx, float(theta))
 
     def comm_init(self, unique_id, rank, nranks, n_total):
-        _lib.check(self._lib.bioen_b200_comm_init(self._h, unique_id, rank, nranks, int(n_total)), "comm_init")
+        _lib.check(self._lib.bioen_b200_comm_init(self._ctx, unique_id, rank, nranks, int(n_total)), "comm_init")
         self.nranks = nranks
 
     # ---- evaluations --------------------------------------------------------------------------------
@@ -161,7 +167,7 @@ class Problem:
         if x.size != self._dim(method):
             raise ValueError("wrong length of the variable vector")
         f = C.c_double()
-        _lib.check(self._lib.bioen_b200_eval(self._h, method, _lib.ptr(x), C.byref(f), None), "eval")
+        _lib.check(self._lib.bioen_b200_eval(self._ctx, method, _lib.ptr(x), C.byref(f), None), "eval")
         return f.value
 
     def objective_and_gradient(self, x, method=None):
@@ -171,7 +177,7 @@ class Problem:
             raise ValueError("wrong length of the variable vector")
         f = C.c_double()
         g = np.empty(x.size, dtype=np.float64)
-        _lib.check(self._lib.bioen_b200_eval(self._h, method, _lib.ptr(x), C.byref(f), _lib.ptr(g)), "eval")
+        _lib.check(self._lib.bioen_b200_eval(self._ctx, method, _lib.ptr(x), C.byref(f), _lib.ptr(g)), "eval")
         return f.value, g
 
     def gradient(self, x, method=None):
@@ -183,7 +189,7 @@ class Problem:
         x = _lib.vec(x)
         w = np.empty(self.n, dtype=np.float64)
         s = C.c_double()
-        _lib.check(self._lib.bioen_b200_weights(self._h, method, _lib.ptr(x), _lib.ptr(w), C.byref(s)), "weights")
+        _lib.check(self._lib.bioen_b200_weights(self._ctx, method, _lib.ptr(x), _lib.ptr(w), C.byref(s)), "weights")
         return w, (s.value if method == LOGW else None)
 
     def average(self, w):
@@ -192,7 +198,7 @@ class Problem:
         if w.size != self.n:
             raise ValueError("w must have n entries")
         out = np.empty(self.m, dtype=np.float64)
-        _lib.check(self._lib.bioen_b200_average(self._h, _lib.ptr(w), _lib.ptr(out)), "average")
+        _lib.check(self._lib.bioen_b200_average(self._ctx, _lib.ptr(w), _lib.ptr(out)), "average")
         return out
 
     def forces_from_weights(self, w, gradient=True):
@@ -200,7 +206,7 @@ class Problem:
         w = _lib.vec(w)
         f = C.c_double()
         g = np.empty(self.m, dtype=np.float64) if gradient else None
-        _lib.check(self._lib.bioen_b200_forces_from_weights(self._h, _lib.ptr(w), C.byref(f),
+        _lib.check(self._lib.bioen_b200_forces_from_weights(self._ctx, _lib.ptr(w), C.byref(f),
                                                             _lib.ptr(g) if gradient else None), "forces_from_weights")
         return (f.value, g) if gradient else f.value
 
@@ -216,7 +222,7 @@ class Problem:
         x = np.empty_like(x0)
         fmin = C.c_double()
         info = (C.c_int * 4)()
-        code = self._lib.bioen_b200_opt_lbfgs(self._h, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
+        code = self._lib.bioen_b200_opt_lbfgs(self._ctx, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
         if code == -2000:
             raise RuntimeError("bioen_b200_opt_lbfgs failed: " + _lib.last_error())
         return x, fmin.value, code, dict(iterations=info[0], evaluations=info[1])
@@ -233,7 +239,7 @@ class Problem:
         x = np.empty_like(x0)
         fmin = C.c_double()
         info = (C.c_int * 4)()
-        code = self._lib.bioen_b200_opt_gsl(self._h, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
+        code = self._lib.bioen_b200_opt_gsl(self._ctx, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
         if code == -2000:
             raise RuntimeError("bioen_b200_opt_gsl failed: " + _lib.last_error())
         return x, fmin.value, code, dict(iterations=info[0], gradient_evaluations=info[1], f_only_evaluations=info[2])
@@ -262,7 +268,7 @@ class Problem:
         codes = (C.c_int * K)()
         info = (C.c_int * (2 * K))()
         stats = np.zeros(4, dtype=np.float64)
-        _lib.check(self._lib.bioen_b200_theta_scan(self._h, method, K, _lib.ptr(thetas), _lib.ptr(X0), _lib.ptr(X), c, v,
+        _lib.check(self._lib.bioen_b200_theta_scan(self._ctx, method, K, _lib.ptr(thetas), _lib.ptr(X0), _lib.ptr(X), c, v,
                                                    _lib.ptr(fmin), codes, info, _lib.ptr(stats)), "theta_scan")
         return X, fmin, np.array(codes[:]), dict(iterations=np.array(info[0::2]), evaluations=np.array(info[1::2]),
                                                  rounds=int(stats[0]), gemm_launches=int(stats[1]),
@@ -272,15 +278,15 @@ class Problem:
     def time_evals(self, x_dev_ptr, grad_dev_ptr, warmup, steps, method=None):
         method = self.method if method is None else method
         ms, pass_ms, launches = C.c_float(), C.c_float(), C.c_longlong()
-        _lib.check(self._lib.bioen_b200_time_evals(self._h, method, C.c_void_p(int(x_dev_ptr)),
+        _lib.check(self._lib.bioen_b200_time_evals(self._ctx, method, C.c_void_p(int(x_dev_ptr)),
                                                    C.c_void_p(int(grad_dev_ptr)), warmup, steps, C.byref(ms),
                                                    C.byref(pass_ms), C.byref(launches)), "time_evals")
         return ms.value, pass_ms.value, launches.value
 
     def kernels_launched(self):
-        return int(self._lib.bioen_b200_kernels_launched(self._h))
+        return int(self._lib.bioen_b200_kernels_launched(self._ctx))
 
     def scalars(self):
         out = np.empty(64, dtype=np.float64)
-        _lib.check(self._lib.bioen_b200_debug_read(self._h, 0, _lib.ptr(out), 64), "debug_read")
+        _lib.check(self._lib.bioen_b200_debug_read(self._ctx, 0, _lib.ptr(out), 64), "debug_read")
         return out

@@ -251,3 +251,18 @@ def test_pinned_host_arrays(oracle):
     del yp
     gc.collect()
     assert np.array_equal(view, P["yTilde"][3:5])      # the pinned block lives as long as any view of it
+
+
+def test_problem_use_after_close_raises(oracle):
+    import bioen_b200
+    P = oracle.synthetic_problem(5, 40, seed=1)
+    p = bioen_b200.Problem(P["yTilde"])
+    p.set_logw(P["G"], P["YTilde"], 1.0)
+    p.close()
+    p.close()                                   # idempotent
+    with pytest.raises(RuntimeError, match="after close"):
+        p.objective(np.zeros(40))
+    with pytest.raises(ValueError):
+        bioen_b200.Problem(np.zeros(7))         # not a matrix
+    with pytest.raises(RuntimeError):
+        bioen_b200.Problem(shape=(0, 5))        # empty problems are refused by the library
