@@ -142,13 +142,21 @@ def last_error():
 
 
 def check(status, what="bioen_b200"):
-    """Raise for a non-zero status of a part-2 call."""
+    """Raise for a non-zero status of a part-2 call (and consume the thread's pending-error flag, which is meant
+    for the part-1 entry points that have no status of their own)."""
     if status:
-        raise RuntimeError("%s failed: %s" % (what, last_error()))
+        msg = last_error()
+        load().bioen_b200_error_pending()
+        raise RuntimeError("%s failed: %s" % (what, msg))
+
+
+def clear_pending():
+    """Forget an error that was already reported through a status code (call before a part-1 entry point)."""
+    load().bioen_b200_error_pending()
 
 
 def check_pending(what):
-    """Raise if a part-1 call (no status in its signature) failed."""
+    """Raise if a part-1 call (no status in its signature) failed since the last clear_pending()."""
     if load().bioen_b200_error_pending():
         raise RuntimeError("%s failed: %s" % (what, last_error()))
 

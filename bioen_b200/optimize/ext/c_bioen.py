@@ -60,6 +60,7 @@ def library_lbfgs():                                 # c_bioen.pyx:230
 def bioen_log_posterior_logw(gPrime, g, G, yTilde, YTilde, theta, caching=False):
     """c_bioen.pyx:246-292.  Faithful to the reference, the SECOND argument `g` is what the C objective
     receives as reference log-weights (c_bioen.pyx:278-279); `G` is unused here."""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     gp, gref, Y = _lib.vec(gPrime), _lib.vec(g), _lib.vec(YTilde)
@@ -71,6 +72,7 @@ def bioen_log_posterior_logw(gPrime, g, G, yTilde, YTilde, theta, caching=False)
 
 def grad_bioen_log_posterior_logw(gPrime, g, G, yTilde, YTilde, theta, caching=False, print_timing=False):
     """c_bioen.pyx:295-359"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     gp, Gv, Y = _lib.vec(gPrime), _lib.vec(G), _lib.vec(YTilde)
@@ -144,6 +146,7 @@ def _finish_lbfgs(name, errno, result, fmin):
 
 def bioen_opt_bfgs_logw(g, G, yTilde, YTilde, theta, params):
     """c_bioen.pyx:362-438 -> (xfinal[n], fmin)"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     gv, Gv, Y = _lib.vec(g), _lib.vec(G), _lib.vec(YTilde)
@@ -157,6 +160,7 @@ def bioen_opt_bfgs_logw(g, G, yTilde, YTilde, theta, params):
 
 def bioen_opt_lbfgs_logw(g, G, yTilde, YTilde, theta, params):
     """c_bioen.pyx:441-520 -> (xfinal[n], fmin)"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     gv, Gv, Y = _lib.vec(g), _lib.vec(G), _lib.vec(YTilde)
@@ -170,6 +174,7 @@ def bioen_opt_lbfgs_logw(g, G, yTilde, YTilde, theta, params):
 
 def bioen_log_posterior_forces(forces, w0, yTilde, YTilde, theta, caching=False):
     """c_bioen.pyx:523-581: weights from the forces, then the objective for those weights"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     f, w0v, Y = _lib.vec(forces), _lib.vec(w0), _lib.vec(YTilde)
@@ -185,6 +190,7 @@ def bioen_log_posterior_forces(forces, w0, yTilde, YTilde, theta, caching=False)
 
 def grad_bioen_log_posterior_forces(forces, w0, yTilde, YTilde, theta, caching=False):
     """c_bioen.pyx:584-643"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     f, w0v, Y = _lib.vec(forces), _lib.vec(w0), _lib.vec(YTilde)
@@ -201,6 +207,7 @@ def grad_bioen_log_posterior_forces(forces, w0, yTilde, YTilde, theta, caching=F
 
 def bioen_opt_bfgs_forces(forces, w0, yTilde, YTilde, theta, params):
     """c_bioen.pyx:646-716 -> (xfinal[m], fmin)"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     f, w0v, Y = _lib.vec(forces), _lib.vec(w0), _lib.vec(YTilde)
@@ -214,6 +221,7 @@ def bioen_opt_bfgs_forces(forces, w0, yTilde, YTilde, theta, params):
 
 def bioen_opt_lbfgs_forces(forces, w0, yTilde, YTilde, theta, params):
     """c_bioen.pyx:719-792 -> (xfinal[m], fmin)"""
+    _lib.clear_pending()
     yT = _lib.mat(yTilde)
     m, n = yT.shape
     f, w0v, Y = _lib.vec(forces), _lib.vec(w0), _lib.vec(YTilde)

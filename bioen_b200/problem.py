@@ -73,7 +73,9 @@ class Problem:
         self.device = int(device)
         self._h = self._lib.bioen_b200_create(self.m, self.n, self.device)
         if not self._h:
-            raise RuntimeError("bioen_b200_create failed: " + _lib.last_error())
+            msg = _lib.last_error()
+            _lib.clear_pending()
+            raise RuntimeError("bioen_b200_create failed: " + msg)
         self.method = None
         self.nranks = 1
         if yTilde is not None:

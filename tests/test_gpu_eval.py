@@ -266,3 +266,18 @@ def test_problem_use_after_close_raises(oracle):
         bioen_b200.Problem(np.zeros(7))         # not a matrix
     with pytest.raises(RuntimeError):
         bioen_b200.Problem(shape=(0, 5))        # empty problems are refused by the library
+
+
+def test_reported_error_does_not_leak_into_the_next_stateless_call(oracle):
+    """An error that was raised through a status code must not make the next reference-style (part 1) call fail."""
+    import bioen_b200
+    from bioen_b200.optimize.ext import c_bioen
+    P = oracle.synthetic_problem(6, 50, seed=2)
+    with pytest.raises(RuntimeError):
+        bioen_b200.Problem(shape=(0, 3))
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        with pytest.raises(RuntimeError):
+            p.upload_rows(5, P["yTilde"][:4])
+    f = c_bioen.bioen_log_posterior_logw(np.zeros(50), np.zeros(50), np.zeros(50), P["yTilde"], P["YTilde"], 2.0)
+    fo, _ = oracle.logw_fg(np.zeros(50), np.zeros(50), P["yTilde"], P["YTilde"], 2.0)
+    assert rel(f, fo) < TOL
