@@ -13,9 +13,10 @@ One "step" = one evaluation of the log-posterior AND its gradient at a fresh poi
   cpu_baseline  the reference's own OpenMP C kernels (oracle/_ref, built from /root/reference by oracle/Makefile)
              on the host cores, on a column sample of the same problem
 
-N > 1 (torchrun): the structure axis is sharded, every rank holds N = 1e6 columns (weak scaling), one fused
-NCCL all-reduce of M+3 doubles (+ tiny scalar reductions) per evaluation; `value` counts 1e6-structure
-evaluations per second summed over ranks.
+N > 1 (torchrun): the structure axis is sharded, every rank holds N = 1e6 columns (weak scaling), one exchange
+of M+3 doubles (+ tiny scalar reductions) per evaluation, carried by the library's peer-memory kernel over
+NVLink (`config.exchange` = "p2p"; "nccl" when peer mapping is unavailable or BIOEN_B200_P2P=0); `value` counts
+1e6-structure evaluations per second summed over ranks.
 
 `--impl reference` times the reference CPU implementation alone (no GPU code on that path).
 """
@@ -381,7 +382,7 @@ def run_b200(args):
             "method": args.method, "n_per_gpu": N, "m": M, "n_total": n_total,
             "l2": "inputs (%.1f GB) larger than L2 (126 MB); every step evaluates a new point" % (alg_bytes / 1e9),
             "global_evals_per_s": args.steps / (ms * 1e-3),
-            "generate_s": gen_s,
+            "generate_s": gen_s, "exchange": prob.comm_mode(),
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": profiled_traffic(args.method, M, N),

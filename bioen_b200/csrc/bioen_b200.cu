@@ -272,6 +272,9 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
     return guarded("bioen_b200_set_option", [&] {
         switch (option) {
             case BIOEN_B200_OPT_FUSED_FORCES: ctx->C.allow_fused = value != 0; break;
+            case BIOEN_B200_OPT_P2P:
+                if (ctx->comm) ctx->comm->use_p2p = value != 0;
+                break;
             default: throw std::invalid_argument("bioen_b200: unknown option");
         }
     });
@@ -590,8 +593,14 @@ int bioen_b200_comm_init(bioen_b200_ctx* ctx, const char id[128], int rank, int 
         ctx->comm.reset(new Comm(id, rank, nranks));
         ctx->C.set_comm(ctx->comm.get());
         ctx->C.N_total = n_total;
+        long long cap = ctx->C.M + 16;
+        if (cap < 1024) cap = 1024;
+        if (cap > (long long)kP2PMaxCount) cap = (long long)kP2PMaxCount;
+        ctx->comm->enable_p2p(cap, ctx->C.stream);
     });
 }
+
+int bioen_b200_comm_mode(bioen_b200_ctx* ctx) { return ctx->comm ? ctx->comm->mode() : 0; }
 
 int bioen_b200_eval_dev(bioen_b200_ctx* ctx, int method, double* x_dev, double* grad_dev) {
     return guarded("bioen_b200_eval_dev", [&] {
@@ -639,7 +648,7 @@ int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double
         CUDA_CHECK(cudaEventCreate(&e0));
         CUDA_CHECK(cudaEventCreate(&e1));
         C.begin_pass_timing(steps * 4);
-        const long long k0 = C.kernels_launched;
+        const long long k0 = bioen_b200_kernels_launched(ctx);
         CUDA_CHECK(cudaEventRecord(e0, C.stream));
         for (int k = 0; k < steps; ++k) one(warmup + k);
         CUDA_CHECK(cudaEventRecord(e1, C.stream));
@@ -647,7 +656,7 @@ int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double
         float total = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&total, e0, e1));
         if (ms) *ms = total;
-        if (launches) *launches = C.kernels_launched - k0;
+        if (launches) *launches = bioen_b200_kernels_launched(ctx) - k0;
         const float pm = C.end_pass_timing();
         if (pass_ms) *pass_ms = pm;
         cudaEventDestroy(e0);
@@ -684,7 +693,9 @@ int bioen_b200_download_ytilde(bioen_b200_ctx* ctx, int row0, int nrows, long lo
     });
 }
 
-long long bioen_b200_kernels_launched(bioen_b200_ctx* ctx) { return ctx->C.kernels_launched; }
+long long bioen_b200_kernels_launched(bioen_b200_ctx* ctx) {
+    return ctx->C.kernels_launched + (ctx->comm ? ctx->comm->p2p_launches : 0);
+}
 
 int bioen_b200_debug_read(bioen_b200_ctx* ctx, int what, double* out_host, size_t count) {
     return guarded("bioen_b200_debug_read", [&] {

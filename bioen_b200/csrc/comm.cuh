@@ -6,10 +6,20 @@
 // time with dlopen: inside a PyTorch process that is the NCCL torch already loaded; a single-GPU user never
 // needs NCCL at all.  The communicator is created from a 128-byte unique id that the Python layer
 // broadcasts through torch.distributed (bioen_b200/dist.py).
+//
+// The exchanges are tiny (3 ... M+3 doubles) and sit on the critical path of every evaluation and of every
+// L-BFGS dot product, so their cost is pure latency.  NCCL needs ~25-30 us for one; the path therefore carries its
+// own exchange over NVLink peer memory (k_p2p_exchange below): every rank owns an inbox that its peers map through
+// CUDA IPC, one small kernel stores the rank's contribution straight into every peer's inbox, publishes a
+// release-flag, waits for the peers' flags and combines the inboxes in rank order (so all ranks hold bit-identical
+// results).  NCCL is kept for the bootstrap (handle exchange), for messages larger than the inbox, and as the
+// collective path when peer mapping is not available (BIOEN_B200_P2P=0 forces it).
 #pragma once
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -55,10 +65,108 @@ struct NcclApi {
     }
 };
 
+// ---- peer-memory exchange ---------------------------------------------------------------------------------
+// Region owned by each rank (one cudaMalloc, mapped by every peer):
+//   [0, 128)    flags[src]  last epoch whose contribution rank `src` has delivered here (monotonic)
+//   [128, 136)  epoch       this rank's exchange counter (device side, so captured graphs replay correctly)
+//   [256, ...)  inbox[2][nranks][cap] doubles, indexed by epoch parity and source rank
+// Parity double buffering is enough: a rank can start exchange e+2 only after every peer has published e+1,
+// i.e. after every peer has finished reading exchange e.
+constexpr int kP2PMaxRanks = 16;
+constexpr int kP2PThreads = 1024;
+constexpr size_t kP2PHeaderBytes = 256;
+constexpr size_t kP2PMaxCount = 8192;  // doubles per rank and exchange; larger messages go through NCCL
+enum P2POp { kP2PSum = 0, kP2PMax = 1, kP2PGather = 2 };
+
+struct P2PArgs {
+    unsigned char* region[kP2PMaxRanks];  // region[r]: rank r's region as mapped in this process
+    int rank, nranks;
+    long long cap;
+    const double* send;
+    double* recv;
+    int count, op;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kP2PThreads, 1) k_p2p_exchange(const P2PArgs a) {
+    __shared__ unsigned long long s_epoch;
+    __shared__ int s_fail;
+    unsigned char* me = a.region[a.rank];
+    const int tid = threadIdx.x, R = a.nranks;
+    if (tid == 0) {
+        unsigned long long* ep = reinterpret_cast<unsigned long long*>(me + 128);
+        s_epoch = *ep + 1;
+        *ep = s_epoch;
+        s_fail = 0;
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
+    const size_t par = (size_t)(epoch & 1);
+    // deliver this rank's contribution into every inbox (its own included)
+    for (int r = 0; r < R; ++r) {
+        double* dst = reinterpret_cast<double*>(a.region[r] + kP2PHeaderBytes) + (par * R + a.rank) * a.cap;
+        for (int i = tid; i < a.count; i += kP2PThreads) dst[i] = a.send[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < R) {
+        st_release_sys(reinterpret_cast<unsigned long long*>(a.region[tid]) + a.rank, epoch);
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(me) + tid;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) < epoch) {
+            if (global_timer_ns() - t0 > a.timeout_ns) {  // a peer never arrived: poison the result, do not hang
+                s_fail = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const double* in = reinterpret_cast<const double*>(me + kP2PHeaderBytes) + par * R * a.cap;
+    if (s_fail) {
+        const int total = (a.op == kP2PGather) ? a.count * R : a.count;
+        for (int i = tid; i < total; i += kP2PThreads) a.recv[i] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    if (a.op == kP2PGather) {
+        for (int r = 0; r < R; ++r)
+            for (int i = tid; i < a.count; i += kP2PThreads) a.recv[(size_t)r * a.count + i] = __ldcg(in + r * a.cap + i);
+    } else {
+        for (int i = tid; i < a.count; i += kP2PThreads) {
+            double s = __ldcg(in + i);
+            for (int r = 1; r < R; ++r) {
+                const double v = __ldcg(in + r * a.cap + i);
+                s = (a.op == kP2PSum) ? s + v : fmax(s, v);
+            }
+            a.recv[i] = s;
+        }
+    }
+}
+
 class Comm {
    public:
     int rank = 0, nranks = 1;
     NcclApi::comm_t comm = nullptr;
+    // peer-memory exchange state
+    bool p2p = false;         // regions mapped on every rank
+    bool use_p2p = true;      // run-time switch (BIOEN_B200_OPT_P2P); must be flipped on all ranks together
+    unsigned char* region = nullptr;
+    unsigned char* mapped[kP2PMaxRanks] = {};
+    long long cap = 0;
+    long long p2p_launches = 0;
 
     static void unique_id(char out[128]) {
         NcclApi::unique_id id;
@@ -71,19 +179,103 @@ class Comm {
         check(NcclApi::get().CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank");
     }
     ~Comm() {
+        release_p2p();
         if (comm) NcclApi::get().CommDestroy(comm);
     }
+    // Map every rank's inbox into this process.  Collective: every rank must call it.  Any failure on any rank
+    // (no peer access, IPC not permitted in this container, ...) leaves all ranks on the NCCL path.
+    void enable_p2p(long long cap_doubles, cudaStream_t st) {
+        const char* env = getenv("BIOEN_B200_P2P");
+        int fail = (env && env[0] == '0') || nranks > kP2PMaxRanks;
+        cap = cap_doubles;
+        const size_t bytes = kP2PHeaderBytes + (size_t)2 * nranks * cap * sizeof(double);
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (!fail) {
+            if (cudaMalloc(&region, bytes) != cudaSuccess || cudaMemset(region, 0, bytes) != cudaSuccess ||
+                cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine, region) != cudaSuccess)
+                fail = 1;
+        }
+        // exchange the 64-byte handles (+ a failure word) through NCCL
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+        constexpr int W = 9;  // doubles per rank: 8 handle words + failure flag
+        double h_send[W], *d_send = nullptr, *d_all = nullptr;
+        std::vector<double> h_all((size_t)W * nranks);
+        memcpy(h_send, &mine, 64);
+        h_send[8] = fail ? 1.0 : 0.0;
+        CUDA_CHECK(cudaMalloc(&d_send, sizeof(h_send)));
+        CUDA_CHECK(cudaMalloc(&d_all, h_all.size() * sizeof(double)));
+        CUDA_CHECK(cudaMemcpyAsync(d_send, h_send, sizeof(h_send), cudaMemcpyHostToDevice, st));
+        nccl_allgather(d_send, d_all, W, st);
+        CUDA_CHECK(cudaMemcpyAsync(h_all.data(), d_all, h_all.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int r = 0; r < nranks; ++r) fail |= (h_all[(size_t)r * W + 8] != 0.0);
+        if (!fail) {
+            for (int r = 0; r < nranks && !fail; ++r) {
+                if (r == rank) { mapped[r] = region; continue; }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, &h_all[(size_t)r * W], 64);
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) fail = 1;
+                else mapped[r] = static_cast<unsigned char*>(ptr);
+            }
+        }
+        // agree on the outcome; this all-gather is also the barrier behind which every inbox is zeroed and mapped
+        h_send[8] = fail ? 1.0 : 0.0;
+        CUDA_CHECK(cudaMemcpyAsync(d_send, h_send, sizeof(h_send), cudaMemcpyHostToDevice, st));
+        nccl_allgather(d_send, d_all, W, st);
+        CUDA_CHECK(cudaMemcpyAsync(h_all.data(), d_all, h_all.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int r = 0; r < nranks; ++r) fail |= (h_all[(size_t)r * W + 8] != 0.0);
+        cudaFree(d_send);
+        cudaFree(d_all);
+        if (fail) {
+            release_p2p();
+            (void)cudaGetLastError();  // a refused IPC call is not an error of the path: NCCL carries it
+        } else {
+            p2p = true;
+        }
+    }
+    void release_p2p() {
+        for (int r = 0; r < kP2PMaxRanks; ++r) {
+            if (mapped[r] && r != rank) cudaIpcCloseMemHandle(mapped[r]);
+            mapped[r] = nullptr;
+        }
+        if (region) cudaFree(region);
+        region = nullptr;
+        p2p = false;
+    }
+    // 0: single rank / none, 1: NCCL, 2: peer-memory kernel
+    int mode() const { return nranks <= 1 ? 0 : (p2p && use_p2p ? 2 : 1); }
+
     void allreduce_sum(double* buf, size_t count, cudaStream_t st) {
+        if (exchange(buf, buf, count, kP2PSum, st)) return;
         check(NcclApi::get().AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kSum, comm, st), "ncclAllReduce");
     }
     void allreduce_max(double* buf, size_t count, cudaStream_t st) {
+        if (exchange(buf, buf, count, kP2PMax, st)) return;
         check(NcclApi::get().AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kMax, comm, st), "ncclAllReduce");
     }
     void allgather(const double* send, double* recv, size_t count, cudaStream_t st) {
-        check(NcclApi::get().AllGather(send, recv, count, NcclApi::kFloat64, comm, st), "ncclAllGather");
+        if (exchange(send, recv, count, kP2PGather, st)) return;
+        nccl_allgather(send, recv, count, st);
     }
 
    private:
+    void nccl_allgather(const double* send, double* recv, size_t count, cudaStream_t st) {
+        check(NcclApi::get().AllGather(send, recv, count, NcclApi::kFloat64, comm, st), "ncclAllGather");
+    }
+    bool exchange(const double* send, double* recv, size_t count, int op, cudaStream_t st) {
+        if (!(p2p && use_p2p) || count > (size_t)cap) return false;
+        P2PArgs a{};
+        for (int r = 0; r < nranks; ++r) a.region[r] = mapped[r];
+        a.rank = rank; a.nranks = nranks; a.cap = cap; a.send = send; a.recv = recv; a.count = (int)count; a.op = op;
+        a.timeout_ns = 30ull * 1000000000ull;
+        k_p2p_exchange<<<1, kP2PThreads, 0, st>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        ++p2p_launches;
+        return true;
+    }
     static void check(int rc, const char* what) {
         if (rc != 0)
             throw std::runtime_error(std::string("bioen_b200: ") + what + " failed: " +

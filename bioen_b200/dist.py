@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: the structure axis N is sharded over the ranks of a torch.distributed job (one process
 per GPU).  torch.distributed is used ONLY to bootstrap (broadcast the NCCL unique id, scatter/gather host
-vectors); the per-evaluation collectives are issued by libbioen_b200.so itself on its compute stream
-(csrc/comm.cuh): one all-reduce of M+3 doubles per log-weights evaluation, 1-2 doubles per L-BFGS dot product.
+vectors); the per-evaluation exchanges are issued by libbioen_b200.so itself on its compute stream
+(csrc/comm.cuh: a peer-memory kernel over NVLink, NCCL when peers cannot be mapped): M+3 doubles per log-weights
+evaluation, 1-2 doubles per L-BFGS dot product.
 """
 import ctypes
 

@@ -157,6 +157,10 @@ class Problem:
 
     def comm_init(self, unique_id, rank, nranks, n_total):
         _lib.check(self._lib.bioen_b200_comm_init(self._ctx, unique_id, rank, nranks, int(n_total)), "comm_init")
+
+    def comm_mode(self):
+        """How the per-evaluation exchanges travel: 'single', 'nccl' or 'p2p' (peer-memory kernel over NVLink)."""
+        return ("single", "nccl", "p2p")[self._lib.bioen_b200_comm_mode(self._ctx)]
         self.nranks = nranks
 
     # ---- evaluations --------------------------------------------------------------------------------

@@ -168,9 +168,11 @@ int bioen_b200_download_ytilde(bioen_b200_ctx *ctx, int row0, int nrows, long lo
 int bioen_b200_set_logw(bioen_b200_ctx *ctx, const double *G_host, const double *YTilde_host, double theta);
 int bioen_b200_set_forces(bioen_b200_ctx *ctx, const double *w0_host, const double *YTilde_host, double theta);
 int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
-/* tuning switches (call before bioen_b200_set_forces).  BIOEN_B200_OPT_FUSED_FORCES (default 1): keep a
- * structure-major copy of yTilde and evaluate the forces method in two fused passes instead of four */
-enum { BIOEN_B200_OPT_FUSED_FORCES = 1 };
+/* tuning switches.  BIOEN_B200_OPT_FUSED_FORCES (default 1; call before bioen_b200_set_forces): keep a
+ * structure-major copy of yTilde and evaluate the forces method in two fused passes instead of four.
+ * BIOEN_B200_OPT_P2P (default 1; after bioen_b200_comm_init, on all ranks together): carry the per-evaluation
+ * exchanges with the library's peer-memory kernel over NVLink instead of NCCL. */
+enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
@@ -224,6 +226,8 @@ double bioen_b200_selftest_interpolate(double a, double fa, double fpa, double b
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);
+/* how the per-evaluation exchanges travel: 0 single rank, 1 NCCL, 2 peer-memory kernel (CUDA IPC + NVLink) */
+int bioen_b200_comm_mode(bioen_b200_ctx *ctx);
 
 /* device-pointer entry points (inputs already resident in HBM; used by bench.py and torch carriers).
  * Everything is enqueued on the context's stream; bioen_b200_fetch waits for it. */

@@ -25,7 +25,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    for (M, N, theta) in ((37, 5001, 1.0), (100, 20000, 10.0), (300, 1000 * world + 3, 3.0)):
+    # p2p: exchanges through the library's peer-memory kernel (default); the first case is repeated over NCCL
+    for (M, N, theta, p2p) in ((37, 5001, 1.0, True), (37, 5001, 1.0, False), (100, 20000, 10.0, True),
+                               (300, 1000 * world + 3, 3.0, True)):
         P = O.synthetic_problem(M, N, seed=12345)
         rng = np.random.default_rng(3)
         G = 0.1 * rng.standard_normal(N)
@@ -34,6 +36,9 @@ def main():
         w0 /= w0.sum()
         f1 = 1e-3 * rng.standard_normal(M)
         sp = D.ShardedProblem(P["yTilde"], device=local)
+        sp.p.set_option(2, int(p2p))      # BIOEN_B200_OPT_P2P
+        mode = sp.p.comm_mode()
+        assert p2p or mode == "nccl", mode
         # log-weights evaluation + weights
         sp.set_logw(G, P["YTilde"], theta)
         f, g = sp.objective_and_gradient(g1)
@@ -91,7 +96,7 @@ def main():
             assert np.max(np.abs(fs - fw) / np.abs(fw)) < 1e-9, ("scan forces fmin", M, N, fs, fw)
         sp.close()
         if rank == 0:
-            print("mgpu_check ok: M=%d N=%d world=%d" % (M, N, world), flush=True)
+            print("mgpu_check ok: M=%d N=%d world=%d exchange=%s" % (M, N, world, mode), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

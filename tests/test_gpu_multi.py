@@ -18,4 +18,4 @@ def test_sharded_two_ranks_match_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count("mgpu_check ok") == 3
+    assert res.stdout.count("mgpu_check ok") == 4
