@@ -615,8 +615,8 @@ __global__ void __launch_bounds__(1024) kbf_grad(const BatchBufs b, const KVec p
 
 // ------------------------------------------------------------------------------------------------
 // N-sharded scan (one process per GPU): per-problem scalars that are sums over the structure axis are packed
-// into a contiguous buffer, all-reduced with ONE NCCL call, and unpacked; the (max, sum-exp) pairs are
-// all-gathered and merged.  slot < 0: that problem contributes nothing (finished / masked).
+// into a contiguous buffer, all-reduced with ONE exchange (Comm: peer-memory kernel up to its inbox size, NCCL
+// above), and unpacked; the (max, sum-exp) pairs are all-gathered and merged.  slot < 0: that problem contributes nothing (finished / masked).
 // ------------------------------------------------------------------------------------------------
 struct KSlotTab {
     int n;                          // rows used (<= 4)
