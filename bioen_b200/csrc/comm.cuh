@@ -270,7 +270,7 @@ class Comm {
         P2PArgs a{};
         for (int r = 0; r < nranks; ++r) a.region[r] = mapped[r];
         a.rank = rank; a.nranks = nranks; a.cap = cap; a.send = send; a.recv = recv; a.count = (int)count; a.op = op;
-        a.timeout_ns = 30ull * 1000000000ull;
+        a.timeout_ns = 120ull * 1000000000ull;  // generous: ranks may be skewed by host-side setup
         k_p2p_exchange<<<1, kP2PThreads, 0, st>>>(a);
         CUDA_CHECK(cudaGetLastError());
         ++p2p_launches;
