@@ -341,6 +341,7 @@ def run_b200(args):
         barrier()
         optimum = {"seconds": time.perf_counter() - t0, "code": code, "fmin": fmin,
                    "iterations": info["iterations"], "evaluations": info["evaluations"],
+                   "objective_only_evaluations": info["gradients_skipped"],
                    "minimizer": "device L-BFGS (liblbfgs semantics, BioEn defaults: linesearch=2, past=10, "
                                 "delta=1e-6, epsilon=1e-6)", "includes": "x0 H2D + result D2H; yTilde resident"}
 

@@ -272,6 +272,7 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
     return guarded("bioen_b200_set_option", [&] {
         switch (option) {
             case BIOEN_B200_OPT_FUSED_FORCES: ctx->C.allow_fused = value != 0; break;
+            case BIOEN_B200_OPT_LAZY_GRADIENT: ctx->C.lazy_gradient = value != 0; break;
             case BIOEN_B200_OPT_P2P:
                 if (ctx->comm) ctx->comm->use_p2p = value != 0;
                 break;
@@ -386,7 +387,7 @@ static int run_lbfgs_dev(bioen_b200_ctx* ctx, int method, double* x_dev, lbfgs_c
     if (info) {
         info[0] = opt.stats.iterations;
         info[1] = opt.stats.evaluations;
-        info[2] = 0;
+        info[2] = opt.stats.gradients_skipped;   // of those evaluations: objective only (one pass over Y)
         info[3] = 0;
     }
     if (opt.use_graphs && getenv("BIOEN_B200_GRAPH_TRACE"))
@@ -466,7 +467,7 @@ int bioen_b200_opt_gsl(bioen_b200_ctx* ctx, int method, const double* x0_host, d
             info[0] = st.iterations;
             info[1] = st.n_fdf + st.n_df;
             info[2] = st.n_f;
-            info[3] = 0;
+            info[3] = st.n_df_continued;   // of info[1]: gradient half only (same point as the preceding f probe)
         }
         if (visual.verbose) {
             printf("\t%s\n", bioen_gsl_error(r));

@@ -180,6 +180,7 @@ class Context {
 
     // forget the problem but keep every allocation (stateless reference entry points reuse a cached context)
     void reset_for_reuse() {
+        ++eval_gen;
         sync();
         have_logw = have_forces = false;
         fused_ready = false;
@@ -323,10 +324,11 @@ class Context {
     void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
     void set_observations(const double* Y_host) { h2d(Yobs.p, Y_host, M); }
-    void set_theta(double th) { theta = th; }
+    void set_theta(double th) { theta = th; ++eval_gen; }
 
     // logw: reference log-weights G (this rank's slice); log s0 = log sum_j exp(G_j) over ALL ranks
     void set_logw(const double* G_host, bool on_device = false) {
+        ++eval_gen;
         Gv.ensure(Npad + 8);
         if (on_device) d2d(Gv.p, G_host, N); else h2d(Gv.p, G_host, N);
         aux_n.ensure(Npad + 8);  // scratch x for the lse of G
@@ -350,6 +352,7 @@ class Context {
     }
     // forces: reference weights w0 (this rank's slice)
     void set_forces(const double* w0_host, bool on_device = false) {
+        ++eval_gen;
         Gv.ensure(Npad + 8);      // holds w0
         if (on_device) d2d(Gv.p, w0_host, N); else h2d(Gv.p, w0_host, N);
         aux_n.ensure(Npad + 8);   // x_j, later E_j (zero padded: it feeds the row pass)
@@ -472,8 +475,7 @@ class Context {
         ++kernels_launched;
         if (nranks > 1) comm->allreduce_sum(msum.p, M + ntail, stream);
     }
-    void forces_eval_fused(double* x, const double* xp, const double* d, double stp, double* grad,
-                           const double* ddir, const double* stp_dev = nullptr) {
+    void forces_eval_fused_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev) {
         {
             ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p, stp_dev};
             k_forces_update<<<1, 1024, 0, stream>>>(a);
@@ -493,7 +495,8 @@ class Context {
         }
         merge_fused_rows(true, 1);
         finalize_rows_from_msum(true, false);
-        if (!grad) return;
+    }
+    void forces_eval_fused_g(double* grad, const double* ddir) {
         launch_fused<kFusedGradient>(avg.p, w.p, aux_n2.p, nullptr);       // t_j, E_j, grad partials
         merge_fused_rows(false, 0);
         {
@@ -597,9 +600,20 @@ class Context {
     // ---- log-weights evaluation (c_bioen_kernels_logw.c:525-561) ------------------------------------------
     // x (device, N): evaluated point; when xp != nullptr it is first formed as xp + stp*d.
     // grad == nullptr -> objective only (one pass over Y).  ddir: optional direction for sc[SC_DG].
+    // The evaluation is split at the point where the objective is complete: logw_eval_f leaves w, avg and the
+    // residuals on the device, logw_eval_g adds the gradient of that same point (callers that learn from f alone
+    // that the gradient is not needed -- a backtracking trial that fails the Armijo test, GSL's f-then-df pattern --
+    // skip or defer the second pass over Y).  eval_gen changes with every objective evaluation.
+    long long eval_gen = 0;
+    bool lazy_gradient = true;   // BIOEN_B200_OPT_LAZY_GRADIENT: minimisers may use the split (results identical)
     void logw_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir,
                    const double* stp_dev = nullptr) {
+        logw_eval_f(x, xp, d, stp, stp_dev);
+        if (grad) logw_eval_g(x, grad, ddir);
+    }
+    void logw_eval_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev = nullptr) {
         if (!have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
+        ++eval_gen;
         launch_lse(x, xp, d, stp, nullptr, false, stp_dev);
         gather_lse();
         {
@@ -611,7 +625,8 @@ class Context {
         }
         launch_pass<kRowPass, false>(w.p, nullptr);
         finalize_rows(false, 3, true);
-        if (!grad) return;
+    }
+    void logw_eval_g(const double* x, double* grad, const double* ddir) {
         launch_pass<kColPass, true>(nullptr, nullptr);
         {
             LogwGradArgs a{};
@@ -625,6 +640,7 @@ class Context {
     }
     // weights only (the reference's _get_weights): w normalised over all ranks; returns nothing, see sc[]
     void logw_weights_only(double* x) {
+        ++eval_gen;
         launch_lse(x, nullptr, nullptr, 0.0, nullptr, false);
         gather_lse();
         LogwWeightsArgs a{};
@@ -639,9 +655,15 @@ class Context {
     // on every rank.  grad == nullptr -> objective only (two passes over Y).
     void forces_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir,
                      const double* stp_dev = nullptr) {
+        forces_eval_f(x, xp, d, stp, stp_dev);
+        if (grad) forces_eval_g(grad, ddir);
+    }
+    bool forces_fused_now() const { return fused_ready && allow_fused; }
+    void forces_eval_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev = nullptr) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
-        if (fused_ready && allow_fused) {
-            forces_eval_fused(x, xp, d, stp, grad, ddir, stp_dev);
+        ++eval_gen;
+        if (forces_fused_now()) {
+            forces_eval_fused_f(x, xp, d, stp, stp_dev);
             return;
         }
         {
@@ -662,7 +684,13 @@ class Context {
         }
         launch_pass<kRowPass, false>(w.p, nullptr);                     // avg_i
         finalize_rows(true, 1, false);                                  // r_i, chi2, f; ab = {r_i, 0}
-        if (!grad) return;
+    }
+    // gradient of the point forces_eval_f was last called for
+    void forces_eval_g(double* grad, const double* ddir) {
+        if (forces_fused_now()) {
+            forces_eval_fused_g(grad, ddir);
+            return;
+        }
         launch_pass<kColPass, false>(nullptr, nullptr);                 // t_j = sum_i y_ij r_i
         {
             ForcesEArgs a{};
@@ -688,6 +716,7 @@ class Context {
     }
     // weights only (the reference's _get_weights_from_forces): leaves normalised w in `w`
     void forces_weights_only(double* x) {
+        ++eval_gen;
         ForcesUpdateArgs u{M, x, nullptr, nullptr, 0.0, ab.p, sc.p, nullptr};
         k_forces_update<<<1, 1024, 0, stream>>>(u);
         launch_pass<kColPass, false>(nullptr, nullptr);
@@ -704,6 +733,7 @@ class Context {
     // (reference semantics of _bioen_log_posterior_forces / _grad_bioen_log_posterior_forces,
     // c_bioen_kernels_forces.c:227-340)
     void forces_from_weights(double* grad) {
+        ++eval_gen;
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         {
             ForcesLrArgs a{N, w.p, Gv.p, aux_n2.p, msum.p + M, red_partials.p, ticket.p};
@@ -738,6 +768,7 @@ class Context {
     }
     // avg = Y . v for an arbitrary N-vector v already in `w` (post-processing: yopt = y . wopt)
     void average_of_w(double* avg_out_dev) {
+        ++eval_gen;
         launch_pass<kRowPass, false>(w.p, nullptr);
         k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
         ++kernels_launched;

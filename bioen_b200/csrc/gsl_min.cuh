@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kVecThreads) k_count_diff(int n, const double*
 
 struct GslStats {
     int iterations = 0, n_f = 0, n_df = 0, n_fdf = 0;
+    int n_df_continued = 0;   // of n_df: gradient of the point f() had just evaluated -> second half only
 };
 
 // vector toolbox on the context's stream
@@ -125,6 +126,14 @@ class VecOps {
         ++stats.n_df;
         if (forces) C.forces_eval(x, nullptr, nullptr, 0.0, g, nullptr);
         else C.logw_eval(x, nullptr, nullptr, 0.0, g, nullptr);
+    }
+    // gradient at the point the context evaluated LAST with f() (weights, averages and residuals are still on the
+    // device): only the gradient half of the evaluation runs.  The caller guarantees the point is the same.
+    void df_continue(double* x, double* g) {
+        ++stats.n_df;
+        ++stats.n_df_continued;
+        if (forces) C.forces_eval_g(g, nullptr);
+        else C.logw_eval_g(x, g, nullptr);
     }
     double fdf(double* x, double* g) {
         ++stats.n_fdf;
@@ -222,6 +231,10 @@ struct LineWrapper {
     double *x_alpha, *g_alpha;
     double f_alpha = 0, df_alpha = 0;
     double f_key = 0, df_key = 0, x_key = 0, g_key = 0;
+    // which alpha the context's evaluation state (w, avg, residuals) belongs to: set by f(), void after any other
+    // evaluation (eval_gen moves) or a change of x / p.  GSL's Fletcher search asks f(alpha) and then df(alpha).
+    double state_key = 0;
+    long long state_gen = -1;
 
     LineWrapper(VecOps& v, double* x_, double f_, double* g_, double* p_, double* xa, double* ga)
         : V(v), x(x_), g(g_), p(p_), x_alpha(xa), g_alpha(ga) {
@@ -240,13 +253,16 @@ struct LineWrapper {
         moveto(alpha);
         f_alpha = V.f(x_alpha);
         f_key = alpha;
+        state_key = alpha;
+        state_gen = V.C.eval_gen;
         return f_alpha;
     }
     double df(double alpha) {
         if (alpha == df_key) return df_alpha;
         moveto(alpha);
         if (alpha != g_key) {
-            V.df(x_alpha, g_alpha);
+            if (V.C.lazy_gradient && state_gen == V.C.eval_gen && alpha == state_key) V.df_continue(x_alpha, g_alpha);
+            else V.df(x_alpha, g_alpha);
             g_key = alpha;
         }
         df_alpha = V.dot(g_alpha, p);
@@ -271,6 +287,7 @@ struct LineWrapper {
         return f_alpha;
     }
     void change_direction() {
+        state_gen = -1;
         V.copy(x_alpha, x);
         x_key = 0.0;
         f_key = 0.0;

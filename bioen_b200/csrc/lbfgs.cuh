@@ -72,6 +72,7 @@ struct LbfgsParams {  // lbfgs.h lbfgs_parameter_t with _defparam (lbfgs.c:113-1
 
 struct LbfgsStats {
     int iterations = 0, evaluations = 0;
+    int gradients_skipped = 0;   // trials whose gradient pass was not needed (sufficient-decrease test failed)
     double seconds = 0.0;
     double gpu_eval_ms = 0.0, gpu_update_ms = 0.0, host_wait_s = 0.0;   // BIOEN_B200_TRACE=1
 };
@@ -206,14 +207,20 @@ struct LineSearchState {
             stp = stx;
         return stp;
     }
+    // backtracking searches look at the slope of a trial only when its value passes the sufficient-decrease
+    // test (lbfgs.c:683-709), so the caller may skip the gradient of a trial that fails it
+    bool needs_slope(double f) const {
+        if (prm->linesearch == 0) return true;
+        const double dgtest = prm->ftol * dginit;
+        return !(f > finit + stp * dgtest);
+    }
     // 0: another trial needed (stp updated); > 0: accepted after that many trials; < 0: liblbfgs error code
     int update(double f, double dg) {
         const LbfgsParams& p = *prm;
         ++count;
         if (p.linesearch != 0) {
-            const double dgtest = p.ftol * dginit;
             double w;
-            if (f > finit + stp * dgtest) {
+            if (!needs_slope(f)) {
                 w = 0.5;
             } else {
                 if (p.linesearch == 1) return count;
@@ -375,7 +382,10 @@ class Lbfgs {
 
    private:
     // enqueue one f+g evaluation at x (= xp + stp*dir when xp_ given); dg direction optional
-    void eval(const double* xp_, const double* dir, double stp, const double* ddir) {
+    // returns true when h_sc already holds everything the caller will read (objective-only trial)
+    bool eval(const double* xp_, const double* dir, double stp, const double* ddir,
+              const LineSearchState* ls = nullptr) {
+        bool fetched = false;
         if (trace) {
             if (!tev[0]) for (auto& e : tev) cudaEventCreate(&e);
             cudaEventRecord(tev[2], C.stream);          // end of the previous update phase
@@ -389,10 +399,28 @@ class Lbfgs {
             }
             cudaEventRecord(tev[0], C.stream);
         }
-        if (forces) C.forces_eval(x, xp_, dir, stp, g, ddir);
-        else C.logw_eval(x, xp_, dir, stp, g, ddir);
+        if (!ls) {
+            if (forces) C.forces_eval(x, xp_, dir, stp, g, ddir);
+            else C.logw_eval(x, xp_, dir, stp, g, ddir);
+        } else {
+            // line-search trial: the objective first (one pass over Y); the gradient pass only if the search will
+            // look at the slope.  A trial that fails the sufficient-decrease test is discarded by liblbfgs without
+            // its gradient ever being read (the next trial overwrites it; on failure x and g are restored), so
+            // skipping it changes no result.
+            if (forces) C.forces_eval_f(x, xp_, dir, stp);
+            else C.logw_eval_f(x, xp_, dir, stp);
+            C.fetch_scalars();
+            if (ls->needs_slope(C.h_sc[SC_F])) {
+                if (forces) C.forces_eval_g(g, ddir);
+                else C.logw_eval_g(x, g, ddir);
+            } else {
+                ++stats.gradients_skipped;
+                fetched = true;
+            }
+        }
         if (trace) cudaEventRecord(tev[1], C.stream);
         ++stats.evaluations;
+        return fetched;
     }
 
     // ---- CUDA-graph plumbing ---------------------------------------------------------------------------
@@ -425,7 +453,7 @@ class Lbfgs {
     }
 
     // one line-search trial at x = xp + stp*d: evaluation + scalar read-back (host side of lbfgs.c:645-1001)
-    void trial(double stp) {
+    void trial(double stp, const LineSearchState& ls) {
         if (use_graphs) {
             if (!g_trial) {
                 g_trial = capture([&] {
@@ -450,8 +478,8 @@ class Lbfgs {
                 return;
             }
         }
-        eval(xp, d, stp, d);
-        C.fetch_scalars();
+        // More-Thuente reads the slope of every trial: plain f+g evaluation, one read-back
+        if (!eval(xp, d, stp, d, (prm.linesearch != 0 && C.lazy_gradient) ? &ls : nullptr)) C.fetch_scalars();
     }
 
     void enqueue_update(int end_old, int bound, int m) {
@@ -543,7 +571,7 @@ class Lbfgs {
         ls.start(prm, f, dginit, stp);
         for (;;) {
             stp = ls.prepare();
-            trial(stp);
+            trial(stp, ls);
             f = h[SC_F];
             const int verdict = ls.update(f, h[SC_DG]);
             if (verdict != 0) return verdict;

@@ -231,7 +231,7 @@ class Problem:
         code = self._lib.bioen_b200_opt_lbfgs(self._ctx, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
         if code == -2000:
             raise RuntimeError("bioen_b200_opt_lbfgs failed: " + _lib.last_error())
-        return x, fmin.value, code, dict(iterations=info[0], evaluations=info[1])
+        return x, fmin.value, code, dict(iterations=info[0], evaluations=info[1], gradients_skipped=info[2])
 
     def opt_gsl(self, x0, method=None, verbose=0, **cfg):
         """Device-resident GSL-style minimisers.  Returns (x, fmin, status, info)."""
@@ -248,7 +248,8 @@ class Problem:
         code = self._lib.bioen_b200_opt_gsl(self._ctx, method, _lib.ptr(x0), _lib.ptr(x), c, v, C.byref(fmin), info)
         if code == -2000:
             raise RuntimeError("bioen_b200_opt_gsl failed: " + _lib.last_error())
-        return x, fmin.value, code, dict(iterations=info[0], gradient_evaluations=info[1], f_only_evaluations=info[2])
+        return x, fmin.value, code, dict(iterations=info[0], gradient_evaluations=info[1], f_only_evaluations=info[2],
+                                          gradient_half_only=info[3])
 
     def theta_scan(self, thetas, x0=None, method=None, verbose=0, **cfg):
         """Minimise the problem for up to 32 theta values TOGETHER (lockstep L-BFGS, batched fp64 tensor-core

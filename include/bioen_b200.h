@@ -171,8 +171,11 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
 /* tuning switches.  BIOEN_B200_OPT_FUSED_FORCES (default 1; call before bioen_b200_set_forces): keep a
  * structure-major copy of yTilde and evaluate the forces method in two fused passes instead of four.
  * BIOEN_B200_OPT_P2P (default 1; after bioen_b200_comm_init, on all ranks together): carry the per-evaluation
- * exchanges with the library's peer-memory kernel over NVLink instead of NCCL. */
-enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2 };
+ * exchanges with the library's peer-memory kernel over NVLink instead of NCCL.
+ * BIOEN_B200_OPT_LAZY_GRADIENT (default 1): the minimisers run the gradient half of an evaluation only when the
+ * algorithm reads it (backtracking trials that fail the sufficient-decrease test skip it; GSL's f-then-df on one
+ * point does not repeat the objective half).  Results are bit-identical either way; 0 exists for that comparison. */
+enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
@@ -187,8 +190,11 @@ int bioen_b200_forces_from_weights(bioen_b200_ctx *ctx, const double *w_host, do
 
 /* minimisers; x0_host/x_host have n (logw) or m (forces) entries and may alias.  The function result is the
  * minimiser's own status (liblbfgs return code / GSL status, see part 1); *fmin the final objective;
- * info[0] = iterations, info[1] = f+g evaluations (f-only probes counted in info[2]).  A CUDA failure returns
- * -2000 and sets bioen_b200_last_error(). */
+ * info[0] = iterations.  GSL: info[1] = gradient evaluations, info[2] = f-only probes, info[3] = how many of info[1]
+ * asked for the gradient of the point just probed and ran only the gradient half.  L-BFGS: info[1] = callback
+ * evaluations as liblbfgs counts them, info[2] = how many of those were line-search trials that failed the
+ * sufficient-decrease test, for which the gradient pass over yTilde was skipped (liblbfgs never reads it).
+ * A CUDA failure returns -2000 and sets bioen_b200_last_error(). */
 int bioen_b200_opt_lbfgs(bioen_b200_ctx *ctx, int method, const double *x0_host, double *x_host,
                          lbfgs_config_params config, visual_params visual, double *fmin, int info[4]);
 int bioen_b200_opt_gsl(bioen_b200_ctx *ctx, int method, const double *x0_host, double *x_host,

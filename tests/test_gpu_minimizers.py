@@ -320,3 +320,36 @@ def test_minimiser_bit_reproducibility():
                 assert f == f_ref and c == c_ref and np.array_equal(x, x_ref)
                 x, f, c, _ = p.opt_lbfgs(x0)
                 assert f == fl_ref and c == cl_ref and np.array_equal(x, xl_ref)
+
+
+def test_lazy_gradient_is_bit_identical(oracle):
+    """BIOEN_B200_OPT_LAZY_GRADIENT: the minimisers skip (backtracking trials that fail the sufficient-decrease
+    test) or defer (GSL's f-then-df on one point) the gradient half of an evaluation.  liblbfgs / GSL never read
+    what is skipped, so end point, objective, code and evaluation counts must not move by a bit."""
+    import bioen_b200
+    skipped = continued = 0
+    for (M, N, theta) in ((100, 20000, 10.0), (50, 20000, 1.0), (300, 3001, 3.0)):
+        P = oracle.synthetic_problem(M, N, seed=12345)
+        with bioen_b200.Problem(P["yTilde"]) as p:
+            for method, setter, x0 in (("logw", lambda: p.set_logw(P["G"], P["YTilde"], theta), P["GInit"]),
+                                       ("forces", lambda: p.set_forces(P["w0"], P["YTilde"], theta),
+                                        P["forces_init"])):
+                setter()
+                for ls in (1, 2, 3):
+                    p.set_option(3, 1)
+                    x1, f1, c1, i1 = p.opt_lbfgs(x0, linesearch=ls, max_iterations=60)
+                    p.set_option(3, 0)
+                    x0_, f0, c0, i0 = p.opt_lbfgs(x0, linesearch=ls, max_iterations=60)
+                    assert c1 == c0 and f1 == f0 and np.array_equal(x1, x0_), (method, M, N, ls)
+                    assert i1["iterations"] == i0["iterations"] and i1["evaluations"] == i0["evaluations"]
+                    assert i0["gradients_skipped"] == 0
+                    skipped += i1["gradients_skipped"]
+                p.set_option(3, 1)
+                x1, f1, c1, i1 = p.opt_gsl(x0, max_iterations=40)
+                p.set_option(3, 0)
+                x0_, f0, c0, i0 = p.opt_gsl(x0, max_iterations=40)
+                assert c1 == c0 and f1 == f0 and np.array_equal(x1, x0_), (method, M, N, "gsl")
+                assert i1["gradient_evaluations"] == i0["gradient_evaluations"] and i0["gradient_half_only"] == 0
+                continued += i1["gradient_half_only"]
+                p.set_option(3, 1)
+    assert skipped > 0 and continued > 0     # the short cuts were actually taken
