@@ -82,6 +82,7 @@ SIGNATURES = {
     "bioen_b200_set_theta": (C.c_int, [_vp, C.c_double]),
     "bioen_b200_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "bioen_b200_eval": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
+    "bioen_b200_grad_continue": (C.c_int, [_vp, C.c_int, _dp]),
     "bioen_b200_weights": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "bioen_b200_average": (C.c_int, [_vp, _dp, _dp]),
     "bioen_b200_forces_from_weights": (C.c_int, [_vp, _dp, _dp, _dp]),

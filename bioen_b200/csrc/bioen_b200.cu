@@ -65,6 +65,8 @@ struct bioen_b200_ctx {
     Context C;
     std::unique_ptr<Comm> comm;
     DevBuf<double> xn, gn, xm, gm;  // staging vectors for host-pointer calls
+    long long pending_gen = -1;     // C.eval_gen of the last objective-only bioen_b200_eval (bioen_b200_grad_continue)
+    int pending_method = -1;
     bioen_b200_ctx(int m, int n, int dev) : C(m, n, dev) {}
     double* x_for(int method) {
         if (method == BIOEN_B200_FORCES) {
@@ -185,6 +187,7 @@ void bioen_b200_destroy(bioen_b200_ctx* ctx) {
 
 int bioen_b200_upload_ytilde(bioen_b200_ctx* ctx, const double* yTilde_host, size_t ld) {
     return guarded("bioen_b200_upload_ytilde", [&] {
+        ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
         ctx->C.upload_matrix(yTilde_host, ld);
         ctx->C.sync();
@@ -193,6 +196,7 @@ int bioen_b200_upload_ytilde(bioen_b200_ctx* ctx, const double* yTilde_host, siz
 
 int bioen_b200_adopt_ytilde(bioen_b200_ctx* ctx, double* yTilde_dev, size_t ld) {
     return guarded("bioen_b200_adopt_ytilde", [&] {
+        ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
         ctx->C.adopt_matrix(yTilde_dev, ld);
     });
@@ -200,6 +204,7 @@ int bioen_b200_adopt_ytilde(bioen_b200_ctx* ctx, double* yTilde_dev, size_t ld) 
 
 int bioen_b200_upload_rows(bioen_b200_ctx* ctx, int row0, int nrows, const double* rows_host, size_t ld) {
     return guarded("bioen_b200_upload_rows", [&] {
+        ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         if (!C.Y) C.alloc_matrix();
@@ -225,6 +230,7 @@ void bioen_b200_host_free(void* p) {
 
 int bioen_b200_alloc_ytilde(bioen_b200_ctx* ctx) {
     return guarded("bioen_b200_alloc_ytilde", [&] {
+        ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
         ctx->C.alloc_matrix();
     });
@@ -251,6 +257,7 @@ int bioen_b200_set_forces(bioen_b200_ctx* ctx, const double* w0_host, const doub
 
 int bioen_b200_set_logw_dev(bioen_b200_ctx* ctx, const double* G_dev, const double* YTilde_host, double theta) {
     return guarded("bioen_b200_set_logw_dev", [&] {
+        ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
         ctx->C.set_observations(YTilde_host);
         ctx->C.set_theta(theta);
@@ -260,6 +267,7 @@ int bioen_b200_set_logw_dev(bioen_b200_ctx* ctx, const double* G_dev, const doub
 
 int bioen_b200_set_forces_dev(bioen_b200_ctx* ctx, const double* w0_dev, const double* YTilde_host, double theta) {
     return guarded("bioen_b200_set_forces_dev", [&] {
+        ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
         ctx->C.set_observations(YTilde_host);
         ctx->C.set_theta(theta);
@@ -299,6 +307,22 @@ int bioen_b200_eval(bioen_b200_ctx* ctx, int method, const double* x_host, doubl
         if (grad_host) C.d2h(grad_host, g, n);
         C.fetch_scalars();
         if (f) *f = C.h_sc[SC_F];
+        if (!grad_host) { ctx->pending_gen = C.eval_gen; ctx->pending_method = method; }
+    });
+}
+
+int bioen_b200_grad_continue(bioen_b200_ctx* ctx, int method, double* grad_host) {
+    // nothing evaluated, or the device state has moved on since the objective-only evaluation: not an error
+    if (!grad_host || ctx->pending_method != method || ctx->pending_gen != ctx->C.eval_gen) return 2;
+    return guarded("bioen_b200_grad_continue", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        const int n = ctx->dim(method);
+        double* g = ctx->g_for(method);
+        if (method == BIOEN_B200_FORCES) C.forces_eval_g(g, nullptr);
+        else C.logw_eval_g(ctx->x_for(method), g, nullptr);
+        C.d2h(grad_host, g, n);
+        C.fetch_scalars();
     });
 }
 
@@ -487,6 +511,7 @@ int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int method, int K, const double* 
                           lbfgs_config_params config, visual_params visual, double* fmin, int* codes, int* info,
                           double* stats) {
     return guarded("bioen_b200_theta_scan", [&] {
+        ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         const auto t0 = std::chrono::steady_clock::now();
@@ -517,6 +542,7 @@ int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int method, int K, const double* 
 int bioen_b200_time_scan_evals(bioen_b200_ctx* ctx, int method, int K, const double* thetas, const double* x0_host,
                                int warmup, int steps, float* ms, float* gemm_ms, long long* launches) {
     return guarded("bioen_b200_time_scan_evals", [&] {
+        ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         ThetaScan scan(C, K, LbfgsParams(), method == BIOEN_B200_FORCES);
@@ -590,6 +616,7 @@ int bioen_b200_nccl_unique_id(char id[128]) {
 
 int bioen_b200_comm_init(bioen_b200_ctx* ctx, const char id[128], int rank, int nranks, long long n_total) {
     return guarded("bioen_b200_comm_init", [&] {
+        ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
         ctx->comm.reset(new Comm(id, rank, nranks));
         ctx->C.set_comm(ctx->comm.get());
@@ -605,6 +632,7 @@ int bioen_b200_comm_mode(bioen_b200_ctx* ctx) { return ctx->comm ? ctx->comm->mo
 
 int bioen_b200_eval_dev(bioen_b200_ctx* ctx, int method, double* x_dev, double* grad_dev) {
     return guarded("bioen_b200_eval_dev", [&] {
+        ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         if (method == BIOEN_B200_FORCES) C.forces_eval(x_dev, nullptr, nullptr, 0.0, grad_dev, nullptr);
@@ -624,6 +652,7 @@ int bioen_b200_fetch(bioen_b200_ctx* ctx, double* f, double* gnorm2) {
 int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double* grad_dev, int warmup, int steps,
                           float* ms, float* pass_ms, long long* launches) {
     return guarded("bioen_b200_time_evals", [&] {
+        ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         const bool forces = (method == BIOEN_B200_FORCES);
@@ -668,6 +697,7 @@ int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double
 int bioen_b200_generate_ytilde(bioen_b200_ctx* ctx, unsigned long long seed, long long col_offset,
                                const double* ytrue_over_sigma_host, double inv_sigma) {
     return guarded("bioen_b200_generate_ytilde", [&] {
+        ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         if (!C.Y) C.alloc_matrix();

@@ -181,6 +181,10 @@ int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
  * two for logw, two instead of four for forces). */
 int bioen_b200_eval(bioen_b200_ctx *ctx, int method, const double *x_host, double *f, double *grad_host);
+/* gradient at the point of the LAST objective-only bioen_b200_eval of `method` (SciPy-style callers ask f(x) and
+ * then fprime(x)): only the gradient half runs, bit-identical to a full evaluation.  Returns 2 and does nothing
+ * when no such evaluation is pending (any other call on the context in between voids it). */
+int bioen_b200_grad_continue(bioen_b200_ctx *ctx, int method, double *grad_host);
 /* weights for log-weights g[n] / forces f[m]; w_host[n]; *sum (may be NULL) = sum_j exp(g_j) for logw */
 int bioen_b200_weights(bioen_b200_ctx *ctx, int method, const double *x_host, double *w_host, double *sum);
 /* avg[m] = yTilde . w for host w[n] (post-processing with the resident matrix) */

@@ -281,3 +281,34 @@ def test_reported_error_does_not_leak_into_the_next_stateless_call(oracle):
     f = c_bioen.bioen_log_posterior_logw(np.zeros(50), np.zeros(50), np.zeros(50), P["yTilde"], P["YTilde"], 2.0)
     fo, _ = oracle.logw_fg(np.zeros(50), np.zeros(50), P["yTilde"], P["YTilde"], 2.0)
     assert rel(f, fo) < TOL
+
+
+@pytest.mark.parametrize("M,N", [(37, 5001), (300, 3000)])
+def test_gradient_after_objective_runs_the_gradient_half_only(oracle, M, N):
+    """SciPy-style callers ask f(x) and then fprime(x): Problem.gradient continues the pending objective-only
+    evaluation (bioen_b200_grad_continue).  Bit-identical to a full evaluation; anything in between voids it."""
+    P = oracle.synthetic_problem(M, N, seed=7)
+    rng = np.random.default_rng(1)
+    with _problem(P["yTilde"]) as p:
+        for setter, x in ((lambda: p.set_logw(P["G"], P["YTilde"], 4.0), np.ravel(P["G"]) + 0.1 * rng.standard_normal(N)),
+                          (lambda: p.set_forces(P["w0"], P["YTilde"], 4.0), 1e-3 * rng.standard_normal(M))):
+            setter()
+            f_full, g_full = p.objective_and_gradient(x)
+            k0 = p.kernels_launched()
+            f = p.objective(x)
+            k1 = p.kernels_launched()
+            g = p.gradient(x)                       # continuation
+            k2 = p.kernels_launched()
+            assert f == f_full and np.array_equal(g, g_full)
+            g2 = p.gradient(x)                      # nothing pending any more: full evaluation
+            k3 = p.kernels_launched()
+            assert np.array_equal(g2, g_full)
+            assert (k2 - k1) < (k3 - k2) and (k1 - k0) + (k2 - k1) == (k3 - k2)
+            p.objective(x)
+            p.weights(x)                            # moves the device state: the probe is void
+            assert np.array_equal(p.gradient(x), g_full)
+            p.objective(x)
+            y = x.copy()
+            y[0] += 1e-3                            # another point: full evaluation there
+            assert np.array_equal(p.gradient(y), p.objective_and_gradient(y)[1])
+            assert p._lib.bioen_b200_grad_continue(p._ctx, p.method, None) == 2
