@@ -491,7 +491,7 @@ int bioen_b200_opt_gsl(bioen_b200_ctx* ctx, int method, const double* x0_host, d
             info[0] = st.iterations;
             info[1] = st.n_fdf + st.n_df;
             info[2] = st.n_f;
-            info[3] = st.n_df_continued;   // of info[1]: gradient half only (same point as the preceding f probe)
+            info[3] = st.n_df_continued;   // of info[1]: ran one half of the evaluation only (see GslStats)
         }
         if (visual.verbose) {
             printf("\t%s\n", bioen_gsl_error(r));

@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(kVecThreads) k_count_diff(int n, const double*
 
 struct GslStats {
     int iterations = 0, n_f = 0, n_df = 0, n_fdf = 0;
-    int n_df_continued = 0;   // of n_df: gradient of the point f() had just evaluated -> second half only
+    int n_df_continued = 0;   // evaluations that ran one half only: df of the point f() had just evaluated, or an
+                              // fdf whose gradient the algorithm discards (steepest descent's rejected steps)
 };
 
 // vector toolbox on the context's stream
@@ -115,12 +116,39 @@ class VecOps {
         return v == 0.0;
     }
     // ---- the three GSL callbacks (c_bioen_kernels_logw.c:274-362, c_bioen_kernels_forces.c:347-428)
+    long long f_gen = -1;        // C.eval_gen right after the last f(): df_same_point may continue it
+    const double* f_x = nullptr;
     double f(double* x) {
         ++stats.n_f;
         if (forces) C.forces_eval(x, nullptr, nullptr, 0.0, nullptr, nullptr);
         else C.logw_eval(x, nullptr, nullptr, 0.0, nullptr, nullptr);
         C.fetch_scalars();
+        f_gen = C.eval_gen;
+        f_x = x;
         return C.h_sc[SC_F];
+    }
+    // fdf(x, g) for a caller that discards the gradient when f > f_limit (steepest_descent.c:117-127 retries with a
+    // shorter step): the gradient half runs only when it will be kept
+    double fdf_unless_above(double* x, double* g, double f_limit) {
+        if (!C.lazy_gradient) return fdf(x, g);
+        ++stats.n_fdf;
+        if (forces) C.forces_eval_f(x, nullptr, nullptr, 0.0);
+        else C.logw_eval_f(x, nullptr, nullptr, 0.0);
+        C.fetch_scalars();
+        const double fx = C.h_sc[SC_F];
+        if (fx > f_limit) {
+            ++stats.n_df_continued;
+            return fx;
+        }
+        if (forces) C.forces_eval_g(g, nullptr);
+        else C.logw_eval_g(x, g, nullptr);
+        return fx;
+    }
+    // df(x, g) for call sites where x still holds the point the immediately preceding f(x) evaluated
+    // (directional_minimize.c evaluates f at a trial point and, if it is kept, the gradient there)
+    void df_same_point(double* x, double* g) {
+        if (C.lazy_gradient && f_x == x && f_gen == C.eval_gen) df_continue(x, g);
+        else df(x, g);
     }
     void df(double* x, double* g) {
         ++stats.n_df;
@@ -460,7 +488,7 @@ struct Directional : MinimizerBase {
             step = stepc * 2.0;
             f = fc;
             V.copy(x, x1);
-            V.df(x1, gradient);
+            V.df_same_point(x1, gradient);
             return GSL_SUCCESS;
         }
         // intermediate_point (directional_minimize.c:31-83)
@@ -477,7 +505,7 @@ struct Directional : MinimizerBase {
                 }
                 fb = V.f(x1);
                 if (fb >= fa && stepb > 0.0) { fcc = fb; stepcc = stepb; continue; }
-                V.df(x1, gradient);
+                V.df_same_point(x1, gradient);
                 break;
             }
         }
@@ -518,7 +546,7 @@ struct Directional : MinimizerBase {
                     fw = fv; fv = fu; fu = fm;
                     V.copy(x2, x1);
                     V.copy(dx2, dx1);
-                    V.df(x1, gradient);
+                    V.df_same_point(x1, gradient);
                     double t[3];
                     V.dots(p, gradient, gradient, gradient, nullptr, nullptr, t);
                     const double pg1 = t[0], gnorm1 = std::sqrt(t[1]);
@@ -597,7 +625,7 @@ struct SteepestDescent : MinimizerBase {  // steepest_descent.c
             V.axpby(-stp / gnorm, gradient, 0.0, nullptr, dx);
             V.axpby(1.0, x, 1.0, dx, x1);
             if (V.equal(x, x1)) return GSL_ENOPROG;
-            f1 = V.fdf(x1, g1);
+            f1 = V.fdf_unless_above(x1, g1, f0);
             if (f1 > f0) { failed = true; stp *= tol; continue; }
             break;
         }

@@ -195,7 +195,7 @@ int bioen_b200_forces_from_weights(bioen_b200_ctx *ctx, const double *w_host, do
 /* minimisers; x0_host/x_host have n (logw) or m (forces) entries and may alias.  The function result is the
  * minimiser's own status (liblbfgs return code / GSL status, see part 1); *fmin the final objective;
  * info[0] = iterations.  GSL: info[1] = gradient evaluations, info[2] = f-only probes, info[3] = how many of info[1]
- * asked for the gradient of the point just probed and ran only the gradient half.  L-BFGS: info[1] = callback
+ * ran one half of the evaluation only (gradient of the point just probed; rejected steepest-descent steps).  L-BFGS: info[1] = callback
  * evaluations as liblbfgs counts them, info[2] = how many of those were line-search trials that failed the
  * sufficient-decrease test, for which the gradient pass over yTilde was skipped (liblbfgs never reads it).
  * A CUDA failure returns -2000 and sets bioen_b200_last_error(). */

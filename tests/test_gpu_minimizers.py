@@ -327,7 +327,7 @@ def test_lazy_gradient_is_bit_identical(oracle):
     test) or defer (GSL's f-then-df on one point) the gradient half of an evaluation.  liblbfgs / GSL never read
     what is skipped, so end point, objective, code and evaluation counts must not move by a bit."""
     import bioen_b200
-    skipped = continued = 0
+    skipped, continued = 0, [0] * 5
     for (M, N, theta) in ((100, 20000, 10.0), (50, 20000, 1.0), (300, 3001, 3.0)):
         P = oracle.synthetic_problem(M, N, seed=12345)
         with bioen_b200.Problem(P["yTilde"]) as p:
@@ -344,12 +344,15 @@ def test_lazy_gradient_is_bit_identical(oracle):
                     assert i1["iterations"] == i0["iterations"] and i1["evaluations"] == i0["evaluations"]
                     assert i0["gradients_skipped"] == 0
                     skipped += i1["gradients_skipped"]
+                for alg in range(5):     # conjugate_fr, conjugate_pr, bfgs2, bfgs, steepest_descent
+                    p.set_option(3, 1)
+                    x1, f1, c1, i1 = p.opt_gsl(x0, algorithm=alg, max_iterations=25)
+                    p.set_option(3, 0)
+                    x0_, f0, c0, i0 = p.opt_gsl(x0, algorithm=alg, max_iterations=25)
+                    assert c1 == c0 and f1 == f0 and np.array_equal(x1, x0_), (method, M, N, "gsl", alg)
+                    assert i1["gradient_evaluations"] == i0["gradient_evaluations"]
+                    assert i1["f_only_evaluations"] == i0["f_only_evaluations"] and i0["gradient_half_only"] == 0
+                    continued[alg] += i1["gradient_half_only"]
                 p.set_option(3, 1)
-                x1, f1, c1, i1 = p.opt_gsl(x0, max_iterations=40)
-                p.set_option(3, 0)
-                x0_, f0, c0, i0 = p.opt_gsl(x0, max_iterations=40)
-                assert c1 == c0 and f1 == f0 and np.array_equal(x1, x0_), (method, M, N, "gsl")
-                assert i1["gradient_evaluations"] == i0["gradient_evaluations"] and i0["gradient_half_only"] == 0
-                continued += i1["gradient_half_only"]
-                p.set_option(3, 1)
-    assert skipped > 0 and continued > 0     # the short cuts were actually taken
+    # the short cuts were actually taken (steepest descent only when one of its steps was rejected)
+    assert skipped > 0 and all(c > 0 for c in continued[:4]), (skipped, continued)
