@@ -310,6 +310,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, pass_ms = float(t[0]), float(t[1])
+    # what a plain read-only stream over the same resident matrix reaches on this device (outside the timed region):
+    # the context for a roofline fraction above 1 against the read+write copy figure of MEASURED_PEAKS.json
+    read_gbs = ctypes.c_double(0.0)
+    _lib.check(_lib.load().bioen_b200_read_stream_peak(prob._h, 10, ctypes.byref(read_gbs)), "read_stream_peak")
     units = 1 if args.strong else world     # weak: every rank adds one N-block per evaluation
     value = units * args.steps / (ms * 1e-3)
 
@@ -392,6 +396,10 @@ def run_b200(args):
                      "kernel": ("stream_pass_kernel" if method == LOGW or args.unfused_forces else "fused_team_pass")
                                + " (one pass over yTilde)", "bytes_per_launch": alg_bytes,
                      "ms_per_launch": pass_ms,
+                     "read_only_stream": {"gbs": read_gbs.value, "frac_of_it": achieved / read_gbs.value
+                                          if read_gbs.value > 0 else None,
+                                          "what": "plain 16-byte-load read kernel over the same yTilde, mean of 10 "
+                                                  "launches, measured in this run; `peak` is a copy (read+write) figure"},
                      "step_frac": (2 * M * N * 8.0) / (ms / args.steps * 1e-3) / 1e9 / peak},
         "e2e": {"value": e2e_value, "unit": unit(args), "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,
                 "api": "bioen_b200_eval (C ABI, pinned host vectors; yTilde resident after one upload)"},

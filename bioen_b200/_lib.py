@@ -93,6 +93,7 @@ SIGNATURES = {
     "bioen_b200_time_scan_evals": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "bioen_b200_dmma_peak": (C.c_int, [C.c_int, _dp]),
+    "bioen_b200_read_stream_peak": (C.c_int, [_vp, C.c_int, _dp]),
     "bioen_b200_selftest_linesearch": (C.c_int, [lbfgs_config_params, C.c_double, C.c_double, C.c_double,
                                                  C.CFUNCTYPE(None, C.c_double, _dp, _dp), _dp, _dp, _ip]),
     "bioen_b200_selftest_interpolate": (C.c_double, [C.c_double] * 8 + [C.c_int]),

@@ -36,7 +36,10 @@ namespace bioen {
 constexpr int kBMaxK = 32;          // problems per batch (planes); padded to a multiple of 8
 constexpr int kGRows = 256;         // GEMM tile: rows per CTA
 constexpr int kGKdim = 16;          // GEMM tile: reduction extent per stage (16 doubles = one 128-byte swizzle row)
-constexpr int kGStages = 5;
+#ifndef BIOEN_GEMM_STAGES
+#define BIOEN_GEMM_STAGES 5
+#endif
+constexpr int kGStages = BIOEN_GEMM_STAGES;
 constexpr int kGWarps = 8;
 constexpr int kGThreads = (kGWarps + 1) * 32;
 constexpr int kGTileBytes = kGRows * kGKdim * 8;   // 32 KB

@@ -579,6 +579,54 @@ int bioen_b200_dmma_peak(int device, double* tflops) {
     });
 }
 
+int bioen_b200_read_stream_peak(bioen_b200_ctx* ctx, int reps, double* gbs) {
+    return guarded("bioen_b200_read_stream_peak", [&] {
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        if (!C.Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, C.device));
+        const size_t n2 = (size_t)C.M * C.ld / 2;
+        DevBuf<double> sink;
+        sink.alloc(1);
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        // default: 2 blocks of 1024 threads per SM, 8 loads in flight per thread (256 KB per SM).  The environment
+        // variable exists for the sensitivity study in DESIGN.md ("U,blocks-per-SM", U in {1,2,4,8})
+        int U = 8, bps = 2, order = -1;
+        if (const char* e = getenv("BIOEN_B200_READ_VARIANT")) sscanf(e, "%d,%d", &U, &bps);
+        if (const char* e = getenv("BIOEN_B200_READ_ORDER")) order = atoi(e);   // tile orders of k_read_tiles
+        const int blocks = prop.multiProcessorCount * (bps == 1 ? 1 : 2);
+        const double2* p = reinterpret_cast<const double2*>(C.Y);
+        auto launch = [&] {
+            if (order >= 0) {
+                k_read_tiles<<<blocks, 1024, 0, C.stream>>>(C.Y, C.ld, C.M, C.nRT, C.nCB, order, sink.p);
+                return;
+            }
+            if (U == 1) k_read_stream<1><<<blocks, 1024, 0, C.stream>>>(p, n2, sink.p);
+            else if (U == 2) k_read_stream<2><<<blocks, 1024, 0, C.stream>>>(p, n2, sink.p);
+            else if (U == 4) k_read_stream<4><<<blocks, 1024, 0, C.stream>>>(p, n2, sink.p);
+            else k_read_stream<8><<<blocks, 1024, 0, C.stream>>>(p, n2, sink.p);
+        };
+        launch();
+        double total = 0.0;
+        if (reps < 1) reps = 1;
+        for (int r = 0; r < reps; ++r) {
+            CUDA_CHECK(cudaEventRecord(e0, C.stream));
+            launch();
+            CUDA_CHECK(cudaEventRecord(e1, C.stream));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float t = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+            total += t;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *gbs = (double)n2 * 16.0 * reps / (total * 1e-3) / 1e9;   // mean over reps, like the pass timing
+    });
+}
+
 // host-only: the line-search state machine on a caller-supplied 1-D function (CPU tests of the host logic)
 int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, double dginit, double stp0,
                                    void (*phi)(double stp, double* f, double* dg), double* stp_out, double* f_out,

@@ -82,6 +82,10 @@ class Context {
     long long N_total;   // all columns over all ranks
     long long ld = 0;    // row stride of Y in doubles
     int Mpad, Npad, nRT, nCB;
+    bool interleave = false;
+    // `chunk` as the readers of the pass partials need it (pass_num_slots)
+    long long row_chunk() const { return interleave ? -(long long)grid : chunk; }
+    long long col_chunk() const { return interleave ? (long long)nRT : chunk; }
     int device, num_sms;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -134,14 +138,23 @@ class Context {
         Mpad = nRT * kTileR;
         Npad = nCB * kTileC;
         T = (long long)nRT * nCB;
-        const long long ncta = T < num_sms ? T : num_sms;
+        const long long want_cta = (long long)num_sms * kPassCtasPerSM;
+        const long long ncta = T < want_cta ? T : want_cta;
         chunk = (T + ncta - 1) / ncta;
         grid = (int)((T + chunk - 1) / chunk);
         auto slots = [&](long long L) {
             long long s = (L - 1) / chunk + 2;
             return (int)(s < grid ? s : grid);
         };
-        slotsA = slots(nCB);
+        // tile order of the matrix passes (stream_pass.cuh, TileWalk).  The interleaved order makes the whole chip
+        // read one compact window of the matrix; a TMA-free probe gains 2-3 % from it (scripts/read_order_probe.py),
+        // the TMA passes 0.6 % per pass and nothing per step (437.5 vs 438.5 evals/s), so it is opt-in:
+        // BIOEN_B200_PASS_ORDER=interleave (needs every CTA to get tiles of every row tile: nCB >= 4 * grid)
+        {
+            const char* e = getenv("BIOEN_B200_PASS_ORDER");
+            interleave = nCB >= 4LL * grid && e && e[0] == 'i';
+        }
+        slotsA = interleave ? grid : slots(nCB);
         slotsB = slots(nRT);
         int vb = 4;   // resident 256-thread blocks per SM for the O(N) kernels (measured: 2, 8, 16 are no faster)
         if (const char* e = getenv("BIOEN_B200_VEC_BLOCKS")) vb = std::max(1, atoi(e));
@@ -401,7 +414,16 @@ class Context {
             f_C = (int)std::max(1LL, std::min((long long)kFCMax, 8192LL / row_bytes));
             const long long stage_bytes = (((long long)f_C * row_bytes + 127) & ~127LL) + kTAuxBytes;
             const long long fixed = 2 * row_bytes + 2 * kTMaxRing * 8 + 2LL * kTWarps * 8 + 256;
-            const long long st = std::min((long long)kTMaxRing / teams, (smem_max - fixed) / (teams * stage_bytes));
+            long long st = std::min((long long)kTMaxRing / teams, (smem_max - fixed) / (teams * stage_bytes));
+            // ring depth: enough slabs in flight to cover the HBM latency, not more -- about 128 KB of ring per SM
+            // (measured at M = 1000: 2 stages per team = 130 KB ring 6.86 TB/s, 3 stages = 195 KB 6.56 TB/s; the
+            // tile kernels show the same optimum, see stream_pass.cuh)
+            {
+                const long long per_stage = teams * stage_bytes;
+                const long long want = std::max(2LL, (131072 + per_stage / 2) / per_stage);
+                st = std::min(st, want);
+            }
+            if (const char* e = getenv("BIOEN_B200_FUSED_STAGES")) st = std::min(st, (long long)std::max(2, atoi(e)));
             if (st >= 2) {
                 f_team = true;
                 f_stages = (int)st;
@@ -501,7 +523,7 @@ class Context {
         merge_fused_rows(false, 0);
         {
             ForcesGradArgs a{};
-            a.m = M; a.partial = nullptr; a.ld = Mpad; a.L = nCB; a.chunk = chunk; a.msum = msum.p;
+            a.m = M; a.partial = nullptr; a.ld = Mpad; a.L = nCB; a.chunk = row_chunk(); a.msum = msum.p;
             a.d = ddir; a.grad = grad; a.sc = sc.p;
             k_forces_grad<<<1, 1024, 0, stream>>>(a);
             ++kernels_launched;
@@ -510,7 +532,7 @@ class Context {
     // k_finalize_rows on an msum that is already slot-, CTA- and rank-reduced
     void finalize_rows_from_msum(bool is_forces, bool ab_with_avg) {
         FinalizeArgs a{};
-        a.m = M; a.partial = nullptr; a.ld = Mpad; a.L = nCB; a.chunk = chunk; a.msum = msum.p;
+        a.m = M; a.partial = nullptr; a.ld = Mpad; a.L = nCB; a.chunk = row_chunk(); a.msum = msum.p;
         a.Y = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.ab_with_avg = ab_with_avg ? 1 : 0;
         a.is_forces = is_forces ? 1 : 0; a.theta = theta;
         a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
@@ -527,7 +549,7 @@ class Context {
         LseArgs a{};
         a.n = N; a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev; a.w0 = w0;
         a.col_partial = from_col ? partialB.p : nullptr;
-        a.col_ld = Npad; a.col_L = nRT; a.col_chunk = chunk;
+        a.col_ld = Npad; a.col_L = nRT; a.col_chunk = col_chunk();
         a.write_xnorm = from_col ? 0 : 1;
         a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
         k_update_lse<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
@@ -539,7 +561,8 @@ class Context {
     template <int MODE, bool SUB>
     void launch_pass(const double* vN, const double* vMb) {
         PassArgs a{};
-        a.nRT = nRT; a.nCB = nCB; a.T = T; a.chunk = chunk; a.evict_first = evict_first;
+        a.nRT = nRT; a.nCB = nCB; a.T = T; a.chunk = chunk; a.interleave = interleave ? 1 : 0;
+        a.evict_first = evict_first;
         a.vN = vN; a.vMb = vMb; a.ab = ab.p;
         a.partial = (MODE == kRowPass) ? partialA.p : partialB.p;
         a.ld = (MODE == kRowPass) ? Mpad : Npad;
@@ -582,13 +605,13 @@ class Context {
     // finish a row pass that produced avg (logw: tail = 3 weighted sums, forces: tail = KL)
     void finalize_rows(bool is_forces, int ntail, bool ab_with_avg) {
         FinalizeArgs a{};
-        a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = chunk;
+        a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = row_chunk();
         a.Y = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.ab_with_avg = ab_with_avg ? 1 : 0;
         a.is_forces = is_forces ? 1 : 0; a.theta = theta;
         a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
         a.tail = msum.p + M;
         if (nranks > 1) {
-            k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+            k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, row_chunk(), msum.p);
             ++kernels_launched;
             comm->allreduce_sum(msum.p, M + ntail, stream);
             a.msum = msum.p;
@@ -630,7 +653,7 @@ class Context {
         launch_pass<kColPass, true>(nullptr, nullptr);
         {
             LogwGradArgs a{};
-            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = chunk;
+            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = col_chunk();
             a.g = x; a.G = Gv.p; a.w = w.p; a.d = ddir; a.grad = grad; a.theta = theta;
             a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
             k_logw_grad<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
@@ -694,7 +717,7 @@ class Context {
         launch_pass<kColPass, false>(nullptr, nullptr);                 // t_j = sum_i y_ij r_i
         {
             ForcesEArgs a{};
-            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = chunk;
+            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = col_chunk();
             a.w = w.p; a.lr = aux_n2.p; a.E = aux_n.p; a.theta = theta;   // E overwrites x_j (no longer needed)
             k_forces_E<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
             ++kernels_launched;
@@ -702,10 +725,10 @@ class Context {
         launch_pass<kRowPass, true>(aux_n.p, avg.p);                    // grad_i = sum_j (y_ij - avg_i) E_j
         {
             ForcesGradArgs a{};
-            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = chunk;
+            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = row_chunk();
             a.d = ddir; a.grad = grad; a.sc = sc.p;
             if (nranks > 1) {
-                k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+                k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, row_chunk(), msum.p);
                 ++kernels_launched;
                 comm->allreduce_sum(msum.p, M, stream);
                 a.msum = msum.p;
@@ -746,7 +769,7 @@ class Context {
         launch_pass<kColPass, false>(nullptr, nullptr);
         {
             ForcesEArgs a{};
-            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = chunk;
+            a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = col_chunk();
             a.w = w.p; a.lr = aux_n2.p; a.E = aux_n.p; a.theta = theta;
             k_forces_E<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
             ++kernels_launched;
@@ -754,10 +777,10 @@ class Context {
         launch_pass<kRowPass, true>(aux_n.p, avg.p);
         {
             ForcesGradArgs a{};
-            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = chunk;
+            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = row_chunk();
             a.d = nullptr; a.grad = grad; a.sc = sc.p;
             if (nranks > 1) {
-                k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+                k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, row_chunk(), msum.p);
                 ++kernels_launched;
                 comm->allreduce_sum(msum.p, M, stream);
                 a.msum = msum.p;
@@ -770,7 +793,7 @@ class Context {
     void average_of_w(double* avg_out_dev) {
         ++eval_gen;
         launch_pass<kRowPass, false>(w.p, nullptr);
-        k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, chunk, msum.p);
+        k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, row_chunk(), msum.p);
         ++kernels_launched;
         if (nranks > 1) comm->allreduce_sum(msum.p, M, stream);
         d2d(avg_out_dev, msum.p, M);

@@ -36,7 +36,18 @@ enum PassMode { kRowPass = 0, kColPass = 1 };
 
 constexpr int kTileR = 32;    // rows per tile
 constexpr int kTileC = 128;   // columns per tile  (128 doubles = 1 KB per tile row)
-constexpr int kStages = 6;    // ring depth
+// Ring depth.  MORE is not better: measured at N = 1e6 x M = 1e3 (read-only LDG stream on the same box: 7.25 TB/s)
+//   2 stages 6.52, 3: 7.13, 4: 7.24, 5: 7.13, 6: 7.06 TB/s.  ~100 KB in flight per SM saturate the HBM; deeper
+// queues only add contention in the memory system (the plain LDG stream shows the same: 64 KB/SM in flight 7.3 TB/s,
+// 256 KB/SM 7.18 TB/s).
+#ifndef BIOEN_PASS_STAGES
+#define BIOEN_PASS_STAGES 4
+#endif
+#ifndef BIOEN_PASS_CTAS_PER_SM
+#define BIOEN_PASS_CTAS_PER_SM 1
+#endif
+constexpr int kStages = BIOEN_PASS_STAGES;    // ring depth
+constexpr int kPassCtasPerSM = BIOEN_PASS_CTAS_PER_SM;
 constexpr int kConsumerWarps = 8;
 constexpr int kAuxBytes = 2048;                                   // vector slices travelling with a tile
 constexpr int kTileBytes = kTileR * kTileC * (int)sizeof(double);  // 32 KB
@@ -48,7 +59,8 @@ struct PassArgs {
     int nRT;            // number of row tiles     ceil(M / kTileR)
     int nCB;            // number of column blocks ceil(N / kTileC)
     long long T;        // nRT * nCB
-    long long chunk;    // tiles per CTA
+    long long chunk;    // tiles per CTA (contiguous order)
+    int interleave;     // 1: tiles (row pass) / whole runs (column pass) are dealt round-robin to the CTAs
     int evict_first;    // 1: stream yTilde through L2 with evict_first (matrix >> L2)
     const double* vN;   // ROW: v_j, length >= nCB*kTileC, zero padded
     const double* vMb;  // ROW with SUB: b_i, length >= nRT*kTileR, zero padded
@@ -57,16 +69,71 @@ struct PassArgs {
     long long ld;       // leading dimension of `partial`
 };
 
-// slots a run of length L starting at tile run*L occupies: first CTA and count
+// slots a run of length L starting at tile run*L occupies: first CTA and count.  chunk < 0 is how the readers of
+// an interleaved row pass are told that every one of the -chunk CTAs holds a slot of every run.
 __host__ __device__ inline long long pass_first_cta(long long run, long long L, long long chunk) {
-    return (run * L) / chunk;
+    return chunk < 0 ? 0 : (run * L) / chunk;
 }
 __host__ __device__ inline int pass_num_slots(long long run, long long L, long long chunk) {
+    if (chunk < 0) return (int)(-chunk);
     return (int)(((run + 1) * L - 1) / chunk - (run * L) / chunk) + 1;
 }
 
+// The order in which one CTA visits its tiles.  A run is the set of tiles that accumulate into the same outputs
+// (row pass: the nCB tiles of a row tile; column pass: the nRT tiles of a column block).
+//   contiguous  CTA b owns tiles [b*chunk, (b+1)*chunk) of the run-major order: far-apart regions of the matrix
+//               are streamed at the same time.
+//   interleaved row pass: tile t goes to CTA t mod G; column pass: run r goes to CTA r mod G.  At any moment the
+//               whole chip reads one compact window of the matrix (every row a contiguous stretch of ~G KB), which
+//               the DRAM serves ~2-3 % faster (measured with a TMA-free probe, scripts/read_order_probe.py).
+struct TileWalk {
+    long long run, left, L;
+    int k, G, mode;   // mode 0 contiguous, 1 row-interleaved, 2 column-run-interleaved
+    __device__ __forceinline__ void init(int pass_mode, const PassArgs& a, int b, int grid) {
+        L = (pass_mode == kRowPass) ? a.nCB : a.nRT;
+        G = grid;
+        if (!a.interleave) {
+            mode = 0;
+            const long long t0 = (long long)b * a.chunk;
+            const long long t1 = (t0 + a.chunk < a.T) ? t0 + a.chunk : a.T;
+            left = t1 > t0 ? t1 - t0 : 0;
+            run = t0 / L;
+            k = (int)(t0 - run * L);
+        } else if (pass_mode == kRowPass) {
+            mode = 1;
+            left = b < a.T ? (a.T - b + G - 1) / G : 0;
+            run = b / L;
+            k = (int)(b - run * L);
+        } else {
+            mode = 2;
+            const long long nruns = a.nCB;
+            left = b < nruns ? ((nruns - b + G - 1) / G) * L : 0;
+            run = b;
+            k = 0;
+        }
+    }
+    // does the current tile close the CTA's part of its run?
+    __device__ __forceinline__ bool closes_run() const {
+        return left == 1 || (mode == 1 ? (long long)k + G >= L : k + 1 == (int)L);
+    }
+    __device__ __forceinline__ void advance() {
+        --left;
+        if (mode == 1) {
+            long long kk = (long long)k + G;
+            while (kk >= L) { kk -= L; ++run; }
+            k = (int)kk;
+        } else if (++k == (int)L) {
+            k = 0;
+            run += (mode == 2) ? G : 1;
+        }
+    }
+    __device__ __forceinline__ long long slot(int b, long long chunk) const {
+        return mode == 0 ? (long long)b - pass_first_cta(run, L, chunk) : (mode == 1 ? b : 0);
+    }
+};
+
 template <int MODE, bool SUB>
-__global__ void __launch_bounds__(kPassThreads, 1)
+__global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
     stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 128-byte align the ring by hand (dynamic smem base is only guaranteed 16-byte aligned)
@@ -77,9 +144,8 @@ __global__ void __launch_bounds__(kPassThreads, 1)
     uint64_t* empty = full + kStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long t0 = (long long)blockIdx.x * a.chunk;
-    const long long t1 = (t0 + a.chunk < a.T) ? t0 + a.chunk : a.T;
-    const long long L = (MODE == kRowPass) ? a.nCB : a.nRT;  // run length in tiles
+    TileWalk tw;   // producer and consumers walk the same tile sequence
+    tw.init(MODE, a, (int)blockIdx.x, (int)gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -92,16 +158,14 @@ __global__ void __launch_bounds__(kPassThreads, 1)
 
     if (warp == kConsumerWarps) {
         // ------------------------------------------------------------------ producer
-        if (lane == 0 && t0 < t1) {
+        if (lane == 0 && tw.left > 0) {
             prefetch_tensormap(&tmap);
             const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
-            long long run = t0 / L;
-            int k = (int)(t0 - run * L);
             int stage = 0;
             uint32_t phase = 1;  // a fresh barrier passes a wait on parity 1
-            for (long long t = t0; t < t1; ++t) {
-                const int rt = (MODE == kRowPass) ? (int)run : k;
-                const int cb = (MODE == kRowPass) ? k : (int)run;
+            for (; tw.left > 0; tw.advance()) {
+                const int rt = (MODE == kRowPass) ? (int)tw.run : tw.k;
+                const int cb = (MODE == kRowPass) ? tw.k : (int)tw.run;
                 unsigned char* st = smem + (size_t)stage * kStageBytes;
                 mbar_wait(&empty[stage], phase);
                 uint32_t bytes = kTileBytes;
@@ -117,7 +181,6 @@ __global__ void __launch_bounds__(kPassThreads, 1)
                 } else {
                     bulk_load_1d(st + kTileBytes, a.ab + (size_t)rt * kTileR * 2, kTileR * 16, &full[stage]);
                 }
-                if (++k == (int)L) { k = 0; ++run; }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -125,9 +188,7 @@ __global__ void __launch_bounds__(kPassThreads, 1)
     }
 
     // ---------------------------------------------------------------------- consumers
-    if (t0 >= t1) return;
-    long long run = t0 / L;
-    int k = (int)(t0 - run * L);
+    if (tw.left == 0) return;
     int stage = 0;
     uint32_t phase = 0;
 
@@ -136,7 +197,7 @@ __global__ void __launch_bounds__(kPassThreads, 1)
         double acc[RPW];
 #pragma unroll
         for (int r = 0; r < RPW; ++r) acc[r] = 0.0;
-        for (long long t = t0; t < t1; ++t) {
+        for (; tw.left > 0; tw.advance()) {
             const unsigned char* st = smem + (size_t)stage * kStageBytes;
             mbar_wait(&full[stage], phase);
             const double2* vv = reinterpret_cast<const double2*>(st + kTileBytes);
@@ -161,10 +222,8 @@ __global__ void __launch_bounds__(kPassThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
-            const bool run_ends = (k + 1 == (int)L);
-            if (run_ends || t + 1 == t1) {
-                const long long slot = (long long)blockIdx.x - pass_first_cta(run, L, a.chunk);
-                double* out = a.partial + slot * a.ld + run * kTileR + warp * RPW;
+            if (tw.closes_run()) {
+                double* out = a.partial + tw.slot((int)blockIdx.x, a.chunk) * a.ld + tw.run * kTileR + warp * RPW;
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const double s = warp_sum(acc[r]);
@@ -172,7 +231,6 @@ __global__ void __launch_bounds__(kPassThreads, 1)
                     acc[r] = 0.0;
                 }
             }
-            if (run_ends) { k = 0; ++run; } else { ++k; }
         }
     } else {
         // warp -> 16 columns; lane -> (row group of 8 rows, column pair)
@@ -180,7 +238,7 @@ __global__ void __launch_bounds__(kPassThreads, 1)
         static_assert(CPW == 16 && kTileR == 32, "column-pass lane mapping assumes a 32 x 128 tile");
         const int cp = lane & 7, rg = lane >> 3;
         double acc0 = 0.0, acc1 = 0.0;
-        for (long long t = t0; t < t1; ++t) {
+        for (; tw.left > 0; tw.advance()) {
             const unsigned char* st = smem + (size_t)stage * kStageBytes;
             mbar_wait(&full[stage], phase);
             const double2* abv = reinterpret_cast<const double2*>(st + kTileBytes);
@@ -201,21 +259,19 @@ __global__ void __launch_bounds__(kPassThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
-            const bool run_ends = (k + 1 == (int)L);
-            if (run_ends || t + 1 == t1) {
+            if (tw.closes_run()) {
                 // add the four row groups in a fixed order
                 acc0 += __shfl_xor_sync(0xffffffffu, acc0, 8);
                 acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
                 acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16);
                 acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
                 if (rg == 0) {
-                    const long long slot = (long long)blockIdx.x - pass_first_cta(run, L, a.chunk);
-                    double2* out = reinterpret_cast<double2*>(a.partial + slot * a.ld + run * kTileC + warp * CPW);
+                    double2* out = reinterpret_cast<double2*>(a.partial + tw.slot((int)blockIdx.x, a.chunk) * a.ld +
+                                                              tw.run * kTileC + warp * CPW);
                     out[cp] = make_double2(acc0, acc1);
                 }
                 acc0 = acc1 = 0.0;
             }
-            if (run_ends) { k = 0; ++run; } else { ++k; }
         }
     }
 }

@@ -596,4 +596,64 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plain read-only stream over the resident matrix: every thread sums 16-byte loads, nothing is written.  An upper
+// reference for what a read-only pass over yTilde can reach on this device (the copy figure in
+// MEASURED_PEAKS.json mixes reads and writes and is lower).
+template <int U>
+__global__ void __launch_bounds__(1024, 2) k_read_stream(const double2* __restrict__ p, size_t n2, double* sink) {
+    double s0 = 0.0, s1 = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < n2; i += U * stride) {
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldcs(p + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { s0 += v[u].x; s1 += v[u].y; }
+    }
+    for (; i < n2; i += stride) {
+        const double2 v = __ldcs(p + i);
+        s0 += v.x;
+        s1 += v.y;
+    }
+    if (s0 + s1 == 1.2345e-300) *sink = s0;   // keeps the loads alive, never true in practice
+}
+
+// The same read-only measurement with the ACCESS ORDER of the matrix passes: a block reads 32-row x 128-column
+// tiles (32 segments of 1 KB, one row pitch apart) in one of four orders.  Separates "what the tile order costs at
+// the DRAM" from "what the TMA pipeline costs".  order 0: row pass, contiguous chunk of tiles per block (tiles of a
+// row tile are adjacent column blocks); 1: row pass, tiles dealt round-robin to the blocks; 2: column pass,
+// contiguous chunk (a run walks down the rows of one column block); 3: column pass, runs dealt round-robin.
+__global__ void __launch_bounds__(1024, 2)
+    k_read_tiles(const double* __restrict__ Y, long long ld, int M, int nRT, int nCB, int order, double* sink) {
+    const long long T = (long long)nRT * nCB, G = gridDim.x, b = blockIdx.x;
+    const long long chunk = (T + G - 1) / G;
+    const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+    double s0 = 0.0, s1 = 0.0;
+    auto tile = [&](long long rt, long long cb) {
+        const long long row = rt * 32 + r;
+        if (row < M) {
+            const double2* p = reinterpret_cast<const double2*>(Y + row * ld + cb * 128);
+            const double2 u = __ldcs(p + c), v = __ldcs(p + 32 + c);
+            s0 += u.x + v.x;
+            s1 += u.y + v.y;
+        }
+    };
+    if (order == 0 || order == 2) {
+        const long long t0 = b * chunk, t1 = (t0 + chunk < T) ? t0 + chunk : T;
+        const long long L = (order == 0) ? nCB : nRT;
+        for (long long t = t0; t < t1; ++t) {
+            const long long run = t / L, k = t - run * L;
+            if (order == 0) tile(run, k); else tile(k, run);
+        }
+    } else if (order == 1) {
+        for (long long t = b; t < T; t += G) tile(t / nCB, t % nCB);
+    } else {
+        for (long long cb = b; cb < nCB; cb += G)
+            for (long long rt = 0; rt < nRT; ++rt) tile(rt, cb);
+    }
+    if (s0 + s1 == 1.2345e-300) *sink = s0;
+}
+
 }  // namespace bioen

@@ -221,6 +221,9 @@ int bioen_b200_theta_scan(bioen_b200_ctx *ctx, int method, int K, const double *
 int bioen_b200_time_scan_evals(bioen_b200_ctx *ctx, int method, int K, const double *thetas, const double *x0_host,
                                int warmup, int steps, float *ms, float *gemm_ms, long long *launches);
 int bioen_b200_dmma_peak(int device, double *tflops);
+/* mean GB/s of `reps` launches of a plain read-only stream (16-byte loads, nothing written) over the resident
+ * yTilde: what a read-only pass can reach on this device, next to the copy figure of MEASURED_PEAKS.json */
+int bioen_b200_read_stream_peak(bioen_b200_ctx *ctx, int reps, double *gbs);
 
 /* host-only test hook (no GPU needed): runs the liblbfgs line search selected by config (More-Thuente or one of
  * the three backtracking variants, lbfgs.c:645-1001) on the 1-D function phi(stp) -> (f, df/dstp).  Returns the
