@@ -97,6 +97,9 @@ SIGNATURES = {
     "bioen_b200_selftest_linesearch": (C.c_int, [lbfgs_config_params, C.c_double, C.c_double, C.c_double,
                                                  C.CFUNCTYPE(None, C.c_double, _dp, _dp), _dp, _dp, _ip]),
     "bioen_b200_selftest_interpolate": (C.c_double, [C.c_double] * 8 + [C.c_int]),
+    "bioen_b200_selftest_tilewalk": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int,
+                                                   C.c_longlong, _ip, _ip, C.POINTER(C.c_longlong), _ip]),
+    "bioen_b200_selftest_num_slots": (C.c_int, [C.c_longlong, C.c_longlong, C.c_longlong]),
     "bioen_b200_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "bioen_b200_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_longlong]),
     "bioen_b200_comm_mode": (C.c_int, [_vp]),

@@ -658,6 +658,26 @@ double bioen_b200_selftest_interpolate(double a, double fa, double fpa, double b
     return fletcher::interpolate(a, fa, fpa, b, fb, fpb, xmin, xmax, order);
 }
 
+// host-only: the tile sequence one CTA of a matrix pass walks (stream_pass.cuh, TileWalk) and the slot it writes its
+// partial sums to -- the same code the kernel runs, for CPU tests of coverage and of the slot bookkeeping
+long long bioen_b200_selftest_tilewalk(int pass_mode, int nRT, int nCB, int grid, long long chunk, int interleave,
+                                       int cta, long long max_tiles, int* rt, int* cb, long long* slot, int* closes) {
+    PassArgs a{};
+    a.nRT = nRT; a.nCB = nCB; a.T = (long long)nRT * nCB; a.chunk = chunk; a.interleave = interleave;
+    TileWalk tw;
+    tw.init(pass_mode, a, cta, grid);
+    long long n = 0;
+    for (; tw.left > 0; tw.advance(), ++n) {
+        if (n >= max_tiles) continue;
+        rt[n] = (pass_mode == kRowPass) ? (int)tw.run : tw.k;
+        cb[n] = (pass_mode == kRowPass) ? tw.k : (int)tw.run;
+        slot[n] = tw.slot(cta, chunk);
+        closes[n] = tw.closes_run() ? 1 : 0;
+    }
+    return n;
+}
+int bioen_b200_selftest_num_slots(long long run, long long L, long long chunk) { return pass_num_slots(run, L, chunk); }
+
 int bioen_b200_nccl_unique_id(char id[128]) {
     return guarded("bioen_b200_nccl_unique_id", [&] { Comm::unique_id(id); });
 }

@@ -89,7 +89,7 @@ __host__ __device__ inline int pass_num_slots(long long run, long long L, long l
 struct TileWalk {
     long long run, left, L;
     int k, G, mode;   // mode 0 contiguous, 1 row-interleaved, 2 column-run-interleaved
-    __device__ __forceinline__ void init(int pass_mode, const PassArgs& a, int b, int grid) {
+    __host__ __device__ __forceinline__ void init(int pass_mode, const PassArgs& a, int b, int grid) {
         L = (pass_mode == kRowPass) ? a.nCB : a.nRT;
         G = grid;
         if (!a.interleave) {
@@ -113,10 +113,10 @@ struct TileWalk {
         }
     }
     // does the current tile close the CTA's part of its run?
-    __device__ __forceinline__ bool closes_run() const {
+    __host__ __device__ __forceinline__ bool closes_run() const {
         return left == 1 || (mode == 1 ? (long long)k + G >= L : k + 1 == (int)L);
     }
-    __device__ __forceinline__ void advance() {
+    __host__ __device__ __forceinline__ void advance() {
         --left;
         if (mode == 1) {
             long long kk = (long long)k + G;
@@ -127,7 +127,7 @@ struct TileWalk {
             run += (mode == 2) ? G : 1;
         }
     }
-    __device__ __forceinline__ long long slot(int b, long long chunk) const {
+    __host__ __device__ __forceinline__ long long slot(int b, long long chunk) const {
         return mode == 0 ? (long long)b - pass_first_cta(run, L, chunk) : (mode == 1 ? b : 0);
     }
 };

@@ -236,6 +236,13 @@ int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, dou
 double bioen_b200_selftest_interpolate(double a, double fa, double fpa, double b, double fb, double fpb, double xmin,
                                        double xmax, int order);
 
+/* host-only test hooks: the tile sequence CTA `cta` of a matrix pass walks (pass_mode 0 row pass, 1 column pass;
+ * arrays of max_tiles entries: tile coordinates, partial-sum slot, 1 where the CTA's part of a run ends; returns the
+ * number of tiles), and the number of slots the readers of the partial sums expect for a run */
+long long bioen_b200_selftest_tilewalk(int pass_mode, int nRT, int nCB, int grid, long long chunk, int interleave,
+                                       int cta, long long max_tiles, int *rt, int *cb, long long *slot, int *closes);
+int bioen_b200_selftest_num_slots(long long run, long long L, long long chunk);
+
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);
