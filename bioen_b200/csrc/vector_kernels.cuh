@@ -624,7 +624,8 @@ __global__ void __launch_bounds__(1024, 2) k_read_stream(const double2* __restri
 // tiles (32 segments of 1 KB, one row pitch apart) in one of four orders.  Separates "what the tile order costs at
 // the DRAM" from "what the TMA pipeline costs".  order 0: row pass, contiguous chunk of tiles per block (tiles of a
 // row tile are adjacent column blocks); 1: row pass, tiles dealt round-robin to the blocks; 2: column pass,
-// contiguous chunk (a run walks down the rows of one column block); 3: column pass, runs dealt round-robin.
+// contiguous chunk (a run walks down the rows of one column block); 3: column pass, runs dealt round-robin;
+// 4: column pass, contiguous chunk, a run covers two adjacent column blocks.
 __global__ void __launch_bounds__(1024, 2)
     k_read_tiles(const double* __restrict__ Y, long long ld, int M, int nRT, int nCB, int order, double* sink) {
     const long long T = (long long)nRT * nCB, G = gridDim.x, b = blockIdx.x;
@@ -649,6 +650,15 @@ __global__ void __launch_bounds__(1024, 2)
         }
     } else if (order == 1) {
         for (long long t = b; t < T; t += G) tile(t / nCB, t % nCB);
+    } else if (order == 4) {
+        // column pass whose runs cover TWO adjacent column blocks: 2 KB contiguous per row, contiguous chunks
+        const long long npair = (nCB + 1) / 2, Tp = npair * nRT, chunkp = (Tp + G - 1) / G;
+        const long long t0 = b * chunkp, t1 = (t0 + chunkp < Tp) ? t0 + chunkp : Tp;
+        for (long long t = t0; t < t1; ++t) {
+            const long long p = t / nRT, rt = t - p * nRT;
+            tile(rt, 2 * p);
+            if (2 * p + 1 < nCB) tile(rt, 2 * p + 1);
+        }
     } else {
         for (long long cb = b; cb < nCB; cb += G)
             for (long long rt = 0; rt < nRT; ++rt) tile(rt, cb);
