@@ -98,30 +98,72 @@ class ShardedProblem:
     def set_forces(self, w0, YTilde, theta):
         self.p.set_forces(self._slice(w0), YTilde, theta)
 
-    def objective_and_gradient(self, x):
-        if self.p.method == LOGW:
+    # The methods below take the same arguments as bioen_b200.Problem's (the optional `method` must be the one
+    # that was set), so that optimize.{log_weights,forces}.find_optimum(..., problem=ShardedProblem(...)) runs the
+    # reference API on all GPUs of the job.
+    @property
+    def method(self):
+        return self.p.method
+
+    @property
+    def n(self):
+        return self.n_total
+
+    @property
+    def device(self):
+        return self.p.device
+
+    def _check(self, method):
+        if method is not None and method != self.p.method:
+            raise ValueError("ShardedProblem: call set_logw / set_forces for this method first")
+        return self.p.method == LOGW
+
+    def set_theta(self, theta):
+        self.p.set_theta(theta)
+
+    def objective_and_gradient(self, x, method=None):
+        if self._check(method):
             f, g = self.p.objective_and_gradient(self._slice(x))
             return f, self._gather(g)
         return self.p.objective_and_gradient(x)
 
-    def objective(self, x):
-        return self.p.objective(self._slice(x) if self.p.method == LOGW else x)
+    def objective(self, x, method=None):
+        return self.p.objective(self._slice(x) if self._check(method) else x)
 
-    def weights(self, x):
-        w, s = self.p.weights(self._slice(x) if self.p.method == LOGW else x)
+    def gradient(self, x, method=None):
+        return self.objective_and_gradient(x, method)[1]
+
+    def weights(self, x, method=None):
+        w, s = self.p.weights(self._slice(x) if self._check(method) else x)
         return self._gather(w), s
 
-    def opt_lbfgs(self, x0, **cfg):
-        if self.p.method == LOGW:
+    def average(self, w):
+        """y.w over all ranks for full-length (or rank-local) weights; the partial sums are combined inside the
+        library, every rank gets the same M-vector."""
+        return self.p.average(self._slice(w))
+
+    def opt_lbfgs(self, x0, method=None, **cfg):
+        if self._check(method):
             x, fmin, code, info = self.p.opt_lbfgs(self._slice(x0), **cfg)
             return self._gather(x), fmin, code, info
         return self.p.opt_lbfgs(x0, **cfg)
 
-    def opt_gsl(self, x0, **cfg):
-        if self.p.method == LOGW:
+    def opt_gsl(self, x0, method=None, **cfg):
+        if self._check(method):
             x, fmin, code, info = self.p.opt_gsl(self._slice(x0), **cfg)
             return self._gather(x), fmin, code, info
         return self.p.opt_gsl(x0, **cfg)
+
+    def like(self, y):
+        """A problem of the same kind (same devices, same sharding) holding another m' x N matrix, e.g. the
+        un-normalised observables y for the post-processing y.wopt."""
+        return ShardedProblem(y, self.p.device, group=self.group)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def theta_scan(self, thetas, x0=None, **cfg):
         """Batched theta scan on the sharded problem; X planes are gathered to full length for log-weights."""

@@ -28,6 +28,12 @@ def device_average(w, y, problem=None):
         return p.average(w)
 
 
+def average_like(problem, w, y):
+    """y.w on the device(s) `problem` lives on (a Problem, or a dist.ShardedProblem over all GPUs of the job)."""
+    with problem.like(y) as q:
+        return q.average(w)
+
+
 def print_highlighted(text, verbose=True):
     """bioen/optimize/common.py:63-80"""
     if verbose:

@@ -108,6 +108,10 @@ class Problem:
     def __exit__(self, *exc):
         self.close()
 
+    def like(self, y):
+        """A problem on the same device holding another matrix (e.g. y for the post-processing y.wopt)."""
+        return Problem(y, device=self.device)
+
     # ---- data ---------------------------------------------------------------------------------------
     def adopt(self, dev_ptr, ld):
         """Use a matrix already on the device (e.g. a torch tensor's data_ptr()); caller keeps ownership."""

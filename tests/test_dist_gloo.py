@@ -88,3 +88,129 @@ def test_sharded_schedule_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: (0, 501), 1: (501, 1001)}
+
+
+class _StandIn:
+    """CPU stand-in with bioen_b200.Problem's interface: this rank's columns, oracle arithmetic on the gathered
+    problem.  It lets the world-size-2 test below drive dist.ShardedProblem and optimize.*.find_optimum -- the
+    slicing, gathering and call signatures -- without a GPU.  (The GPU library under ShardedProblem is covered by
+    tests/mgpu_check.py.)"""
+
+    def __init__(self, local, device=0):
+        from bioen_b200 import dist as D
+        self.local = np.asarray(local, dtype=np.float64)
+        self.m, self.n = self.local.shape
+        self.device, self.method = device, None
+        world = dist.get_world_size()
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([self.n]))
+        self.sizes = [int(s) for s in sizes]
+        self.n_total = sum(self.sizes)
+        self.lo = sum(self.sizes[:dist.get_rank()])
+        self.full = np.stack([D.allgather_vector(self.local[i], self.n_total) for i in range(self.m)])
+
+    def comm_init(self, *a):
+        pass
+
+    def _full(self, v):
+        from bioen_b200 import dist as D
+        return D.allgather_vector(np.asarray(v, dtype=np.float64).ravel(), self.n_total)
+
+    def _mine(self, v):
+        return np.ascontiguousarray(v[self.lo:self.lo + self.n])
+
+    def set_logw(self, G, Y, theta):
+        self.G, self.Y, self.theta, self.method = self._full(G), np.asarray(Y, dtype=np.float64).ravel(), theta, 0
+
+    def set_forces(self, w0, Y, theta):
+        self.w0, self.Y, self.theta, self.method = self._full(w0), np.asarray(Y, dtype=np.float64).ravel(), theta, 1
+
+    def _fg(self, x):
+        from oracle import oracle as O
+        if self.method == 0:
+            return O.logw_fg_np(x, self.G, self.full, self.Y, self.theta)
+        return O.forces_fg_np(x, self.w0, self.full, self.Y, self.theta)
+
+    def objective(self, x, method=None):
+        return self._fg(self._full(x) if self.method == 0 else np.asarray(x, dtype=np.float64).ravel())[0]
+
+    def objective_and_gradient(self, x, method=None):
+        if self.method == 0:
+            f, g = self._fg(self._full(x))
+            return f, self._mine(g)
+        return self._fg(np.asarray(x, dtype=np.float64).ravel())
+
+    def weights(self, x, method=None):
+        from oracle import oracle as O
+        if self.method == 0:
+            w, s = O.logw_weights_np(self._full(x))
+            return self._mine(w), s
+        return self._mine(O.forces_weights_np(np.asarray(x, dtype=np.float64).ravel(), self.w0, self.full)), None
+
+    def average(self, w):
+        part = torch.from_numpy(self.local @ np.asarray(w, dtype=np.float64).ravel())
+        dist.all_reduce(part)
+        return part.numpy()
+
+    def opt_lbfgs(self, x0, method=None, verbose=0, **cfg):
+        from oracle import oracle as O
+        start = self._full(x0) if self.method == 0 else np.asarray(x0, dtype=np.float64).ravel()
+        r = O.lbfgs(self._fg, start, **cfg)
+        x = self._mine(r["x"]) if self.method == 0 else r["x"]
+        return x, r["fx"], r["code"], dict(iterations=r["iterations"], evaluations=r["evaluations"])
+
+    def close(self):
+        pass
+
+
+def _worker_find_optimum(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bioen_b200 import dist as D
+        from bioen_b200 import optimize
+        from oracle import oracle as O
+        D.Problem = _StandIn                       # the GPU library is not available here
+        D.connect = lambda p, n_total, group=None, device=None: p
+        M, N, theta = 9, 203, 2.0
+        P = O.synthetic_problem(M, N, seed=3)
+        y = 0.5 * P["yTilde"] + 0.25               # "un-normalised observables": a different M x N matrix
+        cfg = optimize.minimize.Parameters("lbfgs")
+        cfg["verbose"] = False
+        # log-weights through the reference API, N split over the two ranks
+        sp = D.ShardedProblem(P["yTilde"], device=0)
+        assert (sp.lo, sp.hi) == D.shard_bounds(N, rank, world) and sp.n == N
+        wopt, yopt, gopt, f0, f1 = optimize.log_weights.find_optimum(P["GInit"], P["G"], y, P["yTilde"], P["YTilde"],
+                                                                     theta, cfg, problem=sp)
+        r = O.lbfgs(lambda v: O.logw_fg_np(v, P["G"].ravel(), P["yTilde"], P["YTilde"].ravel(), theta),
+                    P["GInit"].ravel(), **optimize.log_weights._lbfgs_kwargs(cfg))
+        assert wopt.shape == (N, 1) and gopt.shape == (N,) and yopt.shape == (M,)
+        assert np.array_equal(gopt, r["x"]) and f1 == r["fx"] and f1 < f0
+        w = np.exp(r["x"] - r["x"].max())
+        w /= w.sum()
+        assert np.allclose(wopt.ravel(), w, rtol=1e-13, atol=0) and np.allclose(yopt, y @ w, rtol=1e-12)
+        # forces: replicated M-vector, weights gathered
+        res = optimize.forces.find_optimum(P["forces_init"], P["w0"], y, P["yTilde"], P["YTilde"], theta, cfg,
+                                           problem=sp)
+        wopt, yopt, fopt, f0, f1, chi2, S = res
+        r = O.lbfgs(lambda v: O.forces_fg_np(v, P["w0"].ravel(), P["yTilde"], P["YTilde"].ravel(), theta),
+                    P["forces_init"].ravel(), **optimize.log_weights._lbfgs_kwargs(cfg))
+        assert np.array_equal(fopt, r["x"]) and f1 == r["fx"]
+        assert wopt.shape == (N, 1) and abs(wopt.sum() - 1.0) < 1e-12 and np.allclose(yopt, y @ wopt.ravel(), rtol=1e-12)
+        assert abs(theta * S + chi2 - f1) < 1e-10 * abs(f1)
+        # signature checks of the wrapper itself
+        with pytest.raises(ValueError):
+            sp.objective(P["GInit"], D.LOGW)       # forces is the method that is set
+        sp.close()
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_find_optimum_on_sharded_problem_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_find_optimum, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
