@@ -642,6 +642,9 @@ int bioen_b200_selftest_linesearch(lbfgs_config_params config, double finit, dou
         double f = 0.0, dg = 0.0;
         phi(stp, &f, &dg);
         ++n;
+        // as the device driver does: where the search will not read the slope, the gradient half of the evaluation
+        // is never run -- poison dg so that the CPU tests would notice if update() looked at it after all
+        if (!ls.needs_slope(f)) dg = kNaN;
         const int verdict = ls.update(f, dg);
         if (verdict != 0) {
             if (stp_out) *stp_out = stp;

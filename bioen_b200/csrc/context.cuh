@@ -199,6 +199,7 @@ class Context {
         fused_ready = false;
         yt_valid = false;
         allow_fused = true;
+        lazy_gradient = true;
         comm = nullptr;
         nranks = 1;
         N_total = N;
