@@ -82,10 +82,10 @@ class Context {
     long long N_total;   // all columns over all ranks
     long long ld = 0;    // row stride of Y in doubles
     int Mpad, Npad, nRT, nCB;
-    bool interleave = false;
+    bool interleave_row = false, interleave_col = false;
     // `chunk` as the readers of the pass partials need it (pass_num_slots)
-    long long row_chunk() const { return interleave ? -(long long)grid : chunk; }
-    long long col_chunk() const { return interleave ? (long long)nRT : chunk; }
+    long long row_chunk() const { return interleave_row ? -(long long)grid : chunk; }
+    long long col_chunk() const { return interleave_col ? (long long)nRT : chunk; }
     int device, num_sms;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -149,12 +149,15 @@ class Context {
         // tile order of the matrix passes (stream_pass.cuh, TileWalk).  The interleaved order makes the whole chip
         // read one compact window of the matrix; a TMA-free probe gains 2-3 % from it (scripts/read_order_probe.py),
         // the TMA passes 0.6 % per pass and nothing per step (437.5 vs 438.5 evals/s), so it is opt-in:
-        // BIOEN_B200_PASS_ORDER=interleave (needs every CTA to get tiles of every row tile: nCB >= 4 * grid)
+        // BIOEN_B200_PASS_ORDER=interleave (both passes), =irow or =icol (one of them); needs every CTA to get tiles
+        // of every row tile: nCB >= 4 * grid
         {
             const char* e = getenv("BIOEN_B200_PASS_ORDER");
-            interleave = nCB >= 4LL * grid && e && e[0] == 'i';
+            const bool ok = nCB >= 4LL * grid && e && e[0] == 'i';
+            interleave_row = ok && (e[1] == 'n' || e[1] == 'r');
+            interleave_col = ok && (e[1] == 'n' || e[1] == 'c');
         }
-        slotsA = interleave ? grid : slots(nCB);
+        slotsA = interleave_row ? grid : slots(nCB);
         slotsB = slots(nRT);
         int vb = 4;   // resident 256-thread blocks per SM for the O(N) kernels (measured: 2, 8, 16 are no faster)
         if (const char* e = getenv("BIOEN_B200_VEC_BLOCKS")) vb = std::max(1, atoi(e));
@@ -562,7 +565,8 @@ class Context {
     template <int MODE, bool SUB>
     void launch_pass(const double* vN, const double* vMb) {
         PassArgs a{};
-        a.nRT = nRT; a.nCB = nCB; a.T = T; a.chunk = chunk; a.interleave = interleave ? 1 : 0;
+        a.nRT = nRT; a.nCB = nCB; a.T = T; a.chunk = chunk;
+        a.interleave = ((MODE == kRowPass) ? interleave_row : interleave_col) ? 1 : 0;
         a.evict_first = evict_first;
         a.vN = vN; a.vMb = vMb; a.ab = ab.p;
         a.partial = (MODE == kRowPass) ? partialA.p : partialB.p;
