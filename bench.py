@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: --structures is the TOTAL N, split over the GPUs (default: weak, N per GPU)")
     ap.add_argument("--no-optimum", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads records (other BASELINE configs)")
+    ap.add_argument("--no-find-optimum", action="store_true", help="skip the public-API find_optimum timing")
     ap.add_argument("--no-dropin", action="store_true", help="skip the host-matrix drop-in call (needs M*N*8 B of host RAM)")
     ap.add_argument("--unfused-forces", action="store_true", help="forces: four tile passes instead of two fused")
     ap.add_argument("--theta-scan", type=int, default=0, metavar="K",
@@ -152,7 +154,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference's OpenMP C kernels on the host cores
+# shared by both arms
 # ----------------------------------------------------------------------------------------------------------
 def host_cores():
     try:
@@ -161,81 +163,253 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_evals(M, N_full, cols, steps, warmup, method):
-    """f+g evaluations/s of the reference C code (oracle/_ref) -- or of the oracle port if _ref is absent --
-    on a `cols`-column sample, scaled to N_full columns (cost is linear in N).  Returns (value, info)."""
+def workload_config(args, world):
+    """`config` of the JSON line: IDENTICAL for the B200 arm and the reference arm of one launch (the arms differ in
+    `run_info`, not here)."""
+    n_local = args.n if not args.strong else None
+    n_total = args.n if args.strong else args.n * world
+    alg = float(args.m) * args.n * 8.0
+    return {
+        "workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d per GPU (yTilde %.1f GB fp64), theta=%g"
+                    % (args.method, args.n, args.m, alg / 1e9, THETA) if not args.strong else
+                    "%s f+g evaluation, synthetic generic data N=%d x M=%d in total, split over the GPUs, theta=%g"
+                    % (args.method, args.n, args.m, THETA),
+        "method": args.method, "m": args.m, "n_per_gpu": n_local, "n_total": n_total, "theta": THETA, "seed": SEED,
+        "l2": "inputs (%.1f GB per block) larger than L2 (126 MB) / any host cache; every step evaluates a new point"
+              % (alg / 1e9),
+        "optimum": "L-BFGS from x0 = 0 with BioEn's defaults (linesearch=2, past=10, delta=1e-6, epsilon=1e-6, "
+                   "ftol=1e-5, max_linesearch=100)",
+    }
+
+
+T2O_FILE = os.path.join(ROOT, "gpurun_out", "bench_reference_optimum.json")
+
+
+def _t2o_key(args):
+    return "%s:%d:%d:%g:%d" % (args.method, args.m, args.n, THETA, SEED)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's OpenMP C kernels + liblbfgs on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def host_generate(M, cols, col0=0):
+    """The same synthetic matrix the B200 arm generates on the device (counter-based law, oracle/hostgen.c), built
+    on the host cores; entries agree with the device's to 1-2 ulp."""
+    from oracle import oracle as O
+    lib = O.hostgen()
+    a, _ = observations(M)
+    yT = np.empty((M, cols))
+    lib.hostgen_generic_ytilde(yT.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), cols, M, cols, SEED, col0,
+                               a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), SIG_SIM / SIG_EXP)
+    return yT
+
+
+def available_ram():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
+
+
+def cpu_reference(M, N_full, steps, warmup, method, want_optimum, max_cols=None):
+    """The reference C code (oracle/_ref: BioEn's OpenMP kernels + liblbfgs 1.10, unmodified) -- or the oracle port
+    if _ref is absent -- on the host cores.  Runs on the FULL N_full-column problem when host RAM allows, else on
+    a column sample with the rate scaled linearly in N (stated in `sample`).  Every timed step is one f+g
+    evaluation at a new point; `value` is the MEAN rate over the steps.  Returns (evals/s, info, optimum|None)."""
     from oracle import oracle as O
     from oracle import ref
     cores = host_cores()
-    a, YT = observations(M)
-    rng = np.random.default_rng(SEED + 1)
-    yT = np.empty((M, cols))
-    blk = 64
-    for i in range(0, M, blk):  # chunked: bounded temporaries
-        j = min(M, i + blk)
-        yT[i:j] = a[i:j, None] + (SIG_SIM / SIG_EXP) * rng.standard_normal((j - i, cols))
+    _, YT = observations(M)
+    cols = N_full
+    need = lambda c, copies: int(copies * M * c * 8 * 1.05) + (2 << 30)
+    if max_cols:
+        cols = min(cols, max_cols)
+    ram = available_ram()
+    while ram and cols > 50000 and need(cols, 1) > ram:
+        cols //= 2
+    t0 = time.perf_counter()
+    yT = host_generate(M, cols)
+    gen_s = time.perf_counter() - t0
     G = np.zeros(cols)
     w0 = np.full(cols, 1.0 / cols)
-    x = 0.1 * rng.standard_normal(cols) if method == "logw" else 1e-3 * rng.standard_normal(M)
-    best = None
+    rng = np.random.default_rng(SEED + 7)
+    x = (0.1 * rng.standard_normal(N_full))[:cols] if method == "logw" else 1e-3 * rng.standard_normal(M)
+    x = np.ascontiguousarray(x)
     if ref.available():
-        kind = "reference"
+        kind, used = "reference", cores
         ref.set_num_threads(cores)
         ref.set_fast_openmp_flag(1)      # the reference's fastest mode
-        used = cores
-        evs = []
-        for caching in (True, False):    # the reference's transposed-cache option: time both, keep the faster
-            evs.append((ref.LogwEvaluator(G, yT, YT, THETA, caching=caching) if method == "logw"
-                        else ref.ForcesEvaluator(w0, yT, YT, THETA, caching=caching), caching))
+        # the reference's transposed-cache option ("auto" = on up to 8 GiB, bioen/optimize/common.py:83-106): time
+        # both where a second copy fits, keep the faster
+        modes = [False] + ([True] if (not ram or need(cols, 2.2) < ram) else [])
+        evs = [((ref.LogwEvaluator(G, yT, YT, THETA, caching=c) if method == "logw"
+                 else ref.ForcesEvaluator(w0, yT, YT, THETA, caching=c)), c) for c in modes]
     else:
-        kind = "port"
-        used = 1
+        kind, used = "port", 1
         evs = [((lambda v: O.logw_fg(v, G, yT, YT, THETA)) if method == "logw"
                 else (lambda v: O.forces_fg(v, w0, yT, YT, THETA)), False)]
+    best = None
     for ev, caching in evs:
-        for _ in range(max(1, warmup)):
+        for k in range(max(1, warmup)):
             ev(x)
         times = []
         for k in range(steps):
+            x[0] += 1e-9                 # a new point every step
             t0 = time.perf_counter()
-            ev(x + 1e-9 * k)
+            ev(x)
             times.append(time.perf_counter() - t0)
-        if best is None or min(times) < best[0]:
-            best = (min(times), float(np.mean(times)), caching)
-    dt_best, dt_mean, caching = best
-    per_eval_full = dt_best * (N_full / cols)
-    info = {"kind": kind, "cores": used, "ms_per_eval_sample": 1e3 * dt_best,
-            "sample": "%d of %d columns x %d rows (%.1f GB), best of %d f+g evaluations (mean %.1f ms, best "
-                      "%.1f ms), fast_openmp=1, yTildeT cache %s (faster of on/off); evals/s scaled by %d/%d "
-                      "(cost linear in N)" % (cols, N_full, M, M * cols * 8 / 1e9, steps, 1e3 * dt_mean,
-                                              1e3 * dt_best, "on" if caching else "off", cols, N_full)}
-    return 1.0 / per_eval_full, info
+        if best is None or np.mean(times) < best[0]:
+            best = (float(np.mean(times)), float(min(times)), caching)
+    dt_mean, dt_best, caching = best
+    scale = N_full / cols
+    info = {"kind": kind, "cores": used, "ms_per_eval_mean": 1e3 * dt_mean * scale, "ms_per_eval_best": 1e3 * dt_best * scale,
+            "host_generate_s": gen_s,
+            "sample": ("the full problem: %d columns x %d rows (%.1f GB)" % (cols, M, M * cols * 8 / 1e9) if cols == N_full
+                       else "%d of %d columns x %d rows (%.1f GB; host RAM %.0f GB), rate scaled by %d/%d (cost linear "
+                            "in N)" % (cols, N_full, M, M * cols * 8 / 1e9, ram / 1e9, cols, N_full))
+                      + "; mean of %d f+g evaluations at new points (mean %.1f ms, best %.1f ms), %d OpenMP threads, "
+                        "fast_openmp=1, yTildeT cache %s (faster of on/off where both fit), built -O3 -march=x86-64-v3 "
+                        "(the library is compiled off-box; the kernels are DRAM-bound, AVX-512 would not change them)"
+                        % (steps, 1e3 * dt_mean, 1e3 * dt_best, used, "on" if caching else "off")}
+    optimum = None
+    if want_optimum and kind == "reference" and cols == N_full:
+        x0 = np.zeros(cols if method == "logw" else M)
+        t0 = time.perf_counter()
+        if method == "logw":
+            xo, fmin, code = ref.opt_lbfgs_logw(x0, G, yT, YT, THETA, caching=caching)
+            its = ctypes.c_size_t.in_dll(ref.lib(), "iterations_lbfgs_logw").value
+        else:
+            xo, fmin, code = ref.opt_lbfgs_forces(x0, w0, yT, YT, THETA, caching=caching)
+            its = ctypes.c_size_t.in_dll(ref.lib(), "iterations_lbfgs_forces").value
+        secs = time.perf_counter() - t0
+        optimum = {"seconds": secs, "fmin": fmin, "code": int(code), "iterations": int(its),
+                   "minimizer": "the reference's _opt_lbfgs_%s (liblbfgs 1.10, BioEn defaults) on the full problem, "
+                                "%d OpenMP threads, yTildeT cache %s" % (method, used, "on" if caching else "off"),
+                   "includes": "host arrays in, result out; the matrix (and its cached transpose) already in host RAM"}
+    elif want_optimum:
+        optimum = {"unavailable": "needs oracle/_ref and the full matrix in host RAM (%.0f GB available)" % (ram / 1e9)}
+    return 1.0 / (dt_mean * scale), info, optimum
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
     t_wall = time.perf_counter()
-    value, info = cpu_reference_evals(args.m, args.n, args.cpu_cols, steps, min(args.warmup, 2), args.method)
+    value, info, optimum = cpu_reference(args.m, args.n, args.steps, args.warmup, args.method,
+                                         want_optimum=not args.no_optimum and not args.strong)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": unit(args), "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d, theta=%g"
-                               % (args.method, args.n, args.m, THETA), "method": args.method},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": unit(args),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": unit(args), "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
-        "e2e": {"value": value, "unit": unit(args), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
+        "gpu_launches": 0,
+        "run_info": {"ms_per_eval_mean": info["ms_per_eval_mean"], "ms_per_eval_best": info["ms_per_eval_best"],
+                     "host_generate_s": info["host_generate_s"],
+                     "note": "one host runs the blocks of all %d GPU(s) one after the other: the rate in N-column "
+                             "blocks per second does not depend on n_gpus" % args.gpus},
     }
+    # (the unit counts N-column blocks, so the host's rate is the same at every n_gpus)
+    line["e2e"] = {"value": line["value"], "unit": unit(args), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if optimum:
+        line["time_to_optimum"] = optimum
+        if "fmin" in optimum:
+            try:   # left for the B200 arm of the same round-end run (it asserts agreement of the two optima)
+                os.makedirs(os.path.dirname(T2O_FILE), exist_ok=True)
+                with open(T2O_FILE, "w") as fh:
+                    json.dump({"key": _t2o_key(args), **optimum, "cores": info["cores"]}, fh)
+            except OSError:
+                pass
+    line["wall_s"] = time.perf_counter() - t_wall
     emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------
+def roofline_hbm(M, N, pass_ms, step_ms, kernel, traffic=None, read_gbs=None):
+    peak, peak_src = measured_peak()
+    alg = float(M) * N * 8.0
+    ach = alg / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+         "peak_source": peak_src, "kernel": kernel + " (one pass over yTilde)", "bytes_per_launch": alg,
+         "ms_per_launch": pass_ms, "step_frac": (2 * alg) / (step_ms * 1e-3) / 1e9 / peak if step_ms > 0 else None}
+    if read_gbs:
+        r["read_only_stream"] = {"gbs": read_gbs, "frac_of_it": ach / read_gbs,
+                                 "what": "plain 16-byte-load read kernel over the same yTilde, mean of 10 launches, "
+                                         "measured in this run; `peak` is a copy (read+write) figure"}
+    return r
+
+
+def connect_problem(prob, rank, world, n_total, dev):
+    """library-side communicator for this rank's block (NCCL id broadcast by torch.distributed)"""
+    import torch
+    import torch.distributed as dist
+    from bioen_b200 import _lib
+    idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        raw = ctypes.create_string_buffer(128)
+        _lib.check(_lib.load().bioen_b200_nccl_unique_id(raw), "nccl_unique_id")
+        idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+    dist.broadcast(idbuf, 0)
+    prob.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world, n_total)
+
+
+def timed_evals(prob, method, nvar, dev, warmup, steps, seed_shift=0, world=1):
+    """device-resident timing of `steps` f+g evaluations; returns (total ms, mean pass ms, launches), max over ranks"""
+    import torch
+    import torch.distributed as dist
+    rng = np.random.default_rng(SEED + 7 + seed_shift)
+    x = torch.from_numpy((0.1 if method == 0 else 1e-3) * rng.standard_normal(nvar)).to(dev)
+    g = torch.zeros_like(x)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ms, pass_ms, launches = prob.time_evals(x.data_ptr(), g.data_ptr(), warmup, steps, method)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ms, pass_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, pass_ms = float(t[0]), float(t[1])
+    return ms, pass_ms, int(launches)
+
+
+def small_workload(name, M, N, local, dev, steps, warmup):
+    """One BASELINE config that is not the headline: logw and forces f+g rates, roofline of the pass kernel and
+    the device L-BFGS to the optimum, on a freshly generated synthetic problem (single GPU)."""
+    import bioen_b200
+    from bioen_b200.problem import FORCES, LOGW
+    a, YT = observations(M)
+    out = {"name": name, "m": M, "n": N, "ytilde_bytes": M * N * 8}
+    with bioen_b200.Problem(shape=(M, N), device=local) as prob:
+        prob.generate(SEED, 0, a, SIG_SIM / SIG_EXP)
+        for mname, method in (("logw", LOGW), ("forces", FORCES)):
+            if method == LOGW:
+                prob.set_logw(np.zeros(N), YT, THETA)
+            else:
+                prob.set_forces(np.full(N, 1.0 / N), YT, THETA)
+            nvar = N if method == LOGW else M
+            ms, pass_ms, launches = timed_evals(prob, method, nvar, dev, warmup, steps)
+            t0 = time.perf_counter()
+            xo, fmin, code, info = prob.opt_lbfgs(np.zeros(nvar))
+            secs = time.perf_counter() - t0
+            rec = {"value": steps / (ms * 1e-3), "unit": "f+g evals/s", "ms_per_step": ms / steps, "gpu_launches": launches,
+                   "roofline": roofline_hbm(M, N, pass_ms, ms / steps, prob.pass_kernel_name(method)),
+                   "time_to_optimum": {"seconds": secs, "code": code, "fmin": fmin, "iterations": info["iterations"],
+                                       "evaluations": info["evaluations"]}}
+            if M * N * 8 <= 100e6:
+                rec["roofline"]["note"] = ("yTilde (%.1f MB) is L2-resident: the second pass of a step is served from "
+                                           "L2, the HBM figure is nominal" % (M * N * 8 / 1e6))
+            out[mname] = rec
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -265,20 +439,14 @@ def run_b200(args):
     method = LOGW if args.method == "logw" else FORCES
     nvar = N if method == LOGW else M
     a, YT = observations(M)
+    n_total = args.n if args.strong else N * world
 
     prob = bioen_b200.Problem(shape=(M, N), device=local)
     if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            raw = ctypes.create_string_buffer(128)
-            _lib.check(_lib.load().bioen_b200_nccl_unique_id(raw), "nccl_unique_id")
-            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-        dist.broadcast(idbuf, 0)
-        prob.comm_init(bytes(idbuf.cpu().numpy().tobytes()), rank, world, args.n if args.strong else N * world)
+        connect_problem(prob, rank, world, n_total, dev)
     t0 = time.perf_counter()
     prob.generate(SEED, col0, a, SIG_SIM / SIG_EXP)          # this rank's columns of the global matrix
     gen_s = time.perf_counter() - t0
-    n_total = args.n if args.strong else N * world
     if method == LOGW:
         prob.set_logw(np.zeros(N), YT, THETA)
     else:
@@ -335,6 +503,12 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = units * e2e_steps / float(te[0])
 
+    # ---- cross-rank correctness of the sharded evaluation (N > 1): the same point through the peer-memory
+    # exchange and through NCCL, and against an independent recombination of rank-local pieces
+    checks = None
+    if world > 1:
+        checks = sharded_checks(prob, method, x_np, YT, N, n_total, dev, world)
+
     # ---- time to optimum (device L-BFGS, BioEn defaults) -----------------------------------------------
     optimum = None
     if not args.no_optimum:
@@ -348,10 +522,23 @@ def run_b200(args):
                    "objective_only_evaluations": info["gradients_skipped"],
                    "minimizer": "device L-BFGS (liblbfgs semantics, BioEn defaults: linesearch=2, past=10, "
                                 "delta=1e-6, epsilon=1e-6)", "includes": "x0 H2D + result D2H; yTilde resident"}
+        try:   # the reference arm of the same run (it runs first) left its optimum of the same problem here
+            with open(T2O_FILE) as fh:
+                r = json.load(fh)
+            if r.get("key") == _t2o_key(args) and world == 1:
+                d = abs(fmin - r["fmin"]) / abs(r["fmin"])
+                optimum["reference"] = {"seconds": r["seconds"], "fmin": r["fmin"], "code": r["code"],
+                                        "iterations": r["iterations"], "cores": r.get("cores"),
+                                        "fmin_rel_diff": d, "agrees_1e-8": bool(d <= 1e-8),
+                                        "speedup": r["seconds"] / optimum["seconds"]}
+                if d > 1e-6:
+                    raise SystemExit("bench.py: device optimum %.12g differs from the reference's %.12g" % (fmin, r["fmin"]))
+        except (OSError, ValueError, KeyError):
+            pass
 
     # ---- the reference-facing call with HOST buffers: bioen.optimize.ext.c_bioen.bioen_opt_lbfgs_* ------------
     dropin = None
-    if world == 1 and not args.no_dropin and not args.no_optimum:
+    if world == 1 and not args.no_dropin and not args.no_optimum and available_ram() > 1.3 * M * N * 8:
         from bioen_b200 import optimize
         from bioen_b200.optimize.ext import c_bioen
         yT_host = prob.download()                       # the same matrix, now a pageable NumPy array
@@ -370,58 +557,243 @@ def run_b200(args):
                          % args.method, "seconds": total_s, "ytilde_upload_s": upload_s,
                   "h2d_bytes": M * N * 8 + (N + M) * 8, "fmin": fmin2,
                   "agrees_with_resident_run": bool(optimum and abs(fmin2 - optimum["fmin"]) <= 1e-8 * abs(fmin2))}
+        # the public API: bioen_b200.optimize.log_weights.find_optimum, host arrays in -> the reference's tuple out
+        if method == LOGW and not args.no_find_optimum:
+            y_host = yT_host                             # y is yTilde: one resident matrix (see DESIGN 'post-processing')
+            GI = np.zeros((N, 1))
+            t0 = time.perf_counter()
+            res = optimize.log_weights.find_optimum(GI, GI, y_host, yT_host, YT.reshape(1, -1), THETA, cfg)
+            dropin["find_optimum_s"] = time.perf_counter() - t0
+            dropin["find_optimum_fmin"] = float(res[4])
         del yT_host
 
-    peak, peak_src = measured_peak()
-    alg_bytes = float(M) * N * 8.0
-    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
+    kernel = "stream_pass_kernel" if method == LOGW or args.unfused_forces else "fused_team_pass"
+    cfgd = workload_config(args, world)
     line = {
         "metric": METRIC, "value": value, "unit": unit(args), "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": "%s f+g evaluation, synthetic generic data N=%d x M=%d per GPU (yTilde %.1f GB fp64 "
-                        "per GPU, N sharded over %d GPU(s)), theta=%g" % (args.method, N, M, alg_bytes / 1e9,
-                                                                         world, THETA),
-            "method": args.method, "n_per_gpu": N, "m": M, "n_total": n_total,
-            "l2": "inputs (%.1f GB) larger than L2 (126 MB); every step evaluates a new point" % (alg_bytes / 1e9),
-            "global_evals_per_s": args.steps / (ms * 1e-3),
-            "generate_s": gen_s, "exchange": prob.comm_mode(),
-        },
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": profiled_traffic(args.method, M, N),
-                     "traffic_source": "profiles/r1_ncu_full_*.csv (ncu --set full of this workload, mean per launch)",
-                     "peak_source": peak_src,
-                     "kernel": ("stream_pass_kernel" if method == LOGW or args.unfused_forces else "fused_team_pass")
-                               + " (one pass over yTilde)", "bytes_per_launch": alg_bytes,
-                     "ms_per_launch": pass_ms,
-                     "read_only_stream": {"gbs": read_gbs.value, "frac_of_it": achieved / read_gbs.value
-                                          if read_gbs.value > 0 else None,
-                                          "what": "plain 16-byte-load read kernel over the same yTilde, mean of 10 "
-                                                  "launches, measured in this run; `peak` is a copy (read+write) figure"},
-                     "step_frac": (2 * M * N * 8.0) / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "config": cfgd,
+        "run_info": {"n_local": N, "global_evals_per_s": args.steps / (ms * 1e-3), "generate_s": gen_s,
+                     "exchange": prob.comm_mode(), "exchanges_per_evaluation": prob.exchanges_per_eval(method)},
+        "roofline": roofline_hbm(M, N, pass_ms, ms / args.steps, kernel, profiled_traffic(args.method, M, N),
+                                 read_gbs.value),
         "e2e": {"value": e2e_value, "unit": unit(args), "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,
                 "api": "bioen_b200_eval (C ABI, pinned host vectors; yTilde resident after one upload)"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
+    line["roofline"]["traffic_source"] = "profiles/ (ncu --set full of this workload, mean per launch)"
     if optimum:
         line["time_to_optimum"] = optimum
     if dropin:
         line["dropin_time_to_optimum"] = dropin
+    if checks:
+        line["sharded_checks"] = checks
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, info = cpu_reference_evals(M, N, args.cpu_cols, 5, 1, args.method)
+            v, info, _ = cpu_reference(M, N, 5, 1, args.method, want_optimum=False, max_cols=args.cpu_cols)
             line["cpu_baseline"] = {"value": v, "unit": unit(args), "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"]}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": unit(args), "cores": 0, "kind": "unavailable", "sample": str(e)}
-    prob.close()
+
+    # ---- the other BASELINE configs, after the timed region of the headline workload --------------------------
+    if not args.no_extra:
+        extra = []
+        es, ew = min(args.steps, 20), min(args.warmup, 3)
+        # (a) the other method on the same resident matrix
+        other = FORCES if method == LOGW else LOGW
+        oname = "forces" if other == FORCES else "logw"
+        if other == FORCES:
+            prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
+        else:
+            prob.set_logw(np.zeros(N), YT, THETA)
+        ovar = M if other == FORCES else N
+        oms, opass, olaunch = timed_evals(prob, other, ovar, dev, ew, es, seed_shift=(rank if other == LOGW else 0),
+                                          world=world)
+        rec = {"name": "config 3, %s method (same matrix, N=%d x M=%d per GPU)" % (oname, N, M),
+               "value": units * es / (oms * 1e-3), "unit": "f+g evals/s (N-column blocks, summed over GPUs)",
+               "ms_per_step": oms / es, "gpu_launches": olaunch,
+               "roofline": roofline_hbm(M, N, opass, oms / es, prob.pass_kernel_name(other))}
+        if not args.no_optimum:
+            barrier()
+            t0 = time.perf_counter()
+            xo, fmin, code, info = prob.opt_lbfgs(np.zeros(ovar))
+            barrier()
+            rec["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "code": code, "fmin": fmin,
+                                      "iterations": info["iterations"], "evaluations": info["evaluations"]}
+        extra.append(rec)
+        # (b) config 4: the 32-theta L-curve batched on fp64 tensor cores, same matrix
+        if not args.strong:
+            extra.append(theta_scan_record(prob, LOGW, 32, M, N, n_total, YT, rank, world, local, dev,
+                                           min(args.steps, 10), ew, not args.no_optimum))
+        prob.close()
+        # (c) configs 2 and 1 (ala5 shape): small, L2-resident problems, single GPU each (rank 0 reports)
+        if world == 1:
+            extra.append(small_workload("config 2: N=1e5 x M=500 (0.4 GB)", 500, 100000, local, dev, es, ew))
+            extra.append(small_workload("config 1 shape (ala5): N=50001 x M=28 (11 MB)", 28, 50001, local, dev, es, ew))
+        else:
+            # (d) strong scaling of config 3 (N = 1e6 in total over the GPUs) and a config-5 shard per GPU
+            extra.append(sharded_record("config 3 strong: N=1e6 x M=1e3 in total", 1000, 1000000, True, rank, world,
+                                        local, dev, es, ew, not args.no_optimum))
+            free_b, _tot = torch.cuda.mem_get_info(dev)
+            if free_b > 115e9:
+                extra.append(sharded_record("config 5 shard: N=1.25e6 x M=5000 per GPU (50 GB per GPU)", 5000, 1250000,
+                                            False, rank, world, local, dev, min(es, 10), 2, not args.no_optimum))
+        line["extra_workloads"] = extra
+    else:
+        prob.close()
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_checks(prob, method, x_np, YT, N, n_total, dev, world):
+    """N > 1: (1) the exchange carried by the peer-memory kernel and by NCCL gives bit-identical f and gradient;
+    (2) f equals an independent recombination -- rank-local pieces computed by the library WITHOUT its communicator
+    semantics (weights download, local yTilde.w through the average entry point is itself sharded, so the pieces are
+    formed on the host from the downloaded weights) summed with torch.distributed -- to 1e-12."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    f1, g1 = prob.objective_and_gradient(x_np)
+    mode = prob.comm_mode()
+    if mode == "p2p":
+        prob.set_option(2, 0)
+        f2, g2 = prob.objective_and_gradient(x_np)
+        prob.set_option(2, 1)
+        out["p2p_vs_nccl_bit_identical"] = bool(f1 == f2 and np.array_equal(g1, g2))
+        out["p2p_vs_nccl_rel_diff"] = abs(f1 - f2) / abs(f1)
+    # every rank must hold the same f
+    fl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(fl, torch.tensor([f1], dtype=torch.float64, device=dev))
+    out["f_identical_on_all_ranks"] = bool(all(float(v) == f1 for v in fl))
+    if method == 0:
+        # independent recombination: global log-sum-exp and the prior from the rank-local g slices (torch collectives,
+        # host arithmetic), chi^2 from the library's all-reduced averages
+        mx = torch.tensor([x_np.max()], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        e = np.exp(x_np - float(mx))
+        parts = torch.tensor([e.sum(), (x_np * e).sum()], dtype=torch.float64, device=dev)
+        dist.all_reduce(parts)
+        S, gE = float(parts[0]), float(parts[1])
+        w = e / S
+        avg = prob.average(w)                           # all-reduced inside the library
+        r = avg - YT
+        # G = 0: prior = theta * (sum g w - log sum exp g + log n_total)
+        f_host = THETA * (gE / S - (float(mx) + np.log(S)) + np.log(n_total)) + 0.5 * float(r @ r)
+        out["f_vs_host_recombination_rel_diff"] = abs(f_host - f1) / abs(f_host)
+        out["f_vs_host_recombination_ok_1e-12"] = bool(abs(f_host - f1) <= 1e-12 * abs(f_host))
+    return out
+
+
+def sharded_record(name, M, n_arg, strong, rank, world, local, dev, steps, warmup, want_optimum):
+    """A second sharded problem of the same job (strong-scaled config 3, or a config-5 shard per GPU): logw and
+    forces f+g rates with the pass roofline, and the log-weights L-BFGS to the optimum."""
+    import bioen_b200
+    import torch
+    import torch.distributed as dist
+    from bioen_b200.dist import shard_bounds
+    from bioen_b200.problem import FORCES, LOGW
+    if strong:
+        lo, hi = shard_bounds(n_arg, rank, world)
+        N, col0, n_total = hi - lo, lo, n_arg
+    else:
+        N, col0, n_total = n_arg, rank * n_arg, n_arg * world
+    a, YT = observations(M)
+    out = {"name": name, "m": M, "n_local": N, "n_total": n_total, "scaling": "strong" if strong else "weak"}
+    prob = bioen_b200.Problem(shape=(M, N), device=local)
+    try:
+        connect_problem(prob, rank, world, n_total, dev)
+        prob.generate(SEED, col0, a, SIG_SIM / SIG_EXP)
+        units = 1 if strong else world
+        for mname, method in (("logw", LOGW), ("forces", FORCES)):
+            if method == LOGW:
+                prob.set_logw(np.zeros(N), YT, THETA)
+            else:
+                prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
+            nvar = N if method == LOGW else M
+            ms, pass_ms, launches = timed_evals(prob, method, nvar, dev, warmup, steps,
+                                                seed_shift=(rank if method == LOGW else 0), world=world)
+            rec = {"value": units * steps / (ms * 1e-3), "unit": "f+g evals/s (%s, summed over GPUs)"
+                   % ("the whole N" if strong else "N-column blocks"), "ms_per_step": ms / steps,
+                   "gpu_launches": launches, "exchange": prob.comm_mode(),
+                   "roofline": roofline_hbm(M, N, pass_ms, ms / steps, prob.pass_kernel_name(method))}
+            if want_optimum and (method == LOGW or M <= 1000):
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                xo, fmin, code, info = prob.opt_lbfgs(np.zeros(nvar))
+                dist.barrier()
+                rec["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "code": code, "fmin": fmin,
+                                          "iterations": info["iterations"], "evaluations": info["evaluations"]}
+            out[mname] = rec
+    finally:
+        prob.close()
+    return out
+
+
+def theta_scan_record(prob, meth, K, M, N, n_total, YT, rank, world, local, dev, steps, warmup, want_optimum):
+    """BASELINE config 4 on the resident matrix: K theta values batched (skinny fp64 GEMMs on tensor cores)."""
+    import torch
+    import torch.distributed as dist
+    from bioen_b200 import _lib
+    lib = _lib.load()
+    forces = meth == 1
+    nvar = M if forces else N
+    if forces:
+        prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
+    else:
+        prob.set_logw(np.zeros(N), YT, THETA)
+    thetas = np.geomspace(1e3, 1e-1, K)
+    rng = np.random.default_rng(SEED + 7 + (0 if forces else rank))
+    X0 = np.ascontiguousarray((1e-3 if forces else 0.1) * rng.standard_normal((K, nvar)))
+    peak_tf = ctypes.c_double()
+    _lib.check(lib.bioen_b200_dmma_peak(local, ctypes.byref(peak_tf)), "dmma_peak")
+    ms, gemm_ms, launches = ctypes.c_float(), ctypes.c_float(), ctypes.c_longlong()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    _lib.check(lib.bioen_b200_time_scan_evals(prob._h, meth, K, _lib.ptr(thetas), _lib.ptr(X0), warmup, steps,
+                                              ctypes.byref(ms), ctypes.byref(gemm_ms), ctypes.byref(launches)),
+               "time_scan_evals")
+    barrier()
+    t = torch.tensor([ms.value, gemm_ms.value], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms, g_ms = float(t[0]), float(t[1])
+    KP = (K + 7) // 8 * 8
+    flops = 2.0 * M * N * KP
+    ach = flops / (g_ms * 1e-3) / 1e12
+    hbm_peak, _ = measured_peak()
+    rec = {"name": "config 4: theta L-curve scan, K=%d theta values batched, N=%d x M=%d per GPU (%s)"
+                   % (K, N, M, "forces" if forces else "logw"),
+           "value": world * K * steps / (tot_ms * 1e-3), "unit": "problem f+g evals/s (summed over K and GPUs)",
+           "ms_per_step": tot_ms / steps, "gpu_launches": int(launches.value),
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf.value, "unit": "TFLOP/s",
+                        "frac": ach / peak_tf.value, "traffic": None,
+                        "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 loop (no fp64 "
+                                       "figure in MEASURED_PEAKS.json)",
+                        "kernel": "batched_gemm_kernel (one pass over yTilde for all K)", "flops_per_launch": flops,
+                        "ms_per_launch": g_ms,
+                        "hbm_frac_same_launch": (M * N * 8.0) / (g_ms * 1e-3) / 1e9 / hbm_peak}}
+    if want_optimum:
+        barrier()
+        t0 = time.perf_counter()
+        X, fmin, codes, info = prob.theta_scan(thetas, x0=np.zeros(nvar), method=meth)
+        barrier()
+        rec["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "rounds": info["rounds"],
+                                  "codes": [int(c) for c in codes],
+                                  "evaluations_total": int(info["evaluations"].sum()),
+                                  "fmin_first_last": [float(fmin[0]), float(fmin[-1])]}
+    return rec
 
 
 def run_theta_scan(args):

@@ -112,6 +112,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
     "bioen_b200_generate_ytilde": (C.c_int, [_vp, C.c_ulonglong, C.c_longlong, _dp, C.c_double]),
     "bioen_b200_kernels_launched": (C.c_longlong, [_vp]),
+    "bioen_b200_query": (C.c_longlong, [_vp, C.c_int]),
     "bioen_b200_debug_read": (C.c_int, [_vp, C.c_int, _dp, C.c_size_t]),
     "bioen_b200_stream": (_vp, [_vp]),
 }

@@ -799,6 +799,18 @@ long long bioen_b200_kernels_launched(bioen_b200_ctx* ctx) {
     return ctx->C.kernels_launched + (ctx->comm ? ctx->comm->p2p_launches : 0);
 }
 
+long long bioen_b200_query(bioen_b200_ctx* ctx, int what) {
+    Context& C = ctx->C;
+    switch (what) {
+        case 0: return C.forces_fused_now() ? 1 : 0;
+        case 1: return C.nranks > 1 ? C.exchanges_per_eval(false) : 0;
+        case 2: return C.nranks > 1 ? C.exchanges_per_eval(true) : 0;
+        case 3: return 0;
+        case 4: return 8;
+        default: return -1;
+    }
+}
+
 int bioen_b200_debug_read(bioen_b200_ctx* ctx, int what, double* out_host, size_t count) {
     return guarded("bioen_b200_debug_read", [&] {
         Context& C = ctx->C;
@@ -827,11 +839,18 @@ void* bioen_b200_stream(bioen_b200_ctx* ctx) { return (void*)ctx->C.stream; }
 namespace {
 struct TempProblem {
     bioen_b200_ctx* ctx = nullptr;
-    TempProblem(int m, int n, const double* yTilde) {
+    // fused = false: the caller needs only weights or the given-weights entry points, which run on the tile kernels;
+    // no structure-major copy is made then
+    TempProblem(int m, int n, const double* yTilde, bool fused = true) {
         ctx = bioen_b200_create(m, n, default_device());
         if (!ctx) throw std::runtime_error(g_last_error);
-        if (yTilde) {
-            ctx->C.upload_matrix(yTilde, (size_t)n);
+        try {
+            ctx->C.allow_fused = fused;
+            if (yTilde) ctx->C.upload_matrix(yTilde, (size_t)n);
+        } catch (...) {
+            bioen_b200_destroy(ctx);
+            ctx = nullptr;
+            throw;
         }
     }
     ~TempProblem() { bioen_b200_destroy(ctx); }
@@ -911,7 +930,7 @@ double _opt_bfgs_logw(params_t p, gsl_config_params config, visual_params visual
 void _get_weights_from_forces(const double* w0, const double* yTilde, const double* forces, double* w,
                               int /*caching*/, const double* /*yTildeT*/, double* /*tmp_n*/, size_t m, size_t n) {
     guarded("_get_weights_from_forces", [&] {
-        TempProblem P((int)m, (int)n, yTilde);
+        TempProblem P((int)m, (int)n, yTilde, false);
         std::vector<double> zeros(m, 0.0);
         if (bioen_b200_set_forces(P.ctx, w0, zeros.data(), 0.0)) throw std::runtime_error(g_last_error);
         if (bioen_b200_weights(P.ctx, BIOEN_B200_FORCES, forces, w, nullptr)) throw std::runtime_error(g_last_error);
@@ -923,7 +942,7 @@ double _bioen_log_posterior_forces(const double* w0, const double* yTilde, const
                                    const double* /*yTildeT*/, double* /*tmp_n*/, double* /*tmp_m*/, int m, int n) {
     double f = kNaN;
     guarded("_bioen_log_posterior_forces", [&] {
-        TempProblem P(m, n, yTilde);
+        TempProblem P(m, n, yTilde, false);
         if (bioen_b200_set_forces(P.ctx, w0, YTilde, theta)) throw std::runtime_error(g_last_error);
         if (bioen_b200_forces_from_weights(P.ctx, w, &f, nullptr)) throw std::runtime_error(g_last_error);
     });
@@ -934,7 +953,7 @@ void _grad_bioen_log_posterior_forces(const double* w0, const double* yTilde, co
                                       double* gradient, double theta, int /*caching*/, const double* /*yTildeT*/,
                                       double* /*tmp_n*/, double* /*tmp_m*/, int m, int n) {
     guarded("_grad_bioen_log_posterior_forces", [&] {
-        TempProblem P(m, n, yTilde);
+        TempProblem P(m, n, yTilde, false);
         double f;
         if (bioen_b200_set_forces(P.ctx, w0, YTilde, theta)) throw std::runtime_error(g_last_error);
         if (bioen_b200_forces_from_weights(P.ctx, w, &f, gradient)) throw std::runtime_error(g_last_error);

@@ -366,6 +366,7 @@ class Context {
         CUDA_CHECK(cudaMemcpyAsync(sc.p + SC_LOGS0, &logs0, sizeof(double), cudaMemcpyHostToDevice, stream));
         sync();
         have_logw = true;
+        have_forces = false;   // Gv (G vs w0) and the aux vectors are shared by the two methods
     }
     // forces: reference weights w0 (this rank's slice)
     void set_forces(const double* w0_host, bool on_device = false) {
@@ -375,6 +376,7 @@ class Context {
         aux_n.ensure(Npad + 8);   // x_j, later E_j (zero padded: it feeds the row pass)
         aux_n2.ensure(Npad + 8);  // lr_j
         have_forces = true;
+        have_logw = false;        // Gv now holds w0
         if (allow_fused && Y && !fused_ready) prepare_fused();
     }
 
@@ -543,6 +545,12 @@ class Context {
         a.tail = msum.p + M;
         k_finalize_rows<<<(M + kVecThreads - 1) / kVecThreads, kVecThreads, 0, stream>>>(a);
         ++kernels_launched;
+    }
+
+    // exchanges between the ranks inside one f+g evaluation (reported by bench.py)
+    int exchanges_per_eval(bool forces) const {
+        if (nranks <= 1) return 0;
+        return forces ? 3 : 3;   // (max, sum) gather + M-vector sum + {3 scalars | gradient M-vector}
     }
 
     // ---- kernel launch helpers ---------------------------------------------------------------------
@@ -744,6 +752,7 @@ class Context {
     }
     // weights only (the reference's _get_weights_from_forces): leaves normalised w in `w`
     void forces_weights_only(double* x) {
+        if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         ++eval_gen;
         ForcesUpdateArgs u{M, x, nullptr, nullptr, 0.0, ab.p, sc.p, nullptr};
         k_forces_update<<<1, 1024, 0, stream>>>(u);

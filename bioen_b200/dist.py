@@ -165,9 +165,10 @@ class ShardedProblem:
     def __exit__(self, *exc):
         self.close()
 
-    def theta_scan(self, thetas, x0=None, **cfg):
-        """Batched theta scan on the sharded problem; X planes are gathered to full length for log-weights."""
-        if self.p.method == LOGW:
+    def theta_scan(self, thetas, x0=None, method=None, **cfg):
+        """Batched theta scan on the sharded problem (same signature as Problem.theta_scan); X planes are gathered
+        to full length for log-weights."""
+        if self._check(method):
             if x0 is not None:
                 x0 = np.asarray(x0, dtype=np.float64)
                 x0 = x0[..., self.lo:self.hi] if x0.shape[-1] == self.n_total else x0

@@ -172,37 +172,26 @@ def bioen_opt_lbfgs_logw(g, G, yTilde, YTilde, theta, params):
     return _finish_lbfgs("bioen_opt_lbfgs_logw", errno.value, result, fmin)
 
 
+def _forces_given_weights(forces, w0, yTilde, YTilde, theta, want_gradient):
+    """The pyx computes the weights from the forces and then calls the given-weights C entry point with them
+    (c_bioen.pyx:560-579, 620-641).  Here both steps run on ONE resident copy of yTilde (one upload, tile kernels
+    only: no structure-major copy is made for a single evaluation)."""
+    from ...problem import FORCES, Problem
+    with Problem(yTilde) as p:
+        p.set_option(1, 0)
+        p.set_forces(w0, YTilde, theta)
+        w, _ = p.weights(forces, FORCES)
+        return p.forces_from_weights(w, gradient=want_gradient)
+
+
 def bioen_log_posterior_forces(forces, w0, yTilde, YTilde, theta, caching=False):
     """c_bioen.pyx:523-581: weights from the forces, then the objective for those weights"""
-    _lib.clear_pending()
-    yT = _lib.mat(yTilde)
-    m, n = yT.shape
-    f, w0v, Y = _lib.vec(forces), _lib.vec(w0), _lib.vec(YTilde)
-    w = np.empty(n, dtype=np.float64)
-    L = _L()
-    L._get_weights_from_forces(_lib.ptr(w0v), _lib.ptr(yT), _lib.ptr(f), _lib.ptr(w), 0, None, None, m, n)
-    _lib.check_pending("bioen_log_posterior_forces")
-    val = L._bioen_log_posterior_forces(_lib.ptr(w0v), _lib.ptr(yT), _lib.ptr(Y), _lib.ptr(w), None, float(theta),
-                                        0, None, None, None, m, n)
-    _lib.check_pending("bioen_log_posterior_forces")
-    return val
+    return _forces_given_weights(forces, w0, yTilde, YTilde, theta, False)
 
 
 def grad_bioen_log_posterior_forces(forces, w0, yTilde, YTilde, theta, caching=False):
     """c_bioen.pyx:584-643"""
-    _lib.clear_pending()
-    yT = _lib.mat(yTilde)
-    m, n = yT.shape
-    f, w0v, Y = _lib.vec(forces), _lib.vec(w0), _lib.vec(YTilde)
-    w = np.empty(n, dtype=np.float64)
-    gradient = np.empty(m, dtype=np.float64)
-    L = _L()
-    L._get_weights_from_forces(_lib.ptr(w0v), _lib.ptr(yT), _lib.ptr(f), _lib.ptr(w), 0, None, None, m, n)
-    _lib.check_pending("grad_bioen_log_posterior_forces")
-    L._grad_bioen_log_posterior_forces(_lib.ptr(w0v), _lib.ptr(yT), _lib.ptr(Y), _lib.ptr(w), _lib.ptr(gradient),
-                                       float(theta), 0, None, None, None, m, n)
-    _lib.check_pending("grad_bioen_log_posterior_forces")
-    return gradient
+    return _forces_given_weights(forces, w0, yTilde, YTilde, theta, True)[1]
 
 
 def bioen_opt_bfgs_forces(forces, w0, yTilde, YTilde, theta, params):

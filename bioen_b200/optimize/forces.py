@@ -175,7 +175,7 @@ def find_optimum_series(forcesInit, w0, y, yTilde, YTilde, thetas, cfg, batched=
             problem.set_forces(w0, YTilde, thetas[0] if thetas else 0.0)
             f0 = _lib.vec(forcesInit)
             w0v, Yv = _lib.vec(w0), _lib.vec(YTilde)
-            yprob = problem if y is yTilde else Problem(y)
+            yprob = problem if y is yTilde else problem.like(y)
             try:
                 for lo in range(0, len(thetas), 32):
                     chunk = thetas[lo:lo + 32]

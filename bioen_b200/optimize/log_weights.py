@@ -243,7 +243,7 @@ def find_optimum_series(GInit, G, y, yTilde, YTilde, thetas, cfg, batched=True, 
         if batched and cfg["minimizer"].upper() in ("LIBLBFGS", "LBFGS"):
             problem.set_logw(G, YTilde, thetas[0] if thetas else 0.0)
             g0 = _lib.vec(GInit)
-            yprob = problem if y is yTilde else Problem(y)
+            yprob = problem if y is yTilde else problem.like(y)
             try:
                 for lo in range(0, len(thetas), 32):
                     chunk = thetas[lo:lo + 32]

@@ -164,18 +164,28 @@ class Problem:
 
     def comm_init(self, unique_id, rank, nranks, n_total):
         _lib.check(self._lib.bioen_b200_comm_init(self._ctx, unique_id, rank, nranks, int(n_total)), "comm_init")
+        self.nranks = int(nranks)
 
     def comm_mode(self):
         """How the per-evaluation exchanges travel: 'single', 'nccl' or 'p2p' (peer-memory kernel over NVLink)."""
         return ("single", "nccl", "p2p")[self._lib.bioen_b200_comm_mode(self._ctx)]
-        self.nranks = nranks
 
     # ---- evaluations --------------------------------------------------------------------------------
     def _dim(self, method):
         return self.m if method == FORCES else self.n
 
+    def _method(self, method):
+        """The method an evaluation runs for: the one whose data is set; an explicit mismatch is an error (G and w0
+        share device storage, so the other method's data is gone)."""
+        if self.method is None:
+            raise RuntimeError("bioen_b200.Problem: call set_logw or set_forces first")
+        if method is not None and method != self.method:
+            raise ValueError("bioen_b200.Problem: %s data is set; call %s first" % (
+                ("log-weights", "set_forces") if self.method == LOGW else ("forces", "set_logw")))
+        return self.method
+
     def objective(self, x, method=None):
-        method = self.method if method is None else method
+        method = self._method(method)
         x = _lib.vec(x)
         if x.size != self._dim(method):
             raise ValueError("wrong length of the variable vector")
@@ -187,7 +197,7 @@ class Problem:
         return f.value
 
     def objective_and_gradient(self, x, method=None):
-        method = self.method if method is None else method
+        method = self._method(method)
         x = _lib.vec(x)
         if x.size != self._dim(method):
             raise ValueError("wrong length of the variable vector")
@@ -197,7 +207,7 @@ class Problem:
         return f.value, g
 
     def gradient(self, x, method=None):
-        method = self.method if method is None else method
+        method = self._method(method)
         probe, self._probe = getattr(self, "_probe", None), None
         if probe is not None and probe[0] == method:
             x = _lib.vec(x)
@@ -212,7 +222,7 @@ class Problem:
 
     def weights(self, x, method=None):
         """w (n,) and, for the log-weights method, s = sum_j exp(g_j) (None for forces)."""
-        method = self.method if method is None else method
+        method = self._method(method)
         x = _lib.vec(x)
         w = np.empty(self.n, dtype=np.float64)
         s = C.c_double()
@@ -240,7 +250,7 @@ class Problem:
     # ---- minimisers ---------------------------------------------------------------------------------
     def opt_lbfgs(self, x0, method=None, verbose=0, **cfg):
         """Device-resident L-BFGS (liblbfgs semantics).  Returns (x, fmin, code, info)."""
-        method = self.method if method is None else method
+        method = self._method(method)
         p = dict(LBFGS_DEFAULTS)
         p.update(cfg)
         c = _lib.lbfgs_config_params(**{k: p[k] for k, _ in _lib.lbfgs_config_params._fields_})
@@ -256,7 +266,7 @@ class Problem:
 
     def opt_gsl(self, x0, method=None, verbose=0, **cfg):
         """Device-resident GSL-style minimisers.  Returns (x, fmin, status, info)."""
-        method = self.method if method is None else method
+        method = self._method(method)
         p = dict(GSL_DEFAULTS)
         p.update(cfg)
         c = _lib.gsl_config_params(float(p["step_size"]), float(p["tol"]), int(p["max_iterations"]),
@@ -310,6 +320,20 @@ class Problem:
                                                    C.c_void_p(int(grad_dev_ptr)), warmup, steps, C.byref(ms),
                                                    C.byref(pass_ms), C.byref(launches)), "time_evals")
         return ms.value, pass_ms.value, launches.value
+
+    def query(self, what):
+        return int(self._lib.bioen_b200_query(self._ctx, int(what)))
+
+    def pass_kernel_name(self, method=None):
+        """Name of the kernel that streams yTilde for `method` (bench.py's roofline record)."""
+        method = self.method if method is None else method
+        if self.query(3):
+            return "persistent_eval_kernel"
+        return "fused_team_pass" if (method == FORCES and self.query(0)) else "stream_pass_kernel"
+
+    def exchanges_per_eval(self, method=None):
+        method = self.method if method is None else method
+        return self.query(2 if method == FORCES else 1)
 
     def kernels_launched(self):
         return int(self._lib.bioen_b200_kernels_launched(self._ctx))

@@ -268,6 +268,12 @@ int bioen_b200_time_evals(bioen_b200_ctx *ctx, int method, double *x_dev, double
 int bioen_b200_generate_ytilde(bioen_b200_ctx *ctx, unsigned long long seed, long long col_offset,
                                const double *ytrue_over_sigma_host, double inv_sigma);
 long long bioen_b200_kernels_launched(bioen_b200_ctx *ctx);
+/* facts about how the context evaluates (bench.py, tests): what = 0: 1 if the forces method runs on the fused
+ * two-pass kernels; 1 / 2: exchanges between the ranks per log-weights / forces f+g evaluation (0 on one GPU);
+ * 3: 1 if evaluations run as ONE persistent cooperative kernel with yTilde held in L2 (small problems);
+ * 4: bytes per element of the resident matrix (8, or 4 with BIOEN_B200_OPT_FP32_STORAGE).  Returns -1 for an
+ * unknown `what`. */
+long long bioen_b200_query(bioen_b200_ctx *ctx, int what);
 int bioen_b200_debug_read(bioen_b200_ctx *ctx, int what, double *out_host, size_t count);
 /* the context's cudaStream_t (for callers that enqueue their own work around the device entry points) */
 void *bioen_b200_stream(bioen_b200_ctx *ctx);

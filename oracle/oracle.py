@@ -120,6 +120,26 @@ def lib():
     return _lib
 
 
+_hostgen = None
+
+
+def hostgen():
+    """libhostgen.so (oracle/hostgen.c): host twin of the device's synthetic-data generator, for bench.py's
+    reference arm and the tests that compare it with tests/util_rng.py."""
+    global _hostgen
+    if _hostgen is None:
+        path = os.path.join(_HERE, "libhostgen.so")
+        src = os.path.join(_HERE, "hostgen.c")
+        if not os.path.isfile(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "hostgen"])
+        L = C.CDLL(path)
+        L.hostgen_generic_ytilde.restype = None
+        L.hostgen_generic_ytilde.argtypes = [_dp, C.c_size_t, C.c_int, C.c_longlong, C.c_ulonglong, C.c_longlong, _dp,
+                                             C.c_double]
+        _hostgen = L
+    return _hostgen
+
+
 def _p(a):
     return a.ctypes.data_as(_dp)
 
