@@ -17,8 +17,12 @@
 #pragma once
 #include <dlfcn.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -78,14 +82,19 @@ constexpr size_t kP2PHeaderBytes = 256;
 constexpr size_t kP2PMaxCount = 8192;  // doubles per rank and exchange; larger messages go through NCCL
 enum P2POp { kP2PSum = 0, kP2PMax = 1, kP2PGather = 2 };
 
-struct P2PArgs {
+// what a kernel needs to take part in an exchange (passed by value inside the kernel arguments); nranks <= 1 = off
+struct P2PDev {
     unsigned char* region[kP2PMaxRanks];  // region[r]: rank r's region as mapped in this process
     int rank, nranks;
     long long cap;
+    unsigned long long timeout_ns;
+};
+
+struct P2PArgs {
+    P2PDev dev;
     const double* send;
     double* recv;
     int count, op;
-    unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -102,11 +111,20 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-__global__ void __launch_bounds__(kP2PThreads, 1) k_p2p_exchange(const P2PArgs a) {
+// One exchange, executed by ALL threads of ONE block (a 1-block kernel, or the block of a larger kernel that
+// finishes its grid reduction -- the producers of the exchanged values call this from their last-arriving block, so
+// an evaluation needs no separate exchange launches).  Delivers send[0..count) into every rank's inbox and returns
+// a pointer to this rank's inbox of the current epoch: rank r's contribution is at inbox + r*cap.  The caller
+// combines the contributions itself (in rank order: all ranks get bit-identical results) and must not start the
+// NEXT exchange before it has finished reading (guaranteed by stream order / by being the same block).
+// *fail is set when a peer did not arrive within the timeout (the caller poisons its result with NaN).
+__device__ __forceinline__ const double* p2p_deliver_and_wait(const P2PDev& a, const double* send, int count,
+                                                              int* fail) {
     __shared__ unsigned long long s_epoch;
     __shared__ int s_fail;
     unsigned char* me = a.region[a.rank];
-    const int tid = threadIdx.x, R = a.nranks;
+    const int tid = threadIdx.x, nthr = blockDim.x, R = a.nranks;
+    __syncthreads();   // `send` may have been produced by other threads of this block
     if (tid == 0) {
         unsigned long long* ep = reinterpret_cast<unsigned long long*>(me + 128);
         s_epoch = *ep + 1;
@@ -116,10 +134,9 @@ __global__ void __launch_bounds__(kP2PThreads, 1) k_p2p_exchange(const P2PArgs a
     __syncthreads();
     const unsigned long long epoch = s_epoch;
     const size_t par = (size_t)(epoch & 1);
-    // deliver this rank's contribution into every inbox (its own included)
     for (int r = 0; r < R; ++r) {
         double* dst = reinterpret_cast<double*>(a.region[r] + kP2PHeaderBytes) + (par * R + a.rank) * a.cap;
-        for (int i = tid; i < a.count; i += kP2PThreads) dst[i] = a.send[i];
+        for (int i = tid; i < count; i += nthr) dst[i] = send[i];
     }
     __threadfence_system();
     __syncthreads();
@@ -135,25 +152,58 @@ __global__ void __launch_bounds__(kP2PThreads, 1) k_p2p_exchange(const P2PArgs a
         }
     }
     __syncthreads();
-    const double* in = reinterpret_cast<const double*>(me + kP2PHeaderBytes) + par * R * a.cap;
-    if (s_fail) {
-        const int total = (a.op == kP2PGather) ? a.count * R : a.count;
-        for (int i = tid; i < total; i += kP2PThreads) a.recv[i] = __longlong_as_double(0x7ff8000000000000LL);
-        return;
-    }
-    if (a.op == kP2PGather) {
+    *fail = s_fail;
+    return reinterpret_cast<const double*>(me + kP2PHeaderBytes) + par * R * a.cap;
+}
+
+__device__ __forceinline__ double p2p_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// exchange + the standard combinations (sum / max / gather), all threads of one block
+__device__ __forceinline__ void p2p_exchange_block(const P2PDev& a, const double* send, double* recv, int count,
+                                                   int op) {
+    int fail;
+    const double* in = p2p_deliver_and_wait(a, send, count, &fail);
+    const int tid = threadIdx.x, nthr = blockDim.x, R = a.nranks;
+    if (fail) {
+        const int total = (op == kP2PGather) ? count * R : count;
+        for (int i = tid; i < total; i += nthr) recv[i] = p2p_nan();
+    } else if (op == kP2PGather) {
         for (int r = 0; r < R; ++r)
-            for (int i = tid; i < a.count; i += kP2PThreads) a.recv[(size_t)r * a.count + i] = __ldcg(in + r * a.cap + i);
+            for (int i = tid; i < count; i += nthr) recv[(size_t)r * count + i] = __ldcg(in + r * a.cap + i);
     } else {
-        for (int i = tid; i < a.count; i += kP2PThreads) {
+        for (int i = tid; i < count; i += nthr) {
             double s = __ldcg(in + i);
             for (int r = 1; r < R; ++r) {
                 const double v = __ldcg(in + r * a.cap + i);
-                s = (a.op == kP2PSum) ? s + v : fmax(s, v);
+                s = (op == kP2PSum) ? s + v : fmax(s, v);
             }
-            a.recv[i] = s;
+            recv[i] = s;
         }
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kP2PThreads, 1) k_p2p_exchange(const P2PArgs a) {
+    p2p_exchange_block(a.dev, a.send, a.recv, a.count, a.op);
+}
+
+// ---- in-process groups ------------------------------------------------------------------------------------
+// Several contexts of ONE process (one host thread each; the same or different devices) form a group without
+// NCCL or CUDA IPC: every rank publishes its region pointer in a process-wide table and waits for the others.
+// This is how the sharded path -- the exchange protocol and the rank-local arithmetic -- is exercised on a box
+// with a single GPU (tests/test_gpu_loopback.py); with one GPU per rank it also serves single-process multi-GPU use.
+struct LocalGroup {
+    std::mutex mu;
+    std::condition_variable cv;
+    int nranks = 0, published = 0, closed = 0;
+    unsigned char* region[kP2PMaxRanks] = {};
+    int device[kP2PMaxRanks] = {};
+};
+inline LocalGroup& local_group(int id) {
+    static std::mutex mu;
+    static std::map<int, LocalGroup> groups;
+    std::lock_guard<std::mutex> lk(mu);
+    return groups[id];
 }
 
 class Comm {
@@ -167,6 +217,8 @@ class Comm {
     unsigned char* mapped[kP2PMaxRanks] = {};
     long long cap = 0;
     long long p2p_launches = 0;
+    int local_group_id = -1;  // >= 0: in-process group (no NCCL, no IPC)
+    unsigned long long timeout_ns = 120ull * 1000000000ull;  // generous: ranks may be skewed by host-side setup
 
     static void unique_id(char out[128]) {
         NcclApi::unique_id id;
@@ -178,13 +230,62 @@ class Comm {
         memcpy(id.internal, id_bytes, 128);
         check(NcclApi::get().CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank");
     }
+    // in-process group: rank `rank_` of `nranks_` contexts of this process that pass the same group id
+    Comm(int group_id, int rank_, int nranks_) : rank(rank_), nranks(nranks_), local_group_id(group_id) {
+        if (group_id < 0) throw std::invalid_argument("bioen_b200: local group id must be >= 0");
+        if (nranks_ > kP2PMaxRanks) throw std::invalid_argument("bioen_b200: too many ranks for a local group");
+    }
     ~Comm() {
         release_p2p();
         if (comm) NcclApi::get().CommDestroy(comm);
     }
+    bool is_local() const { return local_group_id >= 0; }
+    void read_timeout_env() {
+        if (const char* e = getenv("BIOEN_B200_P2P_TIMEOUT_S")) {
+            const double sec = atof(e);
+            if (sec > 0) timeout_ns = (unsigned long long)(sec * 1e9);
+        }
+    }
+    // what the producing kernels need to run an exchange themselves; nranks = 1 switches their exchange code off
+    P2PDev dev_args() const {
+        P2PDev d{};
+        d.rank = rank; d.nranks = (p2p && use_p2p) ? nranks : 1; d.cap = cap; d.timeout_ns = timeout_ns;
+        for (int r = 0; r < nranks && r < kP2PMaxRanks; ++r) d.region[r] = mapped[r];
+        return d;
+    }
+    bool fused_ok(size_t count) const { return p2p && use_p2p && count <= (size_t)cap; }
+    // publish this rank's region in the process-wide table and wait for the rest of the group
+    void enable_local(long long cap_doubles, int device) {
+        read_timeout_env();
+        cap = cap_doubles;
+        const size_t bytes = kP2PHeaderBytes + (size_t)2 * nranks * cap * sizeof(double);
+        CUDA_CHECK(cudaMalloc(&region, bytes));
+        CUDA_CHECK(cudaMemset(region, 0, bytes));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        LocalGroup& g = local_group(local_group_id);
+        std::unique_lock<std::mutex> lk(g.mu);
+        if (g.published == 0) { g.nranks = nranks; g.closed = 0; }
+        if (g.nranks != nranks || g.region[rank]) throw std::invalid_argument("bioen_b200: inconsistent local group");
+        g.region[rank] = region;
+        g.device[rank] = device;
+        ++g.published;
+        g.cv.notify_all();
+        if (!g.cv.wait_for(lk, std::chrono::seconds(120), [&] { return g.published == g.nranks; }))
+            throw std::runtime_error("bioen_b200: local group did not assemble within 120 s");
+        for (int r = 0; r < nranks; ++r) {
+            mapped[r] = g.region[r];
+            if (g.device[r] != device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(g.device[r], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+                cudaGetLastError();
+            }
+        }
+        p2p = true;
+    }
     // Map every rank's inbox into this process.  Collective: every rank must call it.  Any failure on any rank
     // (no peer access, IPC not permitted in this container, ...) leaves all ranks on the NCCL path.
     void enable_p2p(long long cap_doubles, cudaStream_t st) {
+        read_timeout_env();
         const char* env = getenv("BIOEN_B200_P2P");
         int fail = (env && env[0] == '0') || nranks > kP2PMaxRanks;
         cap = cap_doubles;
@@ -237,6 +338,17 @@ class Comm {
         }
     }
     void release_p2p() {
+        if (is_local()) {
+            // the table entry is cleared when the last rank of the group leaves (regions of peers may still be in use
+            // by their own streams until then; every rank synchronises its stream before destroying its context)
+            LocalGroup& g = local_group(local_group_id);
+            std::unique_lock<std::mutex> lk(g.mu);
+            if (p2p && ++g.closed == g.nranks) {
+                g.published = g.closed = g.nranks = 0;
+                for (auto& r : g.region) r = nullptr;
+            }
+            for (auto& m : mapped) m = nullptr;
+        }
         for (int r = 0; r < kP2PMaxRanks; ++r) {
             if (mapped[r] && r != rank) cudaIpcCloseMemHandle(mapped[r]);
             mapped[r] = nullptr;
@@ -247,13 +359,20 @@ class Comm {
     }
     // 0: single rank / none, 1: NCCL, 2: peer-memory kernel
     int mode() const { return nranks <= 1 ? 0 : (p2p && use_p2p ? 2 : 1); }
+    int exchanges = 0;   // p2p exchanges (separate launches + fused into producers) enqueued so far
 
+    void need_nccl() const {
+        if (!comm) throw std::runtime_error("bioen_b200: message too large for the peer-memory inbox and this group "
+                                            "has no NCCL communicator (in-process group)");
+    }
     void allreduce_sum(double* buf, size_t count, cudaStream_t st) {
         if (exchange(buf, buf, count, kP2PSum, st)) return;
+        need_nccl();
         check(NcclApi::get().AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kSum, comm, st), "ncclAllReduce");
     }
     void allreduce_max(double* buf, size_t count, cudaStream_t st) {
         if (exchange(buf, buf, count, kP2PMax, st)) return;
+        need_nccl();
         check(NcclApi::get().AllReduce(buf, buf, count, NcclApi::kFloat64, NcclApi::kMax, comm, st), "ncclAllReduce");
     }
     void allgather(const double* send, double* recv, size_t count, cudaStream_t st) {
@@ -263,14 +382,14 @@ class Comm {
 
    private:
     void nccl_allgather(const double* send, double* recv, size_t count, cudaStream_t st) {
+        need_nccl();
         check(NcclApi::get().AllGather(send, recv, count, NcclApi::kFloat64, comm, st), "ncclAllGather");
     }
     bool exchange(const double* send, double* recv, size_t count, int op, cudaStream_t st) {
         if (!(p2p && use_p2p) || count > (size_t)cap) return false;
         P2PArgs a{};
-        for (int r = 0; r < nranks; ++r) a.region[r] = mapped[r];
-        a.rank = rank; a.nranks = nranks; a.cap = cap; a.send = send; a.recv = recv; a.count = (int)count; a.op = op;
-        a.timeout_ns = 120ull * 1000000000ull;  // generous: ranks may be skewed by host-side setup
+        a.dev = dev_args();
+        a.send = send; a.recv = recv; a.count = (int)count; a.op = op;
         k_p2p_exchange<<<1, kP2PThreads, 0, st>>>(a);
         CUDA_CHECK(cudaGetLastError());
         ++p2p_launches;

@@ -166,7 +166,14 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* red) {
 // final summation order depends only on the launch geometry.
 template <int K, class Fin>
 __device__ __forceinline__ void grid_sum(double (&v)[K], double* partials, unsigned int* ticket, double* red,
-                                         Fin fin) {
+                                         Fin fin);
+
+// Variant that hands the finish to the caller: returns true (to ALL threads of the block, block-uniformly) in the
+// block that arrived last; there thread 0 holds the K totals in v[] and the ticket is already reset.  Used by the
+// kernels that follow their grid reduction with an exchange between the ranks (all threads of the last block take
+// part in it, see comm.cuh).
+template <int K>
+__device__ __forceinline__ bool grid_sum_last(double (&v)[K], double* partials, unsigned int* ticket, double* red) {
     __shared__ bool is_last;
     block_sum<K>(v, red);
     if (threadIdx.x == 0) {
@@ -177,27 +184,34 @@ __device__ __forceinline__ void grid_sum(double (&v)[K], double* partials, unsig
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double acc[K];
+    if (!is_last) return false;
+    __threadfence();
+    double acc[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.0;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += __ldcg(&partials[(size_t)b * K + k]);
-        }
-        block_sum<K>(acc, red);
-        if (threadIdx.x == 0) {
-            *ticket = 0;
-            fin(acc);
-        }
+        for (int k = 0; k < K; ++k) acc[k] += __ldcg(&partials[(size_t)b * K + k]);
     }
+    block_sum<K>(acc, red);
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = acc[k];
+    }
+    return true;
 }
 
-// Same, for K sums plus one maximum (v[K] is the max-reduced value).
 template <int K, class Fin>
-__device__ __forceinline__ void grid_sum_max(double (&v)[K + 1], double* partials, unsigned int* ticket,
-                                             double* red, Fin fin) {
+__device__ __forceinline__ void grid_sum(double (&v)[K], double* partials, unsigned int* ticket, double* red,
+                                         Fin fin) {
+    if (grid_sum_last<K>(v, partials, ticket, red) && threadIdx.x == 0) fin(v);
+}
+
+// Same, for K sums plus one maximum (v[K] is the max-reduced value); finish handed to the caller (see grid_sum_last).
+template <int K>
+__device__ __forceinline__ bool grid_sum_max_last(double (&v)[K + 1], double* partials, unsigned int* ticket,
+                                                  double* red) {
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     auto block_reduce = [&](double (&x)[K + 1]) {
@@ -224,23 +238,30 @@ __device__ __forceinline__ void grid_sum_max(double (&v)[K + 1], double* partial
         is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double acc[K + 1];
+    if (!is_last) return false;
+    __threadfence();
+    double acc[K + 1];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.0;
-        acc[K] = -1.7976931348623157e308;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    acc[K] = -1.7976931348623157e308;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += __ldcg(&partials[(size_t)b * (K + 1) + k]);
-            acc[K] = fmax(acc[K], __ldcg(&partials[(size_t)b * (K + 1) + K]));
-        }
-        block_reduce(acc);
-        if (threadIdx.x == 0) {
-            *ticket = 0;
-            fin(acc);
-        }
+        for (int k = 0; k < K; ++k) acc[k] += __ldcg(&partials[(size_t)b * (K + 1) + k]);
+        acc[K] = fmax(acc[K], __ldcg(&partials[(size_t)b * (K + 1) + K]));
     }
+    block_reduce(acc);
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+#pragma unroll
+        for (int k = 0; k <= K; ++k) v[k] = acc[k];
+    }
+    return true;
+}
+
+template <int K, class Fin>
+__device__ __forceinline__ void grid_sum_max(double (&v)[K + 1], double* partials, unsigned int* ticket,
+                                             double* red, Fin fin) {
+    if (grid_sum_max_last<K>(v, partials, ticket, red) && threadIdx.x == 0) fin(v);
 }
 
 }  // namespace bioen
