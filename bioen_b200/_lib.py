@@ -102,6 +102,7 @@ SIGNATURES = {
     "bioen_b200_selftest_num_slots": (C.c_int, [C.c_longlong, C.c_longlong, C.c_longlong]),
     "bioen_b200_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "bioen_b200_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_longlong]),
+    "bioen_b200_comm_init_local": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_longlong]),
     "bioen_b200_comm_mode": (C.c_int, [_vp]),
     "bioen_b200_set_logw_dev": (C.c_int, [_vp, _vp, _dp, C.c_double]),
     "bioen_b200_set_forces_dev": (C.c_int, [_vp, _vp, _dp, C.c_double]),

@@ -282,8 +282,13 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
             case BIOEN_B200_OPT_FUSED_FORCES: ctx->C.allow_fused = value != 0; break;
             case BIOEN_B200_OPT_LAZY_GRADIENT: ctx->C.lazy_gradient = value != 0; break;
             case BIOEN_B200_OPT_P2P:
-                if (ctx->comm) ctx->comm->use_p2p = value != 0;
+                if (ctx->comm) {
+                    if (ctx->comm->is_local() && !value)
+                        throw std::invalid_argument("bioen_b200: an in-process group has no NCCL path");
+                    ctx->comm->use_p2p = value != 0;
+                }
                 break;
+            case BIOEN_B200_OPT_FUSED_EXCHANGE: ctx->C.fuse_allowed = value != 0; break;
             default: throw std::invalid_argument("bioen_b200: unknown option");
         }
     });
@@ -696,6 +701,55 @@ int bioen_b200_comm_init(bioen_b200_ctx* ctx, const char id[128], int rank, int 
         if (cap < 1024) cap = 1024;
         if (cap > (long long)kP2PMaxCount) cap = (long long)kP2PMaxCount;
         ctx->comm->enable_p2p(cap, ctx->C.stream);
+    });
+}
+
+// Load every kernel the collective operations launch.  With CUDA's lazy module loading the FIRST launch of a kernel
+// loads it, and that load cannot overlap a running kernel of the same context: a rank of an in-process group that
+// meets a kernel for the first time while its peer's exchange kernel is already spinning for it would stall both
+// until the exchange times out (measured: exactly one timeout per kernel family, first call only).
+static void preload_kernels() {
+    cudaFuncAttributes at;
+#define BIOEN_TOUCH(K) CUDA_CHECK(cudaFuncGetAttributes(&at, K))
+    BIOEN_TOUCH(k_p2p_exchange);
+    BIOEN_TOUCH(k_update_lse); BIOEN_TOUCH(k_logw_weights); BIOEN_TOUCH(k_logw_rows_exchange_finalize);
+    BIOEN_TOUCH(k_reduce_row_slots); BIOEN_TOUCH(k_finalize_rows); BIOEN_TOUCH(k_logw_grad);
+    BIOEN_TOUCH(k_forces_weights); BIOEN_TOUCH(k_forces_lr_from_w); BIOEN_TOUCH(k_forces_E);
+    BIOEN_TOUCH(k_forces_grad); BIOEN_TOUCH(k_forces_update); BIOEN_TOUCH(k_dot3); BIOEN_TOUCH(k_axpby);
+    BIOEN_TOUCH(k_lbfgs_pair); BIOEN_TOUCH(k_lbfgs_twoloop); BIOEN_TOUCH(k_fused_lse_merge);
+    BIOEN_TOUCH(k_fused_merge_rows); BIOEN_TOUCH(k_transpose); BIOEN_TOUCH(k_grid_max_abs);
+    BIOEN_TOUCH((stream_pass_kernel<kRowPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kRowPass, true>));
+    BIOEN_TOUCH((stream_pass_kernel<kColPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kColPass, true>));
+#undef BIOEN_TOUCH
+}
+
+int bioen_b200_comm_init_local(bioen_b200_ctx* ctx, int group, int rank, int nranks, long long n_total) {
+    return guarded("bioen_b200_comm_init_local", [&] {
+        ctx->pending_gen = -1;
+        CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->comm.reset(new Comm(group, rank, nranks));
+        ctx->C.set_comm(ctx->comm.get());
+        ctx->C.N_total = n_total;
+        long long cap = ctx->C.M + 16;
+        if (cap < 1024) cap = 1024;
+        if (cap > (long long)kP2PMaxCount) cap = (long long)kP2PMaxCount;
+        // Ranks of an in-process group may share a device, and the CUDA runtime does not let a kernel issued after
+        // a device allocation overlap a kernel of another stream issued before it: a rank that allocates between its
+        // peer's exchange kernel (already spinning for this rank) and its own would stall both until the exchange
+        // times out.  So everything the collective operations allocate lazily is allocated here, before the group
+        // assembles (enable_local is the barrier).
+        Context& C = ctx->C;
+        preload_kernels();
+        ctx->x_for(BIOEN_B200_LOGW);
+        ctx->x_for(BIOEN_B200_FORCES);
+        C.Gv.ensure(C.Npad + 8);
+        C.aux_n.ensure(C.Npad + 8);
+        C.aux_n2.ensure(C.Npad + 8);
+        {
+            const size_t nmax = (size_t)std::max(C.N, C.M);
+            C.lbfgs_store.reserve(((nmax + 15) & ~(size_t)15) * (4 + 2 * (size_t)LbfgsParams().m));
+        }
+        ctx->comm->enable_local(cap, ctx->C.device);
     });
 }
 

@@ -387,6 +387,8 @@ class Comm {
     }
     bool exchange(const double* send, double* recv, size_t count, int op, cudaStream_t st) {
         if (!(p2p && use_p2p) || count > (size_t)cap) return false;
+        NvtxRange nvtx("bioen:p2p_exchange");
+        ++exchanges;
         P2PArgs a{};
         a.dev = dev_args();
         a.send = send; a.recv = recv; a.count = (int)count; a.op = op;

@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <cstdio>
@@ -31,6 +32,16 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define CUDA_CHECK(x) ::bioen::cuda_check((x), #x, __FILE__, __LINE__)
 
 constexpr int kWarp = 32;
+
+// NVTX range (header-only NVTX3: a no-op unless a profiler has injected itself).  Ranges mark the two halves of an
+// evaluation, minimiser iterations, uploads and exchanges, so that an nsys / ncu --nvtx timeline reads in the terms of
+// DESIGN.md.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier + TMA

@@ -50,6 +50,10 @@ struct DevBuf {
     void ensure(size_t count) {
         if (count != n || !p) alloc(count);
     }
+    // at least `count` elements (never shrinks)
+    void reserve(size_t count) {
+        if (count > n || !p) alloc(count);
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -168,7 +172,7 @@ class Context {
         partialB.alloc((size_t)slotsB * Npad);
         ab.alloc((size_t)2 * Mpad);
         avg.alloc(Mpad);
-        msum.alloc(Mpad + 8);
+        msum.alloc(Mpad + 16);
         Yobs.alloc(Mpad);
         w.alloc(Npad + 8);   // +8: the fused kernels copy 16-byte windows that may end one element past N
         sc.alloc(SC_COUNT);
@@ -218,6 +222,7 @@ class Context {
 
     // ---- matrix -------------------------------------------------------------------------------
     void upload_matrix(const double* host, size_t ld_host) {
+        NvtxRange nvtx("bioen:upload_ytilde");
         ld = round_up(N, 16);
         if (Yown.n != (size_t)M * ld || !Yown.p) {
             Yown.release();
@@ -387,6 +392,7 @@ class Context {
     }
     // structure-major copy Yt[j][i] of the resident matrix (the reference's yTildeT cache, made on the device)
     void make_transposed() {
+        NvtxRange nvtx("bioen:transpose_ytilde");
         if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         ldt = (M + 1LL) & ~1LL;
         if (Yt.n != (size_t)N * ldt || !Yt.p) {
@@ -455,6 +461,11 @@ class Context {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
         CUDA_CHECK(cudaFuncSetAttribute(fused_team_pass<KI, T, kFusedGradient>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, f_smem));
+        // also loads the two kernels now (lazy module loading must not happen inside a collective operation of an
+        // in-process group, see preload_kernels in bioen_b200.cu)
+        cudaFuncAttributes at;
+        CUDA_CHECK(cudaFuncGetAttributes(&at, fused_team_pass<KI, T, kFusedSoftmaxAvg>));
+        CUDA_CHECK(cudaFuncGetAttributes(&at, fused_team_pass<KI, T, kFusedGradient>));
     }
 #define BIOEN_TEAM_DISPATCH(FN)                                   \
     do {                                                          \
@@ -504,6 +515,7 @@ class Context {
         if (nranks > 1) comm->allreduce_sum(msum.p, M + ntail, stream);
     }
     void forces_eval_fused_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev) {
+        NvtxRange nvtx("bioen:forces_eval_f(fused)");
         {
             ForcesUpdateArgs a{M, x, xp, d, stp, ab.p, sc.p, stp_dev};
             k_forces_update<<<1, 1024, 0, stream>>>(a);
@@ -525,6 +537,7 @@ class Context {
         finalize_rows_from_msum(true, false);
     }
     void forces_eval_fused_g(double* grad, const double* ddir) {
+        NvtxRange nvtx("bioen:forces_eval_g(fused)");
         launch_fused<kFusedGradient>(avg.p, w.p, aux_n2.p, nullptr);       // t_j, E_j, grad partials
         merge_fused_rows(false, 0);
         {
@@ -550,7 +563,18 @@ class Context {
     // exchanges between the ranks inside one f+g evaluation (reported by bench.py)
     int exchanges_per_eval(bool forces) const {
         if (nranks <= 1) return 0;
-        return forces ? 3 : 3;   // (max, sum) gather + M-vector sum + {3 scalars | gradient M-vector}
+        if (!forces && fuse_exchange()) return 2;   // M+5 doubles (objective half) + 4 scalars (gradient half)
+        return 3;   // (max, sum) gather + M-vector sum + {3 scalars | gradient M-vector}
+    }
+    // Sharded log-weights evaluation with the exchanges inside the producing kernels (peer-memory path only): the
+    // normalisation pair travels with the row sums, so the objective half needs ONE exchange and no exchange launch.
+    bool fuse_exchange() const { return nranks > 1 && comm && comm->fused_ok((size_t)M + 5) && fuse_allowed; }
+    bool fuse_allowed = true;   // BIOEN_B200_OPT_FUSED_EXCHANGE
+    P2PDev p2p_dev() const {
+        if (nranks > 1 && comm && fuse_exchange()) { ++comm->exchanges; return comm->dev_args(); }
+        P2PDev d{};
+        d.nranks = 1;
+        return d;
     }
 
     // ---- kernel launch helpers ---------------------------------------------------------------------
@@ -648,31 +672,48 @@ class Context {
         if (grad) logw_eval_g(x, grad, ddir);
     }
     void logw_eval_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev = nullptr) {
+        NvtxRange nvtx("bioen:logw_eval_f");
         if (!have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
         ++eval_gen;
         launch_lse(x, xp, d, stp, nullptr, false, stp_dev);
-        gather_lse();
+        const bool fused = fuse_exchange();
+        eval_fused = fused;
+        if (!fused) gather_lse();
         {
             LogwWeightsArgs a{};
             a.n = N; a.g = x; a.G = Gv.p; a.w = w.p; a.lse_pairs = lse_pairs(); a.nranks = nranks;
             a.msum_tail = msum.p + M; a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+            a.local_only = fused ? 1 : 0;
             k_logw_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
             ++kernels_launched;
         }
         launch_pass<kRowPass, false>(w.p, nullptr);
-        finalize_rows(false, 3, true);
+        if (fused) {
+            RowsExchangeArgs a{};
+            a.m = M; a.partial = partialA.p; a.ld = Mpad; a.L = nCB; a.chunk = row_chunk(); a.msum = msum.p;
+            a.p2p = p2p_dev(); a.Y = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.theta = theta; a.sc = sc.p;
+            k_logw_rows_exchange_finalize<<<1, kRowsXThreads, 0, stream>>>(a);
+            ++kernels_launched;
+        } else {
+            finalize_rows(false, 3, true);
+        }
     }
+    bool eval_fused = false;   // the last logw_eval_f left un-normalised e_j in `w` (fused sharded path)
     void logw_eval_g(const double* x, double* grad, const double* ddir) {
+        NvtxRange nvtx("bioen:logw_eval_g");
         launch_pass<kColPass, true>(nullptr, nullptr);
         {
             LogwGradArgs a{};
             a.n = N; a.col_partial = partialB.p; a.ld = Npad; a.L = nRT; a.chunk = col_chunk();
             a.g = x; a.G = Gv.p; a.w = w.p; a.d = ddir; a.grad = grad; a.theta = theta;
             a.partials = red_partials.p; a.ticket = ticket.p; a.sc = sc.p;
+            a.wio = w.p;
+            if (eval_fused) a.p2p = p2p_dev(); else a.p2p.nranks = 1;
             k_logw_grad<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
             ++kernels_launched;
         }
-        if (nranks > 1) comm->allreduce_sum(sc.p + SC_DG, 3, stream);  // dg, ||g||^2, ||x||^2
+        if (nranks > 1 && !eval_fused) comm->allreduce_sum(sc.p + SC_DG, 3, stream);  // dg, ||g||^2, ||x||^2
+        eval_fused = false;   // `w` is normalised now
     }
     // weights only (the reference's _get_weights): w normalised over all ranks; returns nothing, see sc[]
     void logw_weights_only(double* x) {
@@ -825,6 +866,7 @@ class Context {
         CUDA_CHECK(e);
     }
     void fetch_scalars() {
+        NvtxRange nvtx("bioen:fetch_scalars");
         d2h(h_sc, sc.p, SC_COUNT);
         spin_sync();
     }

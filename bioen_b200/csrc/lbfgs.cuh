@@ -305,6 +305,7 @@ class Lbfgs {
 
     // x_dev (device, n doubles): start point on entry, end point on exit.  Returns the liblbfgs code.
     int run(double* x_dev, double* fx_out) {
+        NvtxRange nvtx("bioen:lbfgs");
         x = x_dev;
         trace = getenv("BIOEN_B200_TRACE") != nullptr;
         {
@@ -319,7 +320,7 @@ class Lbfgs {
         const size_t np = ((size_t)n + 15) & ~(size_t)15;
         // the work vectors live in the context and are reused by the next minimisation of the same size (every
         // vector is written before it is read, so no clearing is needed)
-        C.lbfgs_store.ensure(np * (4 + 2 * (size_t)m));
+        C.lbfgs_store.reserve(np * (4 + 2 * (size_t)m));
         g = C.lbfgs_store.p; xp = g + np; gp = xp + np; d = gp + np;
         S.resize(m); Yv.resize(m);
         for (int i = 0; i < m; ++i) { S[i] = d + np * (1 + i); Yv[i] = d + np * (1 + m + i); }
@@ -344,6 +345,7 @@ class Lbfgs {
 
         int k = 1, end = 0;
         for (;;) {
+            NvtxRange nvtx_it("bioen:lbfgs_iteration");
             int ls = linesearch(fx, step, dginit, dginit_known);
             if (ls < 0) {
                 // revert to the previous point (lbfgs.c:475-481)
@@ -483,11 +485,16 @@ class Lbfgs {
     }
 
     void enqueue_update(int end_old, int bound, int m) {
-        PairArgs a{n, x, g, xp, gp, S[end_old], Yv[end_old], end_old, C.red_partials.p, C.ticket.p, C.sc.p};
+        NvtxRange nvtx("bioen:lbfgs_update(pair+two_loop)");
+        const bool fused = reduce && C.fuse_exchange();
+        PairArgs a{n, x, g, xp, gp, S[end_old], Yv[end_old], end_old, C.red_partials.p, C.ticket.p, C.sc.p, {}};
+        if (fused) a.p2p = C.p2p_dev(); else a.p2p.nranks = 1;
         k_lbfgs_pair<<<vec_blocks, kVecThreads, 0, C.stream>>>(a);
         ++C.kernels_launched;
-        if (reduce) C.comm->allreduce_sum(C.sc.p + SC_YS, 2, C.stream);
-        C.d2d(C.sc.p + SC_YS0 + end_old, C.sc.p + SC_YS, 1);
+        if (reduce && !fused) {
+            C.comm->allreduce_sum(C.sc.p + SC_YS, 2, C.stream);
+            C.d2d(C.sc.p + SC_YS0 + end_old, C.sc.p + SC_YS, 1);
+        }
         two_loop(bound, (end_old + 1) % m, m);
     }
     void update_direction(int end_old, int bound, int m) {
@@ -513,11 +520,13 @@ class Lbfgs {
 
     // the recursion of lbfgs.c:572-598 as 2*bound+1 fused kernels; the last one also leaves g.d in SC_DGINIT
     void two_loop(int bound, int end, int m) {
+        const bool fused = reduce && C.fuse_exchange();
         auto launch = [&](TwoLoopArgs& a) {
             a.n = n; a.d = d; a.g = g; a.partials = C.red_partials.p; a.ticket = C.ticket.p; a.sc = C.sc.p;
+            if (fused && a.v) a.p2p = C.p2p_dev(); else a.p2p.nranks = 1;
             k_lbfgs_twoloop<<<vec_blocks, kVecThreads, 0, C.stream>>>(a);
             ++C.kernels_launched;
-            if (reduce && a.v) C.comm->allreduce_sum(C.sc.p + a.out, 1, C.stream);
+            if (reduce && !fused && a.v) C.comm->allreduce_sum(C.sc.p + a.out, 1, C.stream);
         };
         std::vector<int> js(bound);
         int j = end;

@@ -7,6 +7,7 @@
 #pragma once
 #include <float.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "stream_pass.cuh"
 
@@ -27,6 +28,7 @@ enum ScalarSlot {
     SC_DG = 11,       // grad . d      } local parts until all-reduced (3 contiguous doubles)
     SC_GNORM2 = 12,   // ||grad||^2    }
     SC_XNORM2 = 13,   // ||x||^2       }
+    SC_WSCALE = 14,   // sharded log-weights: w_j = e_j * sc[SC_WSCALE], e_j = exp(g_j - rank-local max)
     SC_GINF = 15,     // max |grad_j|  (GSL stop test)
     // L-BFGS scalars
     SC_YS = 16,       // y.s of the newest pair
@@ -177,12 +179,16 @@ struct LogwWeightsArgs {
     double* partials;
     unsigned int* ticket;
     double* sc;
+    // 1: sharded run whose normalisation travels WITH the row sums (one exchange per evaluation): w_j = e_j =
+    //    exp(g_j - m_p) with the rank-local maximum m_p, sums of e_j-weighted terms, and tail[3..4] = (m_p, S_p)
+    int local_only;
 };
 
 __global__ void __launch_bounds__(kVecThreads) k_logw_weights(const LogwWeightsArgs a) {
     __shared__ double red[3 * 32];
     double M, S;
-    global_lse(a.lse_pairs, a.nranks, M, S);
+    if (a.local_only) { M = a.sc[SC_LSE_MAX]; S = 1.0; }
+    else global_lse(a.lse_pairs, a.nranks, M, S);
     const double inv = 1.0 / S;
     double v[3] = {0.0, 0.0, 0.0};
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
@@ -195,13 +201,101 @@ __global__ void __launch_bounds__(kVecThreads) k_logw_weights(const LogwWeightsA
     }
     double* tail = a.msum_tail;
     double* sc = a.sc;
+    const int local_only = a.local_only;
     grid_sum<3>(v, a.partials, a.ticket, red, [=](const double(&t)[3]) {
         tail[0] = t[0];
         tail[1] = t[1];
         tail[2] = t[2];
-        sc[SC_GMAX] = M;
-        sc[SC_S] = S;
+        if (local_only) {
+            tail[3] = M;
+            tail[4] = sc[SC_LSE_SUM];
+        } else {
+            sc[SC_GMAX] = M;
+            sc[SC_S] = S;
+        }
     });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sharded log-weights evaluation, the ONE exchange of the objective half, fused with what surrounds it (one block):
+//   slot reduction of the local row pass  ->  this rank's M + 5 doubles {A_p,i = sum_j y_ij e_j; sum (g-G) e,
+//   sum g e, sum G e; m_p; S_p} delivered to every rank's inbox  ->  combination in rank order with the factors
+//   c_p = exp(m_p - m), m = max_p m_p, S = sum_p S_p c_p:  avg_i = sum_p A_p,i c_p / S (likewise the three prior sums)
+//   ->  r_i, chi^2, prior, objective (what k_finalize_rows does on one GPU)  ->  sc[SC_WSCALE] = c_rank / S, the
+//   factor that turns this rank's e_j into globally normalised weights in k_logw_grad.
+// SURVEY 8e / north_star item 4: "one allreduce of the M-vector plus the log-sum-exp / entropy scalars".
+// ------------------------------------------------------------------------------------------------
+struct RowsExchangeArgs {
+    int m;
+    const double* partial;   // row-pass slots
+    long long ld, L, chunk;
+    double* msum;            // m + 5 doubles; [m..m+4] already hold the tail written by k_logw_weights(local_only)
+    P2PDev p2p;
+    const double* Y;
+    double* ab;
+    double* avg;
+    double theta;
+    double* sc;
+};
+
+constexpr int kRowsXThreads = 1024;
+
+__global__ void __launch_bounds__(kRowsXThreads, 1) k_logw_rows_exchange_finalize(const RowsExchangeArgs a) {
+    __shared__ double red[32];
+    __shared__ double s_c[kP2PMaxRanks];
+    __shared__ double s_inv;
+    const int tid = threadIdx.x, R = a.p2p.nranks;
+    for (int i = tid; i < a.m; i += kRowsXThreads) {
+        const int ns = pass_num_slots(i / kTileR, a.L, a.chunk);
+        double s = 0.0;
+        for (int q = 0; q < ns; ++q) s += a.partial[(size_t)q * a.ld + i];
+        a.msum[i] = s;
+    }
+    int fail;
+    const double* in = p2p_deliver_and_wait(a.p2p, a.msum, a.m + 5, &fail);
+    const long long cap = a.p2p.cap;
+    if (tid == 0) {
+        double mx = __ldcg(in + a.m + 3);
+        for (int r = 1; r < R; ++r) mx = fmax(mx, __ldcg(in + r * cap + a.m + 3));
+        double S = 0.0;
+        for (int r = 0; r < R; ++r) {
+            s_c[r] = exp(__ldcg(in + r * cap + a.m + 3) - mx);
+            S += __ldcg(in + r * cap + a.m + 4) * s_c[r];
+        }
+        s_inv = 1.0 / S;
+        a.sc[SC_GMAX] = mx;
+        a.sc[SC_S] = S;
+        a.sc[SC_WSCALE] = fail ? p2p_nan() : s_c[a.p2p.rank] * s_inv;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    double v[1] = {0.0};
+    for (int i = tid; i < a.m; i += kRowsXThreads) {
+        double s = 0.0;
+        for (int r = 0; r < R; ++r) s = fma(__ldcg(in + r * cap + i), s_c[r], s);
+        s *= inv;
+        const double rr = s - a.Y[i];
+        a.avg[i] = s;
+        reinterpret_cast<double2*>(a.ab)[i] = make_double2(rr, s);
+        v[0] = fma(rr, rr, v[0]);
+    }
+    block_sum<1>(v, red);
+    if (tid == 0) {
+        double t[3];
+        for (int k = 0; k < 3; ++k) {
+            double s = 0.0;
+            for (int r = 0; r < R; ++r) s = fma(__ldcg(in + r * cap + a.m + k), s_c[r], s);
+            t[k] = s * inv;
+        }
+        const double chi2 = 0.5 * v[0];
+        const double val = t[0] - (a.sc[SC_GMAX] + log(a.sc[SC_S])) + a.sc[SC_LOGS0];
+        const double prior = val * a.theta;
+        a.sc[SC_GBAR] = t[1];
+        a.sc[SC_CAPGBAR] = t[2];
+        a.sc[SC_CHI2] = chi2;
+        a.sc[SC_PRIOR] = prior;
+        a.sc[SC_F] = fail ? p2p_nan() : prior + chi2;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,17 +391,29 @@ struct LogwGradArgs {
     double* partials;  // gridDim.x * 3
     unsigned int* ticket;
     double* sc;
+    // sharded run with the exchange fused in (p2p.nranks > 1): `wio` holds e_j and is overwritten with the normalised
+    // w_j = e_j * sc[SC_WSCALE]; the block that finishes the grid reduction exchanges {grad.d, ||grad||^2, ||x||^2,
+    // max|grad|} with the other ranks and leaves the global values in sc[]
+    double* wio;
+    P2PDev p2p;
 };
 
 __global__ void __launch_bounds__(kVecThreads) k_logw_grad(const LogwGradArgs a) {
     __shared__ double red[3 * 32];
+    __shared__ double xs[4];
     const double gbar = a.sc[SC_GBAR], Gbar = a.sc[SC_CAPGBAR];
+    const bool fused = a.p2p.nranks > 1;
+    const double wscale = fused ? a.sc[SC_WSCALE] : 1.0;
     double dg = 0.0, gn = 0.0, gi = 0.0;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
         const int ns = pass_num_slots(j / kTileC, a.L, a.chunk);
         double c = 0.0;
         for (int q = 0; q < ns; ++q) c += a.col_partial[(size_t)q * a.ld + j];
-        const double w = a.w[j];
+        double w = a.w[j];
+        if (fused) {
+            w *= wscale;
+            a.wio[j] = w;
+        }
         const double gr = w * a.theta * (a.g[j] - gbar - a.G[j] + Gbar) + w * c;
         a.grad[j] = gr;
         if (a.d) dg = fma(gr, a.d[j], dg);
@@ -315,12 +421,35 @@ __global__ void __launch_bounds__(kVecThreads) k_logw_grad(const LogwGradArgs a)
         gi = fmax(gi, fabs(gr));
     }
     double v[3] = {dg, gn, gi};
-    double* sc = a.sc;
-    grid_sum_max<2>(v, a.partials, a.ticket, red, [=](const double(&t)[3]) {
-        sc[SC_DG] = t[0];
-        sc[SC_GNORM2] = t[1];
-        sc[SC_GINF] = t[2];
-    });
+    if (!grid_sum_max_last<2>(v, a.partials, a.ticket, red)) return;
+    if (!fused) {
+        if (threadIdx.x == 0) {
+            a.sc[SC_DG] = v[0];
+            a.sc[SC_GNORM2] = v[1];
+            a.sc[SC_GINF] = v[2];
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        xs[0] = v[0];
+        xs[1] = v[1];
+        xs[2] = a.sc[SC_XNORM2];   // local ||x||^2 left by k_update_lse
+        xs[3] = v[2];
+    }
+    int fail;
+    const double* in = p2p_deliver_and_wait(a.p2p, xs, 4, &fail);
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        for (int r = 0; r < a.p2p.nranks; ++r) {
+            const double* q = in + r * a.p2p.cap;
+            t0 += __ldcg(q); t1 += __ldcg(q + 1); t2 += __ldcg(q + 2); t3 = fmax(t3, __ldcg(q + 3));
+        }
+        if (fail) t0 = t1 = t2 = t3 = p2p_nan();
+        a.sc[SC_DG] = t0;
+        a.sc[SC_GNORM2] = t1;
+        a.sc[SC_XNORM2] = t2;
+        a.sc[SC_GINF] = t3;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -528,7 +657,28 @@ struct PairArgs {
     double* partials;
     unsigned int* ticket;
     double* sc;
+    P2PDev p2p;        // nranks > 1: the dot products are summed over the ranks by the finishing block
 };
+
+// the block that finished a grid reduction sums its K totals (thread 0 holds them in v) over the ranks
+template <int K>
+__device__ __forceinline__ void p2p_sum_inline(const P2PDev& p, double (&v)[K]) {
+    __shared__ double xs[K];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) xs[k] = v[k];
+    }
+    int fail;
+    const double* in = p2p_deliver_and_wait(p, xs, K, &fail);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int r = 0; r < p.nranks; ++r) s += __ldcg(in + r * p.cap + k);
+            v[k] = fail ? p2p_nan() : s;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kVecThreads) k_lbfgs_pair(const PairArgs a) {
     __shared__ double red[2 * 32];
@@ -543,13 +693,13 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_pair(const PairArgs a) {
         v[0] = fma(y, s, v[0]);
         v[1] = fma(y, y, v[1]);
     }
-    double* sc = a.sc;
-    const int slot = a.slot;
-    grid_sum<2>(v, a.partials, a.ticket, red, [=](const double(&t)[2]) {
-        sc[SC_YS] = t[0];
-        sc[SC_YY] = t[1];
-        sc[SC_YS0 + slot] = t[0];
-    });
+    if (!grid_sum_last<2>(v, a.partials, a.ticket, red)) return;
+    if (a.p2p.nranks > 1) p2p_sum_inline<2>(a.p2p, v);
+    if (threadIdx.x == 0) {
+        a.sc[SC_YS] = v[0];
+        a.sc[SC_YY] = v[1];
+        a.sc[SC_YS0 + a.slot] = v[0];
+    }
 }
 
 // One step of the two-loop recursion, fused: d <- [init ? -g : d] + coef * u ; d *= scale ; out = v . d
@@ -571,6 +721,7 @@ struct TwoLoopArgs {
     double* partials;
     unsigned int* ticket;
     double* sc;
+    P2PDev p2p;           // nranks > 1: the dot product is summed over the ranks by the finishing block
 };
 
 __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs a) {
@@ -590,9 +741,9 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
         if (a.v) v[0] = fma(a.v[j], dj, v[0]);
     }
     if (a.v) {
-        double* sc = a.sc;
-        const int out = a.out;
-        grid_sum<1>(v, a.partials, a.ticket, red, [=](const double(&t)[1]) { sc[out] = t[0]; });
+        if (!grid_sum_last<1>(v, a.partials, a.ticket, red)) return;
+        if (a.p2p.nranks > 1) p2p_sum_inline<1>(a.p2p, v);
+        if (threadIdx.x == 0) a.sc[a.out] = v[0];
     }
 }
 

@@ -181,5 +181,57 @@ class ShardedProblem:
         self.p.close()
 
 
-__all__ = ["shard_bounds", "shard_sizes", "broadcast_bytes", "allgather_vector", "connect", "ShardedProblem",
+class LocalGroup:
+    """The N-sharded problem inside ONE process: `world` bioen_b200.Problem objects (one host thread each) on the
+    given devices -- which may all be the same GPU -- joined through bioen_b200_comm_init_local, exchanging over peer
+    memory without NCCL or CUDA IPC.  `call(fn)` runs fn(rank, problem, lo, hi) on every rank concurrently and
+    returns the list of results; every collective operation of the library (evaluations, minimisers) must be issued
+    on all ranks this way.  Used by the tests to run the sharded kernels and the exchange protocol on a one-GPU box,
+    and usable as a single-process multi-GPU driver."""
+
+    _next_group = [1]
+
+    def __init__(self, yTilde, world, devices=None, problem_cls=None):
+        from concurrent.futures import ThreadPoolExecutor
+        yT = np.asarray(yTilde, dtype=np.float64)
+        self.world = int(world)
+        self.devices = list(devices) if devices is not None else [0] * self.world
+        self.m, self.n_total = yT.shape
+        self.bounds = [shard_bounds(self.n_total, r, self.world) for r in range(self.world)]
+        self.group = LocalGroup._next_group[0]
+        LocalGroup._next_group[0] += 1
+        self.pool = ThreadPoolExecutor(max_workers=self.world)
+        cls = problem_cls or Problem
+        self.problems = [None] * self.world
+
+        def make(r):
+            lo, hi = self.bounds[r]
+            p = cls(np.ascontiguousarray(yT[:, lo:hi]), device=self.devices[r])
+            self.problems[r] = p
+            if self.world > 1:
+                p.comm_init_local(self.group, r, self.world, self.n_total)
+            return True
+        list(self.pool.map(make, range(self.world)))
+
+    def call(self, fn):
+        futs = [self.pool.submit(fn, r, self.problems[r], *self.bounds[r]) for r in range(self.world)]
+        return [f.result() for f in futs]
+
+    def gather(self, parts):
+        return np.concatenate([np.asarray(p, dtype=np.float64).ravel() for p in parts])
+
+    def close(self):
+        if self.pool is not None:
+            self.call(lambda r, p, lo, hi: p.close())
+            self.pool.shutdown()
+            self.pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+__all__ = ["shard_bounds", "shard_sizes", "broadcast_bytes", "allgather_vector", "connect", "ShardedProblem", "LocalGroup",
            "LOGW", "FORCES"]

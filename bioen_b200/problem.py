@@ -166,6 +166,12 @@ class Problem:
         _lib.check(self._lib.bioen_b200_comm_init(self._ctx, unique_id, rank, nranks, int(n_total)), "comm_init")
         self.nranks = int(nranks)
 
+    def comm_init_local(self, group, rank, nranks, n_total):
+        """Join an in-process group (one host thread per rank; blocks until all `nranks` contexts have joined)."""
+        _lib.check(self._lib.bioen_b200_comm_init_local(self._ctx, int(group), int(rank), int(nranks), int(n_total)),
+                   "comm_init_local")
+        self.nranks = int(nranks)
+
     def comm_mode(self):
         """How the per-evaluation exchanges travel: 'single', 'nccl' or 'p2p' (peer-memory kernel over NVLink)."""
         return ("single", "nccl", "p2p")[self._lib.bioen_b200_comm_mode(self._ctx)]

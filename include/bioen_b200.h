@@ -174,8 +174,12 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * exchanges with the library's peer-memory kernel over NVLink instead of NCCL.
  * BIOEN_B200_OPT_LAZY_GRADIENT (default 1): the minimisers run the gradient half of an evaluation only when the
  * algorithm reads it (backtracking trials that fail the sufficient-decrease test skip it; GSL's f-then-df on one
- * point does not repeat the objective half).  Results are bit-identical either way; 0 exists for that comparison. */
-enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3 };
+ * point does not repeat the objective half).  Results are bit-identical either way; 0 exists for that comparison.
+ * BIOEN_B200_OPT_FUSED_EXCHANGE (default 1; all ranks together): sharded log-weights evaluations and L-BFGS dot
+ * products exchange from INSIDE the kernels that produce the values (no exchange launches; the log-sum-exp pair travels
+ * with the row sums: one exchange per objective half).  0 restores the three separate exchanges per evaluation. */
+enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
+       BIOEN_B200_OPT_FUSED_EXCHANGE = 4 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
@@ -246,6 +250,11 @@ int bioen_b200_selftest_num_slots(long long run, long long L, long long chunk);
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
 int bioen_b200_comm_init(bioen_b200_ctx *ctx, const char id[128], int rank, int nranks, long long n_total);
+/* the same for a group of contexts inside ONE process (one host thread per rank, every rank calls this with the same
+ * `group` >= 0; the same or different devices): no NCCL, no IPC -- the ranks find each other through a process-wide
+ * table and exchange over peer memory only.  This is how the sharded path runs on a single-GPU box (tests), and a
+ * single-process multi-GPU program can use it as well.  Messages above the inbox size (theta scan) are not supported. */
+int bioen_b200_comm_init_local(bioen_b200_ctx *ctx, int group, int rank, int nranks, long long n_total);
 /* how the per-evaluation exchanges travel: 0 single rank, 1 NCCL, 2 peer-memory kernel (CUDA IPC + NVLink) */
 int bioen_b200_comm_mode(bioen_b200_ctx *ctx);
 
