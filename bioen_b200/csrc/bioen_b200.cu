@@ -289,6 +289,7 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
                 }
                 break;
             case BIOEN_B200_OPT_FUSED_EXCHANGE: ctx->C.fuse_allowed = value != 0; break;
+            case BIOEN_B200_OPT_PERSISTENT: ctx->C.persistent_mode = value; break;
             default: throw std::invalid_argument("bioen_b200: unknown option");
         }
     });
@@ -711,7 +712,7 @@ int bioen_b200_comm_init(bioen_b200_ctx* ctx, const char id[128], int rank, int 
 static void preload_kernels() {
     cudaFuncAttributes at;
 #define BIOEN_TOUCH(K) CUDA_CHECK(cudaFuncGetAttributes(&at, K))
-    BIOEN_TOUCH(k_p2p_exchange);
+    BIOEN_TOUCH(k_p2p_exchange); BIOEN_TOUCH(persistent_eval_kernel);
     BIOEN_TOUCH(k_update_lse); BIOEN_TOUCH(k_logw_weights); BIOEN_TOUCH(k_logw_rows_exchange_finalize);
     BIOEN_TOUCH(k_reduce_row_slots); BIOEN_TOUCH(k_finalize_rows); BIOEN_TOUCH(k_logw_grad);
     BIOEN_TOUCH(k_forces_weights); BIOEN_TOUCH(k_forces_lr_from_w); BIOEN_TOUCH(k_forces_E);
@@ -859,8 +860,9 @@ long long bioen_b200_query(bioen_b200_ctx* ctx, int what) {
         case 0: return C.forces_fused_now() ? 1 : 0;
         case 1: return C.nranks > 1 ? C.exchanges_per_eval(false) : 0;
         case 2: return C.nranks > 1 ? C.exchanges_per_eval(true) : 0;
-        case 3: return 0;
+        case 3: return C.persistent_for(what == 3 && C.have_forces) ? 1 : 0;
         case 4: return 8;
+        case 5: return C.persistent_launches;
         default: return -1;
     }
 }

@@ -20,6 +20,7 @@
 
 #include "comm.cuh"
 #include "fused_pass.cuh"
+#include "persistent_eval.cuh"
 #include "stream_pass.cuh"
 #include "vector_kernels.cuh"
 
@@ -108,6 +109,14 @@ class Context {
 
     DevBuf<double> partialA, partialB, ab, avg, msum, Yobs, w, aux_n, aux_n2, Gv, sc, red_partials, lse_all;
     DevBuf<unsigned int> ticket;
+    // persistent cooperative evaluation kernel (persistent_eval.cuh)
+    DevBuf<double> pe_part;
+    DevBuf<unsigned long long> pe_bar;
+    unsigned long long pe_bar_base = 0;
+    bool coop_ok = false;
+    int persistent_mode = -1;              // BIOEN_B200_OPT_PERSISTENT: -1 auto (by size), 0 off, 1 on
+    double persistent_max_bytes = 2.0e9;   // auto: matrices up to this size per GPU (BIOEN_B200_PERSISTENT_MAX_MB)
+    long long persistent_launches = 0;
     double* h_sc = nullptr;  // pinned
     double* h_stp = nullptr; // pinned: step length of the next graph-replayed trial
 
@@ -189,6 +198,19 @@ class Context {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
         CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kPassSmemBytes));
+        pe_part.alloc((size_t)grid * kPSlots + 16);
+        pe_bar.alloc(2);
+        {
+            int coop = 0, per_sm = 0;
+            CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_eval_kernel, kPEvalThreads,
+                                                                     kPassSmemBytes));
+            coop_ok = coop && (long long)per_sm * num_sms >= grid;
+            if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
+            if (const char* e = getenv("BIOEN_B200_PERSISTENT_MAX_MB")) persistent_max_bytes = atof(e) * 1.0e6;
+        }
     }
 
     ~Context() {
@@ -207,6 +229,9 @@ class Context {
         yt_valid = false;
         allow_fused = true;
         lazy_gradient = true;
+        fuse_allowed = true;
+        persistent_mode = -1;
+        if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
         comm = nullptr;
         nranks = 1;
         N_total = N;
@@ -616,6 +641,7 @@ class Context {
     // on this stream between begin_pass_timing() and end_pass_timing(), which returns the mean duration in ms
     std::vector<cudaEvent_t> pass_ev;
     size_t pass_ev_used = 0;
+    long long pass_ev_passes = 0;   // passes bracketed by the event pairs beyond one per pair (persistent kernel)
     bool pass_timing = false;
     void begin_pass_timing(int max_passes) {
         while (pass_ev.size() < (size_t)max_passes * 2) {
@@ -624,6 +650,7 @@ class Context {
             pass_ev.push_back(e);
         }
         pass_ev_used = 0;
+        pass_ev_passes = 0;
         pass_timing = true;
     }
     float end_pass_timing() {
@@ -637,7 +664,7 @@ class Context {
             total += t;
             ++cnt;
         }
-        return cnt ? (float)(total / cnt) : 0.f;
+        return cnt ? (float)(total / (double)(cnt + pass_ev_passes)) : 0.f;
     }
     // finish a row pass that produced avg (logw: tail = 3 weighted sums, forces: tail = KL)
     void finalize_rows(bool is_forces, int ntail, bool ab_with_avg) {
@@ -657,6 +684,50 @@ class Context {
         ++kernels_launched;
     }
 
+    // ---- persistent cooperative evaluation (persistent_eval.cuh) ------------------------------------------------
+    // One kernel per evaluation (or per half).  Used when the matrix is small enough that launch gaps, kernel
+    // ramp-up / tail and separate exchange kernels are a visible share of an evaluation (auto: <= 2 GB per GPU);
+    // the stand-alone kernels remain the path for large matrices, for the fused two-pass forces kernels and for
+    // in-process groups (two cooperative grids cannot be co-resident on one device).
+    bool persistent_for(bool forces) const {
+        if (!coop_ok || persistent_mode == 0 || !Y) return false;
+        if (persistent_mode < 0 && (double)M * (double)ld * 8.0 > persistent_max_bytes) return false;
+        if (forces) return nranks == 1 && !forces_fused_now();
+        if (nranks > 1) return fuse_exchange() && !comm->is_local();
+        return true;
+    }
+    void launch_persistent(int method, int mode, double* x, const double* xp, const double* d, double stp,
+                           const double* stp_dev, double* grad, const double* ddir) {
+        if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        PEvalArgs a{};
+        a.method = method; a.mode = mode; a.M = M; a.N = N;
+        a.row.nRT = nRT; a.row.nCB = nCB; a.row.T = T; a.row.chunk = chunk; a.row.interleave = 0;
+        a.row.evict_first = evict_first; a.row.partial = partialA.p; a.row.ld = Mpad;
+        a.col = a.row;
+        a.col.partial = partialB.p; a.col.ld = Npad;
+        a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev;
+        a.Gv = Gv.p; a.w = w.p; a.aux_n = aux_n.p; a.aux_n2 = aux_n2.p; a.grad = grad; a.ddir = ddir;
+        a.Yobs = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.msum = msum.p; a.theta = theta; a.sc = sc.p;
+        a.part = pe_part.p; a.bar = pe_bar.p; a.bar_base = pe_bar_base; a.ticket = ticket.p;
+        if (method == 0 && nranks > 1) a.p2p = p2p_dev(); else a.p2p.nranks = 1;
+        // the readers of the pass partials inside the kernel use the contiguous tile order
+        if (interleave_row || interleave_col) throw std::logic_error("bioen_b200: persistent kernel needs the contiguous pass order");
+        const int npass = method == 0 ? (mode == kPEvalBoth ? 2 : 1) : (mode == kPEvalBoth ? 4 : 2);
+        const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
+        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+        void* args[] = {(void*)&tmap, (void*)&a};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)persistent_eval_kernel, dim3(grid), dim3(kPEvalThreads), args,
+                                               (size_t)kPassSmemBytes, stream));
+        if (timed) {
+            CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+            pass_ev_passes += npass - 1;   // one event pair brackets npass passes
+        }
+        pe_bar_base += (unsigned long long)peval_num_barriers(method, mode) * (unsigned long long)grid;
+        passes_launched += npass;
+        ++kernels_launched;
+        ++persistent_launches;
+    }
+
     // ---- log-weights evaluation (c_bioen_kernels_logw.c:525-561) ------------------------------------------
     // x (device, N): evaluated point; when xp != nullptr it is first formed as xp + stp*d.
     // grad == nullptr -> objective only (one pass over Y).  ddir: optional direction for sc[SC_DG].
@@ -668,6 +739,14 @@ class Context {
     bool lazy_gradient = true;   // BIOEN_B200_OPT_LAZY_GRADIENT: minimisers may use the split (results identical)
     void logw_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir,
                    const double* stp_dev = nullptr) {
+        if (grad && persistent_for(false)) {
+            NvtxRange nvtx("bioen:logw_eval(persistent)");
+            if (!have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
+            ++eval_gen;
+            launch_persistent(0, kPEvalBoth, x, xp, d, stp, stp_dev, grad, ddir);
+            eval_fused = false;
+            return;
+        }
         logw_eval_f(x, xp, d, stp, stp_dev);
         if (grad) logw_eval_g(x, grad, ddir);
     }
@@ -675,6 +754,11 @@ class Context {
         NvtxRange nvtx("bioen:logw_eval_f");
         if (!have_logw) throw std::logic_error("bioen_b200: log-weights data not set");
         ++eval_gen;
+        if (persistent_for(false)) {
+            launch_persistent(0, kPEvalObjective, x, xp, d, stp, stp_dev, nullptr, nullptr);
+            eval_fused = nranks > 1;
+            return;
+        }
         launch_lse(x, xp, d, stp, nullptr, false, stp_dev);
         const bool fused = fuse_exchange();
         eval_fused = fused;
@@ -701,6 +785,11 @@ class Context {
     bool eval_fused = false;   // the last logw_eval_f left un-normalised e_j in `w` (fused sharded path)
     void logw_eval_g(const double* x, double* grad, const double* ddir) {
         NvtxRange nvtx("bioen:logw_eval_g");
+        if (persistent_for(false) && (nranks == 1 || eval_fused)) {
+            launch_persistent(0, kPEvalGradient, const_cast<double*>(x), nullptr, nullptr, 0.0, nullptr, grad, ddir);
+            eval_fused = false;
+            return;
+        }
         launch_pass<kColPass, true>(nullptr, nullptr);
         {
             LogwGradArgs a{};
@@ -732,15 +821,28 @@ class Context {
     // on every rank.  grad == nullptr -> objective only (two passes over Y).
     void forces_eval(double* x, const double* xp, const double* d, double stp, double* grad, const double* ddir,
                      const double* stp_dev = nullptr) {
+        if (grad && have_forces && persistent_for(true)) {
+            NvtxRange nvtx("bioen:forces_eval(persistent)");
+            ++eval_gen;
+            forces_x = x;
+            launch_persistent(1, kPEvalBoth, x, xp, d, stp, stp_dev, grad, ddir);
+            return;
+        }
         forces_eval_f(x, xp, d, stp, stp_dev);
         if (grad) forces_eval_g(grad, ddir);
     }
+    double* forces_x = nullptr;   // the forces vector of the last objective half (persistent gradient half)
     bool forces_fused_now() const { return fused_ready && allow_fused; }
     void forces_eval_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev = nullptr) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         ++eval_gen;
         if (forces_fused_now()) {
             forces_eval_fused_f(x, xp, d, stp, stp_dev);
+            return;
+        }
+        if (persistent_for(true)) {
+            forces_x = x;
+            launch_persistent(1, kPEvalObjective, x, xp, d, stp, stp_dev, nullptr, nullptr);
             return;
         }
         {
@@ -766,6 +868,10 @@ class Context {
     void forces_eval_g(double* grad, const double* ddir) {
         if (forces_fused_now()) {
             forces_eval_fused_g(grad, ddir);
+            return;
+        }
+        if (persistent_for(true)) {
+            launch_persistent(1, kPEvalGradient, forces_x, nullptr, nullptr, 0.0, nullptr, grad, ddir);
             return;
         }
         launch_pass<kColPass, false>(nullptr, nullptr);                 // t_j = sum_i y_ij r_i

@@ -132,21 +132,16 @@ struct TileWalk {
     }
 };
 
-template <int MODE, bool SUB>
-__global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
-    stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // 128-byte align the ring by hand (dynamic smem base is only guaranteed 16-byte aligned)
-    // offset arithmetic on the extern array (not a uintptr_t round trip) keeps the shared address space known
-    // to the compiler: LDS instead of generic LD.E
-    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+// Ring position of one role (producer or consumer) of a CTA.  It survives from one pass to the next when several
+// passes run inside one kernel (persistent_eval.cuh): the mbarrier phases simply continue.
+struct RingPos {
+    int stage;
+    uint32_t phase;
+};
+
+__device__ __forceinline__ void pass_ring_init(unsigned char* smem) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TileWalk tw;   // producer and consumers walk the same tile sequence
-    tw.init(MODE, a, (int)blockIdx.x, (int)gridDim.x);
-
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
@@ -154,43 +149,48 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
         }
         fence_barrier_init();
     }
-    __syncthreads();
+}
 
-    if (warp == kConsumerWarps) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0 && tw.left > 0) {
-            prefetch_tensormap(&tmap);
-            const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
-            int stage = 0;
-            uint32_t phase = 1;  // a fresh barrier passes a wait on parity 1
-            for (; tw.left > 0; tw.advance()) {
-                const int rt = (MODE == kRowPass) ? (int)tw.run : tw.k;
-                const int cb = (MODE == kRowPass) ? tw.k : (int)tw.run;
-                unsigned char* st = smem + (size_t)stage * kStageBytes;
-                mbar_wait(&empty[stage], phase);
-                uint32_t bytes = kTileBytes;
-                if (MODE == kRowPass) bytes += kTileC * 8 + (SUB ? kTileR * 8 : 0);
-                else bytes += kTileR * 16;
-                mbar_expect_tx(&full[stage], bytes);
-                tma_load_2d(st, &tmap, cb * kTileC, rt * kTileR, &full[stage], policy);
-                if (MODE == kRowPass) {
-                    bulk_load_1d(st + kTileBytes, a.vN + (size_t)cb * kTileC, kTileC * 8, &full[stage]);
-                    if (SUB)
-                        bulk_load_1d(st + kTileBytes + kTileC * 8, a.vMb + (size_t)rt * kTileR, kTileR * 8,
-                                     &full[stage]);
-                } else {
-                    bulk_load_1d(st + kTileBytes, a.ab + (size_t)rt * kTileR * 2, kTileR * 16, &full[stage]);
-                }
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
+// the producer role of one pass: called by ONE lane (warp kConsumerWarps, lane 0)
+template <int MODE, bool SUB>
+__device__ __forceinline__ void pass_produce(unsigned char* smem, const CUtensorMap* tmap, const PassArgs& a,
+                                             TileWalk tw, RingPos& rp) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
+    int stage = rp.stage;
+    uint32_t phase = rp.phase;
+    for (; tw.left > 0; tw.advance()) {
+        const int rt = (MODE == kRowPass) ? (int)tw.run : tw.k;
+        const int cb = (MODE == kRowPass) ? tw.k : (int)tw.run;
+        unsigned char* st = smem + (size_t)stage * kStageBytes;
+        mbar_wait(&empty[stage], phase);
+        uint32_t bytes = kTileBytes;
+        if (MODE == kRowPass) bytes += kTileC * 8 + (SUB ? kTileR * 8 : 0);
+        else bytes += kTileR * 16;
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_2d(st, tmap, cb * kTileC, rt * kTileR, &full[stage], policy);
+        if (MODE == kRowPass) {
+            bulk_load_1d(st + kTileBytes, a.vN + (size_t)cb * kTileC, kTileC * 8, &full[stage]);
+            if (SUB)
+                bulk_load_1d(st + kTileBytes + kTileC * 8, a.vMb + (size_t)rt * kTileR, kTileR * 8, &full[stage]);
+        } else {
+            bulk_load_1d(st + kTileBytes, a.ab + (size_t)rt * kTileR * 2, kTileR * 16, &full[stage]);
         }
-        return;
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    rp.stage = stage;
+    rp.phase = phase;
+}
 
-    // ---------------------------------------------------------------------- consumers
-    if (tw.left == 0) return;
-    int stage = 0;
-    uint32_t phase = 0;
+// the consumer role of one pass: called by the kConsumerWarps consumer warps
+template <int MODE, bool SUB>
+__device__ __forceinline__ void pass_consume(unsigned char* smem, const PassArgs& a, TileWalk tw, RingPos& rp) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int stage = rp.stage;
+    uint32_t phase = rp.phase;
 
     if (MODE == kRowPass) {
         constexpr int RPW = kTileR / kConsumerWarps;  // rows per warp = 4
@@ -274,6 +274,34 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
             }
         }
     }
+    rp.stage = stage;
+    rp.phase = phase;
+}
+
+template <int MODE, bool SUB>
+__global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
+    stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 128-byte align the ring by hand (dynamic smem base is only guaranteed 16-byte aligned)
+    // offset arithmetic on the extern array (not a uintptr_t round trip) keeps the shared address space known
+    // to the compiler: LDS instead of generic LD.E
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TileWalk tw;   // producer and consumers walk the same tile sequence
+    tw.init(MODE, a, (int)blockIdx.x, (int)gridDim.x);
+    pass_ring_init(smem);
+    __syncthreads();
+    if (warp == kConsumerWarps) {
+        if (lane == 0 && tw.left > 0) {
+            prefetch_tensormap(&tmap);
+            RingPos rp{0, 1};  // a fresh barrier passes a wait on parity 1
+            pass_produce<MODE, SUB>(smem, &tmap, a, tw, rp);
+        }
+        return;
+    }
+    if (tw.left == 0) return;
+    RingPos rp{0, 0};
+    pass_consume<MODE, SUB>(smem, a, tw, rp);
 }
 
 }  // namespace bioen

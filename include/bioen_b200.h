@@ -177,9 +177,12 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * point does not repeat the objective half).  Results are bit-identical either way; 0 exists for that comparison.
  * BIOEN_B200_OPT_FUSED_EXCHANGE (default 1; all ranks together): sharded log-weights evaluations and L-BFGS dot
  * products exchange from INSIDE the kernels that produce the values (no exchange launches; the log-sum-exp pair travels
- * with the row sums: one exchange per objective half).  0 restores the three separate exchanges per evaluation. */
+ * with the row sums: one exchange per objective half).  0 restores the three separate exchanges per evaluation.
+ * BIOEN_B200_OPT_PERSISTENT (default -1 = by size; 0 off; 1 on): run an evaluation as ONE persistent cooperative
+ * kernel (grid barriers between its phases, yTilde kept in L2 when it fits) instead of 6-11 kernel launches; auto
+ * selects it for matrices up to 2 GB per GPU (environment: BIOEN_B200_PERSISTENT, BIOEN_B200_PERSISTENT_MAX_MB). */
 enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
-       BIOEN_B200_OPT_FUSED_EXCHANGE = 4 };
+       BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
@@ -280,8 +283,8 @@ long long bioen_b200_kernels_launched(bioen_b200_ctx *ctx);
 /* facts about how the context evaluates (bench.py, tests): what = 0: 1 if the forces method runs on the fused
  * two-pass kernels; 1 / 2: exchanges between the ranks per log-weights / forces f+g evaluation (0 on one GPU);
  * 3: 1 if evaluations run as ONE persistent cooperative kernel with yTilde held in L2 (small problems);
- * 4: bytes per element of the resident matrix (8, or 4 with BIOEN_B200_OPT_FP32_STORAGE).  Returns -1 for an
- * unknown `what`. */
+ * 4: bytes per element of the resident matrix (8, or 4 with BIOEN_B200_OPT_FP32_STORAGE); 5: persistent-kernel launches
+ * so far.  Returns -1 for an unknown `what`. */
 long long bioen_b200_query(bioen_b200_ctx *ctx, int what);
 int bioen_b200_debug_read(bioen_b200_ctx *ctx, int what, double *out_host, size_t count);
 /* the context's cudaStream_t (for callers that enqueue their own work around the device entry points) */

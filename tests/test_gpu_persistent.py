@@ -1,0 +1,88 @@
+"""GPU: the persistent cooperative evaluation kernel (one launch per evaluation, csrc/persistent_eval.cuh) against
+the stand-alone kernels (6-11 launches) and the CPU oracle.  Small matrices take the persistent kernel by default,
+so this file is where the stand-alone kernels keep their small-shape coverage (option 5 = 0) and where the two paths
+are played against each other: same objective and gradient to rounding, same minimiser end points."""
+import numpy as np
+import pytest
+
+from conftest import grad_err, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11
+OPT_PERSISTENT = 5
+
+SHAPES = [(1, 1), (2, 1), (3, 5), (31, 127), (32, 128), (33, 129), (64, 4096), (5, 20000), (28, 50001),
+          (257, 3001), (500, 2049), (1000, 777), (300, 40000)]
+
+
+@pytest.mark.parametrize("M,N", SHAPES)
+def test_persistent_vs_standalone_vs_oracle(oracle, M, N):
+    import bioen_b200
+    P = oracle.synthetic_problem(M, N, seed=100 + M + N)
+    rng = np.random.default_rng(M * 7 + N)
+    G = 0.2 * rng.standard_normal(N)
+    g1 = G + 0.1 * rng.standard_normal(N)
+    w0 = rng.random(N) + 0.1
+    w0 /= w0.sum()
+    f1 = 1e-3 * rng.standard_normal(M)
+    theta = 3.7
+    fo_l, go_l = oracle.logw_fg(g1, G, P["yTilde"], P["YTilde"], theta)
+    fo_f, go_f = oracle.forces_fg(f1, w0, P["yTilde"], P["YTilde"], theta)
+    res = {}
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        for mode in (0, 1):
+            p.set_option(OPT_PERSISTENT, mode)
+            p.set_option(1, 0)                         # forces on the tile kernels (the persistent kernel's path)
+            p.set_logw(G, P["YTilde"], theta)
+            assert p.query(3) == mode
+            n0 = p.query(5)
+            f, g = p.objective_and_gradient(g1)
+            assert rel(f, fo_l) < TOL and grad_err(g, go_l) < TOL, (mode, "logw")
+            fonly = p.objective(g1)
+            g2 = p.gradient(g1)                        # gradient half of the point just probed
+            assert rel(fonly, fo_l) < TOL and np.array_equal(g2, g), (mode, "logw split")
+            p.set_forces(w0, P["YTilde"], theta)
+            ff, gf = p.objective_and_gradient(f1)
+            assert rel(ff, fo_f) < TOL and grad_err(gf, go_f) < TOL, (mode, "forces")
+            fonly = p.objective(f1)
+            g2 = p.gradient(f1)
+            assert rel(fonly, fo_f) < TOL and np.array_equal(g2, gf), (mode, "forces split")
+            assert (p.query(5) - n0 > 0) == bool(mode)
+            # run-to-run bit reproducibility
+            ff2, gf2 = p.objective_and_gradient(f1)
+            assert ff2 == ff and np.array_equal(gf2, gf)
+            res[mode] = (f, g, ff, gf)
+    assert rel(res[0][0], res[1][0]) < 1e-13 and grad_err(res[0][1], res[1][1]) < 1e-12
+    assert rel(res[0][2], res[1][2]) < 1e-13 and grad_err(res[0][3], res[1][3]) < 1e-12
+
+
+@pytest.mark.parametrize("M,N,theta", [(28, 50001, 10.0), (100, 20000, 1.0), (37, 5001, 100.0)])
+def test_minimisers_on_both_paths(oracle, M, N, theta):
+    """Device L-BFGS (both line-search families) and GSL bfgs2 end at the same point whichever way the evaluations
+    are launched, and at the oracle's liblbfgs restatement's end point."""
+    import bioen_b200
+    P = oracle.synthetic_problem(M, N, seed=12345)
+    out = {}
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        for mode in (0, 1):
+            p.set_option(OPT_PERSISTENT, mode)
+            p.set_option(1, 0)
+            p.set_logw(P["G"], P["YTilde"], theta)
+            a = p.opt_lbfgs(P["GInit"], max_iterations=60)
+            b = p.opt_lbfgs(P["GInit"], linesearch=0, max_iterations=60)
+            c = p.opt_gsl(P["GInit"], max_iterations=30)
+            p.set_forces(P["w0"], P["YTilde"], theta)
+            d = p.opt_lbfgs(P["forces_init"], max_iterations=40)
+            e = p.opt_lbfgs(P["forces_init"])
+            out[mode] = (a, b, c, d, e)
+    for k in range(4):
+        x0, f0, c0, _ = out[0][k]
+        x1, f1, c1, _ = out[1][k]
+        assert c0 == c1, (k, c0, c1)
+        assert rel(f1, f0) < 1e-8, (k, f0, f1)
+    # converged forces run: rounding differences grow along a long trajectory (tests/test_gpu_fullsize.py), so the
+    # end points are compared with the bound the other minimiser tests use
+    ro = oracle.lbfgs(lambda v: oracle.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], theta), P["forces_init"])
+    tol = 1e-8 if ro["iterations"] < 150 else 1e-4
+    for mode in (0, 1):
+        assert out[mode][4][2] == ro["code"] and rel(out[mode][4][1], ro["fx"]) < tol, (mode, out[mode][4][1], ro["fx"])
