@@ -117,6 +117,7 @@ class Context {
     int persistent_mode = -1;              // BIOEN_B200_OPT_PERSISTENT: -1 auto (by size), 0 off, 1 on
     double persistent_max_bytes = 2.0e9;   // auto: matrices up to this size per GPU (BIOEN_B200_PERSISTENT_MAX_MB)
     long long persistent_launches = 0;
+    DevBuf<unsigned long long> pe_trace;   // BIOEN_B200_PERSISTENT_TRACE: phase-boundary timestamps of CTA 0
     double* h_sc = nullptr;  // pinned
     double* h_stp = nullptr; // pinned: step length of the next graph-replayed trial
 
@@ -201,7 +202,7 @@ class Context {
         CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kPassSmemBytes));
         pe_part.alloc((size_t)grid * kPSlots + 16);
-        pe_bar.alloc(2);
+        pe_bar.alloc(32);   // [0] arrival counter, [16] released barrier number (separate 128-byte lines)
         {
             int coop = 0, per_sm = 0;
             CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
@@ -710,22 +711,45 @@ class Context {
         a.Yobs = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.msum = msum.p; a.theta = theta; a.sc = sc.p;
         a.part = pe_part.p; a.bar = pe_bar.p; a.bar_base = pe_bar_base; a.ticket = ticket.p;
         if (method == 0 && nranks > 1) a.p2p = p2p_dev(); else a.p2p.nranks = 1;
+        static const bool want_trace = getenv("BIOEN_B200_PERSISTENT_TRACE") != nullptr;
+        if (want_trace) {
+            if (!pe_trace.p) pe_trace.alloc(64);
+            a.trace = pe_trace.p;
+        }
         // the readers of the pass partials inside the kernel use the contiguous tile order
         if (interleave_row || interleave_col) throw std::logic_error("bioen_b200: persistent kernel needs the contiguous pass order");
         const int npass = method == 0 ? (mode == kPEvalBoth ? 2 : 1) : (mode == kPEvalBoth ? 4 : 2);
         const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
-        void* args[] = {(void*)&tmap, (void*)&a};
-        CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)persistent_eval_kernel, dim3(grid), dim3(kPEvalThreads), args,
-                                               (size_t)kPassSmemBytes, stream));
+        // Cooperative launch = the driver's guarantee that all CTAs are resident (the grid barriers need it).
+        // BIOEN_B200_PERSISTENT_PLAIN=1 (diagnostics): an ordinary launch, which is resident as well when nothing
+        // else runs on the device (grid <= SM count, 1 CTA per SM) but is not guaranteed to be.
+        static const bool plain = getenv("BIOEN_B200_PERSISTENT_PLAIN") != nullptr;
+        if (plain) {
+            persistent_eval_kernel<<<grid, kPEvalThreads, kPassSmemBytes, stream>>>(tmap, a);
+            CUDA_CHECK(cudaGetLastError());
+        } else {
+            void* args[] = {(void*)&tmap, (void*)&a};
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)persistent_eval_kernel, dim3(grid), dim3(kPEvalThreads),
+                                                   args, (size_t)kPassSmemBytes, stream));
+        }
         if (timed) {
             CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
             pass_ev_passes += npass - 1;   // one event pair brackets npass passes
         }
-        pe_bar_base += (unsigned long long)peval_num_barriers(method, mode) * (unsigned long long)grid;
+        pe_bar_base += (unsigned long long)peval_num_barriers(method, mode, a.p2p.nranks > 1) * (unsigned long long)grid;
         passes_launched += npass;
         ++kernels_launched;
         ++persistent_launches;
+        if (want_trace && (persistent_launches % 16) == 0) {
+            unsigned long long h[40];
+            sync();
+            CUDA_CHECK(cudaMemcpy(h, pe_trace.p, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[persistent trace] method %d mode %d: phase boundaries (us since kernel start):", method, mode);
+            for (int k = 1; k < 40 && h[k] >= h[0] && h[k] - h[0] < 10000000ull; ++k) fprintf(stderr, " %.1f", (h[k] - h[0]) * 1e-3);
+            fprintf(stderr, "\n");
+            CUDA_CHECK(cudaMemset(pe_trace.p, 0, 64 * sizeof(unsigned long long)));
+        }
     }
 
     // ---- log-weights evaluation (c_bioen_kernels_logw.c:525-561) ------------------------------------------

@@ -61,12 +61,26 @@ struct PEvalArgs {
     unsigned long long bar_base;   // counter value when this launch starts (host-tracked)
     unsigned int* ticket;
     P2PDev p2p;          // nranks > 1: sharded log-weights run, exchanges inside the kernel
+    unsigned long long* trace;   // optional: CTA 0 stores %globaltimer at every phase boundary (diagnostics)
 };
 
+__device__ __forceinline__ void peval_mark(const PEvalArgs& a, int& k) {
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[k] = global_timer_ns();
+    ++k;
+}
+
 // barriers a launch passes (the host advances bar_base by this times the grid size)
-__host__ __device__ inline int peval_num_barriers(int method, int mode) {
-    if (method == 0) return mode == kPEvalObjective ? 3 : mode == kPEvalBoth ? 5 : 1;
-    return mode == kPEvalObjective ? 5 : mode == kPEvalBoth ? 9 : 3;
+__host__ __device__ inline int peval_num_barriers(int method, int mode, bool sharded) {
+    if (method == 0) return mode == kPEvalObjective ? 3 : mode == kPEvalBoth ? (sharded ? 5 : 4) : 1;
+    return mode == kPEvalObjective ? 4 : mode == kPEvalBoth ? 7 : 3;
+}
+
+// what replaces a grid barrier where every CTA has just written the SAME values redundantly (M-vectors finished by
+// all CTAs instead of by CTA 0 + barrier): the CTA's own stores must be complete and visible to its bulk copies
+__device__ __forceinline__ void peval_cta_fence() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
@@ -82,10 +96,16 @@ __device__ __forceinline__ void peval_grid_barrier(const PEvalArgs& a, unsigned 
     __syncthreads();
     ++nbar;
     if (threadIdx.x == 0) {
+        // arrivals are counted on a.bar[0]; the CTA that completes the count publishes the barrier's number on
+        // a.bar[1] (its own cache line), which is what the others poll: the spinning loads do not contend with
+        // the arriving atomics
         const unsigned long long target = a.bar_base + (unsigned long long)nbar * gridDim.x;
         __threadfence();
-        atomicAdd(a.bar, 1ULL);
-        while (ld_acquire_gpu_u64(a.bar) < target) {
+        if (atomicAdd(a.bar, 1ULL) + 1 == target) {
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.bar + 16), "l"(target) : "memory");
+        } else {
+            while (ld_acquire_gpu_u64(a.bar + 16) < target) {
+            }
         }
         __threadfence();
     }
@@ -103,6 +123,57 @@ __device__ __forceinline__ void peval_pass(unsigned char* smem, const CUtensorMa
         if (lane == 0 && tw.left > 0) pass_produce<MODE, SUB>(smem, tmap, pa, tw, prod);
     } else if (tw.left > 0) {
         pass_consume<MODE, SUB>(smem, pa, tw, cons);
+    }
+}
+
+// block-wide merge of (max, sum-of-exp) pairs and one plain sum, result in thread 0: the maximum first (shuffles
+// only), then ONE rescaling exp per thread and plain sums -- instead of the exp chain of pairwise lse_merge steps
+// (5 + 5 dependent merges of two exps each in block_lse), which is latency a persistent CTA feels in every phase
+__device__ __forceinline__ void block_lse2(double& m, double& s, double& xn, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double mm = warp_max(m);
+    __syncthreads();
+    if (lane == 0) red[wid] = mm;
+    __syncthreads();
+    mm = red[0];
+    for (int w = 1; w < nw; ++w) mm = fmax(mm, red[w]);
+    s = (s == 0.0) ? 0.0 : s * exp(m - mm);
+    s = warp_sum(s);
+    xn = warp_sum(xn);
+    __syncthreads();
+    if (lane == 0) { red[32 + wid] = s; red[64 + wid] = xn; }
+    __syncthreads();
+    if (wid == 0) {
+        s = warp_sum(lane < nw ? red[32 + lane] : 0.0);
+        xn = warp_sum(lane < nw ? red[64 + lane] : 0.0);
+    }
+    m = mm;
+}
+
+// Row sums of a row pass from its per-CTA slots, for the rows this thread / warp is responsible for.  When a run of
+// tiles is spread over many CTAs (few row tiles, many column blocks: the ala5 shape has 131 slots per row) a thread
+// that adds its row's slots one after the other is a chain of 131 L2 latencies; then a WARP takes a row (lanes stride
+// over the slots, fixed-order shuffle sum).  The choice depends only on the geometry, so results stay reproducible.
+//   f(i, sum) is called once per row, by the lane / thread that owns the row.
+template <class F>
+__device__ __forceinline__ void peval_row_sums(const PassArgs& row, int M, F f) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const int max_slots = pass_num_slots(0, row.nCB, row.chunk);
+    if (max_slots >= 16) {
+        for (int i = wid; i < M; i += nw) {
+            const int ns = pass_num_slots(i / kTileR, row.nCB, row.chunk);
+            double sum = 0.0;
+            for (int q = lane; q < ns; q += 32) sum += __ldcg(row.partial + (size_t)q * row.ld + i);
+            sum = warp_sum(sum);
+            if (lane == 0) f(i, sum);
+        }
+    } else {
+        for (int i = tid; i < M; i += blockDim.x) {
+            const int ns = pass_num_slots(i / kTileR, row.nCB, row.chunk);
+            double sum = 0.0;
+            for (int q = 0; q < ns; ++q) sum += __ldcg(row.partial + (size_t)q * row.ld + i);
+            f(i, sum);
+        }
     }
 }
 
@@ -135,6 +206,8 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
     if (tid == kConsumerWarps * 32) prefetch_tensormap(&tmap);
     __syncthreads();
     double* mypart = a.part + (size_t)b * kPSlots;
+    int mk = 0;
+    peval_mark(a, mk);
     const double stp = a.stp_dev ? __ldg(a.stp_dev) : a.stp;
     const bool sharded = a.p2p.nranks > 1;
 
@@ -153,16 +226,16 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                     else s += exp(x - m);
                 }
             }
-            block_lse(m, s, xn, red);
+            block_lse2(m, s, xn, red);
             if (tid == 0) { mypart[0] = m; mypart[1] = s; mypart[2] = xn; }
-            peval_grid_barrier(a, nbar);
+            { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
             // ---- V1: every CTA merges the G pairs in the same fixed order; weights and the prior sums
             m = -DBL_MAX; s = 0.0; xn = 0.0;
             for (int q = tid; q < G; q += kPEvalThreads) {
                 lse_merge(m, s, __ldcg(a.part + (size_t)q * kPSlots), __ldcg(a.part + (size_t)q * kPSlots + 1));
                 xn += __ldcg(a.part + (size_t)q * kPSlots + 2);
             }
-            block_lse(m, s, xn, red);
+            block_lse2(m, s, xn, red);
             if (tid == 0) {
                 s_val[0] = m; s_val[1] = s;
                 if (b == 0) { a.sc[SC_LSE_MAX] = m; a.sc[SC_LSE_SUM] = s; a.sc[SC_XNORM2] = xn; }
@@ -184,16 +257,19 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
             }
             block_sum<3>(v, red);
             if (tid == 0) { mypart[3] = v[0]; mypart[4] = v[1]; mypart[5] = v[2]; }
-            peval_grid_barrier(a, nbar);
+            { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
             // ---- P2: row pass  avg ~ Y . w
             {
                 PassArgs pa = a.row;
                 pa.vN = a.w;
                 peval_pass<kRowPass, false>(smem, &tmap, pa, prod, cons);
             }
-            peval_grid_barrier(a, nbar);
-            // ---- V3 (CTA 0): finish the objective
-            if (b == 0) {
+            { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
+            // ---- V3: finish the objective.  One GPU: EVERY CTA does it (identical values, fixed order; only CTA 0
+            // writes the scalar file), which saves the grid barrier that would otherwise publish avg / ab to the
+            // column pass.  Sharded: CTA 0 alone (it runs the exchange), then a barrier.
+            if (a.mode == kPEvalObjective && b != 0) return;
+            if (b == 0 || !sharded) {
                 double t[3] = {0.0, 0.0, 0.0};
                 for (int q = tid; q < G; q += kPEvalThreads) {
                     t[0] += __ldcg(a.part + (size_t)q * kPSlots + 3);
@@ -205,17 +281,14 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                 __syncthreads();
                 if (!sharded) {
                     double c[1] = {0.0};
-                    for (int i = tid; i < a.M; i += kPEvalThreads) {
-                        const int ns = pass_num_slots(i / kTileR, a.row.nCB, a.row.chunk);
-                        double sum = 0.0;
-                        for (int q = 0; q < ns; ++q) sum += __ldcg(a.row.partial + (size_t)q * a.row.ld + i);
+                    peval_row_sums(a.row, a.M, [&](int i, double sum) {
                         const double r = sum - a.Yobs[i];
                         a.avg[i] = sum;
                         reinterpret_cast<double2*>(a.ab)[i] = make_double2(r, sum);
                         c[0] = fma(r, r, c[0]);
-                    }
+                    });
                     block_sum<1>(c, red);
-                    if (tid == 0) {
+                    if (tid == 0 && b == 0) {
                         const double chi2 = 0.5 * c[0];
                         const double prior = (s_val[2] - (Mx + log(S)) + a.sc[SC_LOGS0]) * a.theta;
                         a.sc[SC_GMAX] = Mx; a.sc[SC_S] = S;
@@ -226,12 +299,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                     // this rank's M + 5 doubles -> every rank; combination in rank order (see
                     // k_logw_rows_exchange_finalize, the stand-alone twin of this block)
                     __shared__ double s_c[kP2PMaxRanks];
-                    for (int i = tid; i < a.M; i += kPEvalThreads) {
-                        const int ns = pass_num_slots(i / kTileR, a.row.nCB, a.row.chunk);
-                        double sum = 0.0;
-                        for (int q = 0; q < ns; ++q) sum += __ldcg(a.row.partial + (size_t)q * a.row.ld + i);
-                        a.msum[i] = sum;
-                    }
+                    peval_row_sums(a.row, a.M, [&](int i, double sum) { a.msum[i] = sum; });
                     if (tid == 0) {
                         a.msum[a.M] = s_val[2]; a.msum[a.M + 1] = s_val[3]; a.msum[a.M + 2] = s_val[4];
                         a.msum[a.M + 3] = Mx; a.msum[a.M + 4] = S;
@@ -281,7 +349,8 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                 }
             }
             if (a.mode == kPEvalObjective) return;
-            peval_grid_barrier(a, nbar);
+            if (sharded) { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
+            else { peval_mark(a, mk); peval_cta_fence(); peval_mark(a, mk); }   // (V5 reads <g>, <G> from the scalar file after the barrier that follows P4)
         }
         // ---- P4: column pass  c_j = sum_i r_i (y_ij - avg_i)
         {
@@ -289,7 +358,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
             pa.ab = a.ab;
             peval_pass<kColPass, true>(smem, &tmap, pa, prod, cons);
         }
-        peval_grid_barrier(a, nbar);
+        { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- V5: gradient and its scalars; the CTA that arrives last finishes (and exchanges, sharded)
         {
             const double gbar = a.sc[SC_GBAR], Gbar = a.sc[SC_CAPGBAR];
@@ -310,6 +379,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                 }
             }
             double v[3] = {dg, gn, gi};
+            peval_mark(a, mk);
             if (!grid_sum_max_last<2>(v, a.part, a.ticket, red)) return;
             if (!sharded) {
                 if (tid == 0) { a.sc[SC_DG] = v[0]; a.sc[SC_GNORM2] = v[1]; a.sc[SC_GINF] = v[2]; }
@@ -334,26 +404,27 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
 
     // =============================================================================== forces (tile path)
     if (a.mode != kPEvalGradient) {
-        // ---- V0 (CTA 0): f = xp + stp d, ab = {f_i, 0}, ||f||^2
-        if (b == 0) {
+        // ---- V0 (every CTA, identical values: no grid barrier): f = xp + stp d, ab = {f_i, 0}, ||f||^2
+        {
             double c[1] = {0.0};
             for (int i = tid; i < a.M; i += kPEvalThreads) {
-                double x = a.x[i];
+                double x;
                 if (a.xp) { x = fma(stp, a.d[i], a.xp[i]); a.x[i] = x; }
+                else x = a.x[i];
                 reinterpret_cast<double2*>(a.ab)[i] = make_double2(x, 0.0);
                 c[0] = fma(x, x, c[0]);
             }
             block_sum<1>(c, red);
-            if (tid == 0) a.sc[SC_XNORM2] = c[0];
+            if (tid == 0 && b == 0) a.sc[SC_XNORM2] = c[0];
         }
-        peval_grid_barrier(a, nbar);
+        { peval_mark(a, mk); peval_cta_fence(); peval_mark(a, mk); }
         // ---- P1: column pass  x_j = sum_i f_i y_ij
         {
             PassArgs pa = a.col;
             pa.ab = a.ab;
             peval_pass<kColPass, false>(smem, &tmap, pa, prod, cons);
         }
-        peval_grid_barrier(a, nbar);
+        { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- V2: assemble x_j, CTA-local (max, sum w0 exp(x - max))
         double m = -DBL_MAX, s = 0.0, xn = 0.0;
         if (vec) {
@@ -367,14 +438,14 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                 else s += pw * exp(x - m);
             }
         }
-        block_lse(m, s, xn, red);
+        block_lse2(m, s, xn, red);
         if (tid == 0) { mypart[0] = m; mypart[1] = s; }
-        peval_grid_barrier(a, nbar);
+        { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- V3: global (max, S); w_j, guarded log-ratio, KL
         m = -DBL_MAX; s = 0.0; xn = 0.0;
         for (int q = tid; q < G; q += kPEvalThreads)
             lse_merge(m, s, __ldcg(a.part + (size_t)q * kPSlots), __ldcg(a.part + (size_t)q * kPSlots + 1));
-        block_lse(m, s, xn, red);
+        block_lse2(m, s, xn, red);
         if (tid == 0) {
             s_val[0] = m; s_val[1] = s;
             if (b == 0) { a.sc[SC_LSE_MAX] = m; a.sc[SC_LSE_SUM] = s; a.sc[SC_GMAX] = m; a.sc[SC_S] = s; }
@@ -397,40 +468,38 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
             block_sum<1>(v, red);
             if (tid == 0) mypart[3] = v[0];
         }
-        peval_grid_barrier(a, nbar);
+        { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- P4: row pass  avg = Y . w
         {
             PassArgs pa = a.row;
             pa.vN = a.w;
             peval_pass<kRowPass, false>(smem, &tmap, pa, prod, cons);
         }
-        peval_grid_barrier(a, nbar);
-        // ---- V5 (CTA 0): avg, r, chi^2, objective; ab = {r_i, 0}
-        if (b == 0) {
+        { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
+        // ---- V5 (every CTA, identical values; CTA 0 writes the scalars): avg, r, chi^2, objective; ab = {r_i, 0}
+        if (a.mode == kPEvalObjective && b != 0) return;
+        {
             double t[1] = {0.0};
             for (int q = tid; q < G; q += kPEvalThreads) t[0] += __ldcg(a.part + (size_t)q * kPSlots + 3);
             block_sum<1>(t, red);
             if (tid == 0) s_val[2] = t[0];
             __syncthreads();
             double c[1] = {0.0};
-            for (int i = tid; i < a.M; i += kPEvalThreads) {
-                const int ns = pass_num_slots(i / kTileR, a.row.nCB, a.row.chunk);
-                double sum = 0.0;
-                for (int q = 0; q < ns; ++q) sum += __ldcg(a.row.partial + (size_t)q * a.row.ld + i);
+            peval_row_sums(a.row, a.M, [&](int i, double sum) {
                 const double r = sum - a.Yobs[i];
                 a.avg[i] = sum;
                 reinterpret_cast<double2*>(a.ab)[i] = make_double2(r, 0.0);
                 c[0] = fma(r, r, c[0]);
-            }
+            });
             block_sum<1>(c, red);
-            if (tid == 0) {
+            if (tid == 0 && b == 0) {
                 const double chi2 = 0.5 * c[0], kl = s_val[2];
                 a.sc[SC_KL] = kl; a.sc[SC_CHI2] = chi2; a.sc[SC_PRIOR] = kl * a.theta;
                 a.sc[SC_F] = kl * a.theta + chi2;
             }
         }
         if (a.mode == kPEvalObjective) return;
-        peval_grid_barrier(a, nbar);
+        { peval_mark(a, mk); peval_cta_fence(); peval_mark(a, mk); }
     }
     // ---- P6: column pass  t_j = sum_i r_i y_ij
     {
@@ -438,7 +507,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
         pa.ab = a.ab;
         peval_pass<kColPass, false>(smem, &tmap, pa, prod, cons);
     }
-    peval_grid_barrier(a, nbar);
+    { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
     // ---- V7: E_j = (theta (1 + lr_j) + t_j) w_j
     if (vec) {
         for (int j = j0; j < a.N; j += jstride) {
@@ -448,7 +517,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
             a.aux_n[j] = ((1.0 + a.aux_n2[j]) * a.theta + t) * a.w[j];
         }
     }
-    peval_grid_barrier(a, nbar);
+    { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
     // ---- P8: row pass  grad_i = sum_j (y_ij - avg_i) E_j
     {
         PassArgs pa = a.row;
@@ -456,21 +525,19 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
         pa.vMb = a.avg;
         peval_pass<kRowPass, true>(smem, &tmap, pa, prod, cons);
     }
-    peval_grid_barrier(a, nbar);
+    { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
     // ---- V9 (CTA 0): gradient and its scalars
     if (b == 0) {
         double dg = 0.0, gn = 0.0, gi = 0.0;
-        for (int i = tid; i < a.M; i += kPEvalThreads) {
-            const int ns = pass_num_slots(i / kTileR, a.row.nCB, a.row.chunk);
-            double sum = 0.0;
-            for (int q = 0; q < ns; ++q) sum += __ldcg(a.row.partial + (size_t)q * a.row.ld + i);
+        peval_row_sums(a.row, a.M, [&](int i, double sum) {
             a.grad[i] = sum;
             if (a.ddir) dg = fma(sum, a.ddir[i], dg);
             gn = fma(sum, sum, gn);
             gi = fmax(gi, fabs(sum));
-        }
+        });
         block_sum2_max(dg, gn, gi, red);
         if (tid == 0) { a.sc[SC_DG] = dg; a.sc[SC_GNORM2] = gn; a.sc[SC_GINF] = gi; }
+        peval_mark(a, mk);
     }
 }
 

@@ -247,6 +247,7 @@ def test_cfg2_converged_optimum_against_the_reference_liblbfgs(cfg2):
     wr = ref.forces_weights(xr, cfg2["w0"], cfg2["yT"])
     assert np.max(np.abs(w - wr)) < 1e-6, ("forces weights", np.max(np.abs(w - wr)))
     assert rel(ref.forces_objective(x, cfg2["w0"], cfg2["yT"], cfg2["YT"], theta), fmin) < 1e-11
+    fmin_forces = fmin
     # ---- log-weights: 40 iterations, strict
     p.set_logw(cfg2["G"], cfg2["YT"], theta)
     x, fmin, code, info = p.opt_lbfgs(np.zeros(n), max_iterations=40)
@@ -269,7 +270,15 @@ def test_cfg2_converged_optimum_against_the_reference_liblbfgs(cfg2):
     noise_f, noise_w = rel(fr1, fr0), float(np.max(np.abs(w1_ - w0_)))
     print("cfg2 logw defaults: reference mode-to-mode noise f %.2e w %.2e; device vs reference f %.2e w %.2e"
           % (noise_f, noise_w, rel(fmin, fr0), np.max(np.abs(w - w0_))))
-    assert rel(fmin, fr0) <= max(1e-8, 3 * noise_f), ("logw fmin", fmin, fr0, fr1)
-    assert np.max(np.abs(w - w0_)) <= max(1e-6, 3 * noise_w), ("logw weights", np.max(np.abs(w - w0_)), noise_w)
+    # liblbfgs stops here on `delta`: (f[k-10] - f[k]) / f[k] < 1e-6 -- wherever a trajectory happens to satisfy that
+    # first, still ~2e-5 above the optimum (192.17358, which the forces method reaches).  End points of different
+    # trajectories therefore scatter by a few 1e-6 in f (measured: the reference's own modes 2.8e-7 ... 8.1e-7 apart,
+    # device vs reference 1e-7 ... 3.2e-6, depending on the evaluation path).  Bound: 10 x delta, and never tighter
+    # than 3 x the reference's own scatter in this run.
+    assert rel(fmin, fr0) <= max(1e-5, 3 * noise_f), ("logw fmin", fmin, fr0, fr1)
+    assert np.max(np.abs(w - w0_)) <= max(5e-4, 3 * noise_w), ("logw weights", np.max(np.abs(w - w0_)), noise_w)
+    # all three are equally close to the optimum that the well-conditioned forces problem pins down
+    for fv in (fmin, fr0, fr1):
+        assert 0.0 <= (fv - fmin_forces) / fmin_forces < 1e-4, (fv, fmin_forces)
     # whatever the trajectory, the objective the device reports at its end point is the reference's objective there
     assert rel(ref.logw_objective(x, cfg2["G"], cfg2["yT"], cfg2["YT"], theta), fmin) < 1e-11
