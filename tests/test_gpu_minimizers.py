@@ -39,15 +39,17 @@ def _bound(d, key):
 
 @pytest.mark.parametrize("name", LOGW_FIXTURES + FORCES_FIXTURES)
 @pytest.mark.parametrize("ls", [0, 1, 2, 3])
-def test_lbfgs_matches_reference_endpoint(name, ls):
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_lbfgs_matches_reference_endpoint(name, ls, persistent):
     import bioen_b200
     d = load_golden(name)
     key = "lbfgs%d" % ls
     with bioen_b200.Problem(d["yTilde"]) as p:
+        p.set_option(5, persistent)
         x0 = _setup(p, d)
         x, fmin, code, info = p.opt_lbfgs(x0, linesearch=ls)
         assert code == d[key + "_code"], (code, info)
-        assert rel(fmin, d[key + "_fmin"]) < _bound(d, key)
+        assert rel(fmin, d[key + "_fmin"]) < _bound(d, key), (rel(fmin, d[key + "_fmin"]), _bound(d, key))
         if code in (0, 1, 2):
             # fmin must be the objective at the returned point (test_find_opt_analytical_grad_logw.py:162-188);
             # after a failed line search liblbfgs returns the reverted x with the last trial's f (lbfgs.c:475-481)
@@ -60,20 +62,33 @@ def test_lbfgs_matches_reference_endpoint(name, ls):
                 assert np.max(np.abs(w - wr)) < W_TOL
 
 
+# End points that the stored mode-to-mode noise of the reference under-estimates.  Fletcher-Reeves on
+# data_potra_part_1 (808 x 80, ill-conditioned) passes BioEn's max|g| < 1e-3 stop test in two different places,
+# 8.3e-5 apart in f: the CPU oracle alone shows it (C evaluator 4042.786885 after 644 iterations, NumPy evaluator
+# 4043.121431 after 293, start point perturbed by 1e-15: 4043.121738 after 317, by 1e-14: GSL code 27).  The
+# reference's two OpenMP modes happen to land on the same side; the persistent kernel's rounding lands on the other.
+SENSITIVE_END_POINTS = {("conjugate_fr", "data_potra_part_1_logw_M808xN80"): 3e-4}
+
+
 @pytest.mark.parametrize("name", ["data_16x15", "data_deer_test_logw_M808xN10", "data_potra_part_2_logw_M205xN10",
                                   "data_potra_part_1_logw_M808xN80", "data_forces_M64xN64",
                                   "data_deer_test_forces_M808xN10"])
 @pytest.mark.parametrize("alg", GSL_ALGS)
-def test_gsl_matches_reference_endpoint(name, alg):
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_gsl_matches_reference_endpoint(name, alg, persistent):
+    """Both evaluation paths (stand-alone kernels / persistent kernel: different partial-sum cuts, i.e. different
+    rounding) against the reference's end point."""
     import bioen_b200
     from bioen_b200.optimize.ext import c_bioen
     d = load_golden(name)
     key = "gsl_" + alg
     with bioen_b200.Problem(d["yTilde"]) as p:
+        p.set_option(5, persistent)
         x0 = _setup(p, d)
         x, fmin, code, info = p.opt_gsl(x0, algorithm=c_bioen.get_gsl_method(alg))
         assert code == d[key + "_code"], (code, info)
-        assert rel(fmin, d[key + "_fmin"]) < _bound(d, key)
+        bound = max(_bound(d, key), SENSITIVE_END_POINTS.get((alg, name), 0.0))
+        assert rel(fmin, d[key + "_fmin"]) < bound, (rel(fmin, d[key + "_fmin"]), bound)
         assert rel(p.objective(x), fmin) < 5e-13
 
 
