@@ -85,6 +85,7 @@ SIGNATURES = {
     "bioen_b200_grad_continue": (C.c_int, [_vp, C.c_int, _dp]),
     "bioen_b200_weights": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "bioen_b200_average": (C.c_int, [_vp, _dp, _dp]),
+    "bioen_b200_affine_rows": (C.c_int, [_vp, _dp, _dp]),
     "bioen_b200_forces_from_weights": (C.c_int, [_vp, _dp, _dp, _dp]),
     "bioen_b200_opt_lbfgs": (C.c_int, [_vp, C.c_int, _dp, _dp, lbfgs_config_params, visual_params, _dp, _ip]),
     "bioen_b200_opt_gsl": (C.c_int, [_vp, C.c_int, _dp, _dp, gsl_config_params, visual_params, _dp, _ip]),

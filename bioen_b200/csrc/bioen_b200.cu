@@ -359,6 +359,30 @@ int bioen_b200_average(bioen_b200_ctx* ctx, const double* w_host, double* avg_ho
     });
 }
 
+int bioen_b200_affine_rows(bioen_b200_ctx* ctx, const double* scale_host, const double* offset_host) {
+    return guarded("bioen_b200_affine_rows", [&] {
+        NvtxRange nvtx("bioen:affine_rows");
+        ctx->pending_gen = -1;
+        Context& C = ctx->C;
+        CUDA_CHECK(cudaSetDevice(C.device));
+        if (!C.Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        if (!C.Yown.p) throw std::logic_error("bioen_b200: an adopted matrix belongs to the caller and is not modified");
+        ++C.eval_gen;
+        // scale -> avg, offset -> msum (M-vector scratch of the context; both are rewritten by every evaluation)
+        C.h2d(C.avg.p, scale_host, C.M);
+        C.h2d(C.msum.p, offset_host, C.M);
+        k_affine_rows<<<C.num_sms * 8, 256, 0, C.stream>>>(C.Y, C.ld, C.M, C.N, C.avg.p, C.msum.p);
+        CUDA_CHECK(cudaGetLastError());
+        ++C.kernels_launched;
+        // the structure-major copy (forces method, theta scan) belongs to the old matrix
+        const bool had_fused = C.fused_ready;
+        C.fused_ready = false;
+        C.yt_valid = false;
+        if (had_fused && C.have_forces && C.allow_fused) C.prepare_fused();
+        C.sync();
+    });
+}
+
 int bioen_b200_forces_from_weights(bioen_b200_ctx* ctx, const double* w_host, double* f, double* grad_host) {
     return guarded("bioen_b200_forces_from_weights", [&] {
         Context& C = ctx->C;

@@ -748,6 +748,27 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
 }
 
 // ------------------------------------------------------------------------------------------------
+// In-place row-affine transform of the resident matrix:  y_ij <- scale_i * y_ij + offset_i   (columns j < n only: the
+// padding stays zero).  This is how a nuisance-parameter refit (DEER modulation depth, scattering scale factor:
+// bioen/analyze/observables/observables.py:110-143 rebuilds the whole matrix in a Python double loop) is committed
+// to the matrix that lives in HBM: one read + one write pass, 2*M*N*8 bytes, HBM-bound.
+__global__ void __launch_bounds__(256) k_affine_rows(double* Y, long long ld, int m, int n, const double* scale,
+                                                     const double* offset) {
+    const long long npair = (n + 1) / 2, total = (long long)m * npair;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / npair);
+        const long long jp = t - (long long)i * npair;
+        const double s = scale[i], o = offset[i];
+        double2* p = reinterpret_cast<double2*>(Y + (size_t)i * ld) + jp;
+        double2 v = *p;
+        v.x = fma(s, v.x, o);
+        if (2 * jp + 1 < n) v.y = fma(s, v.y, o);
+        *p = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Plain read-only stream over the resident matrix: every thread sums 16-byte loads, nothing is written.  An upper
 // reference for what a read-only pass over yTilde can reach on this device (the copy figure in
 // MEASURED_PEAKS.json mixes reads and writes and is lower).

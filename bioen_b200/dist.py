@@ -142,6 +142,10 @@ class ShardedProblem:
         library, every rank gets the same M-vector."""
         return self.p.average(self._slice(w))
 
+    def affine_rows(self, scale, offset):
+        """Row-affine transform of every rank's column block (bioen_b200.nuisance commits refits with it)."""
+        self.p.affine_rows(scale, offset)
+
     def opt_lbfgs(self, x0, method=None, **cfg):
         if self._check(method):
             x, fmin, code, info = self.p.opt_lbfgs(self._slice(x0), **cfg)

@@ -244,6 +244,26 @@ class Problem:
         _lib.check(self._lib.bioen_b200_average(self._ctx, _lib.ptr(w), _lib.ptr(out)), "average")
         return out
 
+    def affine_rows(self, scale, offset):
+        """In-place on the device: yTilde_ij <- scale_i * yTilde_ij + offset_i (refitted nuisance parameters, see
+        bioen_b200.nuisance).  Evaluations and minimisers afterwards see the transformed matrix."""
+        scale, offset = _lib.vec(scale), _lib.vec(offset)
+        if scale.size != self.m or offset.size != self.m:
+            raise ValueError("scale and offset must have m entries")
+        _lib.check(self._lib.bioen_b200_affine_rows(self._ctx, _lib.ptr(scale), _lib.ptr(offset)), "affine_rows")
+
+    def chi2_residuals(self, w, scale=None, offset=None, YTilde=None):
+        """Residuals r_i = scale_i * (yTilde . w)_i + offset_i * sum(w) - YTilde_i of the resident matrix seen through
+        a row-affine transform (default: identity), with ONE row pass on the device; chi^2 = 0.5 * r.r.  A nuisance
+        parameter that acts affinely on the rows is scanned with this at O(M) cost per trial value."""
+        w = _lib.vec(w)
+        avg = self.average(w)
+        sw = float(w.sum())
+        scale = np.ones(self.m) if scale is None else _lib.vec(scale)
+        offset = np.zeros(self.m) if offset is None else _lib.vec(offset)
+        r = scale * avg + offset * sw
+        return r if YTilde is None else r - _lib.vec(YTilde)
+
     def forces_from_weights(self, w, gradient=True):
         """Reference semantics of _bioen_log_posterior_forces/_grad_...: objective (, gradient) for GIVEN w."""
         w = _lib.vec(w)

@@ -196,6 +196,13 @@ int bioen_b200_grad_continue(bioen_b200_ctx *ctx, int method, double *grad_host)
 int bioen_b200_weights(bioen_b200_ctx *ctx, int method, const double *x_host, double *w_host, double *sum);
 /* avg[m] = yTilde . w for host w[n] (post-processing with the resident matrix) */
 int bioen_b200_average(bioen_b200_ctx *ctx, const double *w_host, double *avg_host);
+/* in-place row-affine transform of the resident matrix: yTilde_ij <- scale[i] * yTilde_ij + offset[i] (host vectors of m
+ * entries).  Commits refitted nuisance parameters -- DEER modulation depth: (1 - m + m s_ij) / err_i, scattering scale:
+ * c s_ij / err_i, both affine in the rows -- to the matrix in HBM instead of rebuilding and re-uploading it
+ * (the reference rebuilds it on the host: bioen/analyze/observables/observables.py:110-143, 191-216).  One read and
+ * one write pass over the matrix.  A structure-major copy made for the forces method is rebuilt.  Not available for
+ * adopted matrices (caller-owned). */
+int bioen_b200_affine_rows(bioen_b200_ctx *ctx, const double *scale_host, const double *offset_host);
 /* objective / gradient of the forces method for GIVEN weights w[n] (reference semantics, part 1) */
 int bioen_b200_forces_from_weights(bioen_b200_ctx *ctx, const double *w_host, double *f, double *grad_host);
 
