@@ -290,6 +290,7 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
                 break;
             case BIOEN_B200_OPT_FUSED_EXCHANGE: ctx->C.fuse_allowed = value != 0; break;
             case BIOEN_B200_OPT_PERSISTENT: ctx->C.persistent_mode = value; break;
+            case BIOEN_B200_OPT_LBFGS_GRAM: ctx->C.lbfgs_gram_opt = value != 0; break;
             default: throw std::invalid_argument("bioen_b200: unknown option");
         }
     });
@@ -741,7 +742,7 @@ static void preload_kernels() {
     BIOEN_TOUCH(k_reduce_row_slots); BIOEN_TOUCH(k_finalize_rows); BIOEN_TOUCH(k_logw_grad);
     BIOEN_TOUCH(k_forces_weights); BIOEN_TOUCH(k_forces_lr_from_w); BIOEN_TOUCH(k_forces_E);
     BIOEN_TOUCH(k_forces_grad); BIOEN_TOUCH(k_forces_update); BIOEN_TOUCH(k_dot3); BIOEN_TOUCH(k_axpby);
-    BIOEN_TOUCH(k_lbfgs_pair); BIOEN_TOUCH(k_lbfgs_twoloop); BIOEN_TOUCH(k_fused_lse_merge);
+    BIOEN_TOUCH(k_lbfgs_pair); BIOEN_TOUCH(k_lbfgs_twoloop); BIOEN_TOUCH(k_lbfgs_gram_pair); BIOEN_TOUCH(k_lbfgs_combine); BIOEN_TOUCH(k_fused_lse_merge);
     BIOEN_TOUCH(k_fused_merge_rows); BIOEN_TOUCH(k_transpose); BIOEN_TOUCH(k_grid_max_abs);
     BIOEN_TOUCH((stream_pass_kernel<kRowPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kRowPass, true>));
     BIOEN_TOUCH((stream_pass_kernel<kColPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kColPass, true>));
@@ -773,6 +774,8 @@ int bioen_b200_comm_init_local(bioen_b200_ctx* ctx, int group, int rank, int nra
         {
             const size_t nmax = (size_t)std::max(C.N, C.M);
             C.lbfgs_store.reserve(((nmax + 15) & ~(size_t)15) * (4 + 2 * (size_t)LbfgsParams().m));
+            C.lbfgs_gram.reserve(kGramB * kGramB + kGramB + 3);
+            C.lbfgs_gram_partials.reserve((size_t)std::max(C.vec_blocks_n, C.vec_blocks_m) * kGramK + 8);
         }
         ctx->comm->enable_local(cap, ctx->C.device);
     });

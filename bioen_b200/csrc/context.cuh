@@ -124,6 +124,8 @@ class Context {
     // structure-major copy + geometry of the fused two-pass forces kernels (fused_pass.cuh)
     DevBuf<double> Yt, fpart, flse;
     DevBuf<double> lbfgs_store;   // g, xp, gp, d, s[m], y[m] of the device L-BFGS (lbfgs.cuh)
+    DevBuf<double> lbfgs_gram, lbfgs_gram_partials;   // coefficient-space update (BIOEN_B200_OPT_LBFGS_GRAM)
+    bool lbfgs_gram_opt = false;
     long long ldt = 0, f_nslab = 0, f_chunk = 0;
     int f_C = 0, f_stages = 0, f_grid = 0, f_KI = 0, f_smem = 0, f_T = 1, f_rows = 0, f_rows_per_cta = 1;
     bool f_team = false;
@@ -210,6 +212,7 @@ class Context {
                                                                      kPassSmemBytes));
             coop_ok = coop && (long long)per_sm * num_sms >= grid;
             if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
+            if (const char* e = getenv("BIOEN_B200_LBFGS_GRAM")) lbfgs_gram_opt = e[0] == '1';
             if (const char* e = getenv("BIOEN_B200_PERSISTENT_MAX_MB")) persistent_max_bytes = atof(e) * 1.0e6;
         }
     }
@@ -231,6 +234,7 @@ class Context {
         allow_fused = true;
         lazy_gradient = true;
         fuse_allowed = true;
+        lbfgs_gram_opt = getenv("BIOEN_B200_LBFGS_GRAM") != nullptr && getenv("BIOEN_B200_LBFGS_GRAM")[0] == '1';
         persistent_mode = -1;
         if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
         comm = nullptr;

@@ -326,6 +326,11 @@ class Lbfgs {
         for (int i = 0; i < m; ++i) { S[i] = d + np * (1 + i); Yv[i] = d + np * (1 + m + i); }
         std::vector<double> pf(prm.past > 0 ? prm.past : 0);
         const double* h = C.h_sc;
+        if (gram_mode()) {
+            C.lbfgs_gram.reserve(kGramB * kGramB + kGramB + 3);
+            C.lbfgs_gram_partials.reserve((size_t)vec_blocks * kGramK + 8);
+            CUDA_CHECK(cudaMemsetAsync(C.lbfgs_gram.p, 0, (kGramB * kGramB + kGramB) * sizeof(double), C.stream));
+        }
 
         // initial evaluation (lbfgs.c:412)
         eval(nullptr, nullptr, 0.0, nullptr);
@@ -497,7 +502,31 @@ class Lbfgs {
         }
         two_loop(bound, (end_old + 1) % m, m);
     }
+    // opt-in: the whole update as 2 kernels and 1 exchange (coefficient-space recursion, vector_kernels.cuh)
+    void enqueue_update_gram(int end_old, int bound) {
+        NvtxRange nvtx("bioen:lbfgs_update(gram)");
+        GramPairArgs a{};
+        a.n = n; a.x = x; a.g = g; a.xp = xp; a.gp = gp;
+        for (int t = 0; t < kGramM; ++t) { a.S[t] = S[t]; a.Y[t] = Yv[t]; }
+        a.end = end_old; a.bound = bound; a.gram = C.lbfgs_gram.p; a.partials = C.lbfgs_gram_partials.p;
+        a.ticket = C.ticket.p; a.sc = C.sc.p;
+        if (reduce && C.fuse_exchange()) a.p2p = C.p2p_dev(); else a.p2p.nranks = 1;
+        k_lbfgs_gram_pair<<<vec_blocks, kVecThreads, 0, C.stream>>>(a);
+        GramCombineArgs b{};
+        b.n = n; b.g = g; b.coef = C.lbfgs_gram.p + kGramB * kGramB; b.bound = bound; b.d = d;
+        for (int t = 0; t < kGramM; ++t) { b.S[t] = S[t]; b.Y[t] = Yv[t]; }
+        k_lbfgs_combine<<<vec_blocks, kVecThreads, 0, C.stream>>>(b);
+        C.kernels_launched += 2;
+    }
+    bool gram_mode() const {
+        // sharded runs need the in-kernel exchange (the peer-memory path); m is liblbfgs' default 6
+        return C.lbfgs_gram_opt && prm.m == kGramM && (!reduce || C.fuse_exchange());
+    }
     void update_direction(int end_old, int bound, int m) {
+        if (gram_mode()) {
+            enqueue_update_gram(end_old, bound);
+            return;
+        }
         if (use_graphs) {
             const int key = end_old * 64 + bound;
             auto it = g_update.find(key);

@@ -748,6 +748,145 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
 }
 
 // ------------------------------------------------------------------------------------------------
+// L-BFGS direction update in coefficient space (opt-in, BIOEN_B200_OPT_LBFGS_GRAM).
+//
+// liblbfgs' two-loop recursion (lbfgs.c:572-598) is a chain of 2*bound+1 dot products, each of which needs the vector
+// the previous one produced: 2*bound+2 kernels and -- sharded -- as many exchanges per iteration.  All vectors of the
+// recursion lie in the span of the 2*bound+1 basis vectors {s_i, y_i, g}, so the same recursion can run on the
+// (2*bound+1)-dimensional coefficient vector once the Gram matrix of the basis is known (Chen et al., "Large-scale
+// L-BFGS using MapReduce", NIPS 2014).  Only three basis vectors change per iteration (the new s, the new y and g):
+//   kernel 1  k_lbfgs_gram_pair   s = x - xp, y = g - gp (stored in the ring), xp <- x, gp <- g, and the 3 x 13 dot
+//                                 products of {s, y, g} with the whole basis in the SAME sweep; the finishing block
+//                                 sums them over the ranks (ONE exchange), updates the resident Gram matrix, runs the
+//                                 recursion on 13 coefficients and leaves them with g.d, y.s, y.y in device memory
+//   kernel 2  k_lbfgs_combine     d = sum_k c_k b_k
+// i.e. 2 kernels, 1 exchange and ~35 vector streams per iteration instead of 14 kernels, 13 exchanges and ~60.
+// The arithmetic is algebraically that of the two-loop recursion but rounds differently (dot products with the running
+// vector are replaced by combinations of Gram entries), so trajectories differ from the default path in the last bits
+// from the first iteration on: that is why it is an option and not the default.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGramM = 6;                       // history length this path supports (liblbfgs default, BioEn never changes it)
+constexpr int kGramB = 2 * kGramM + 1;          // basis: s[0..5], y[0..5], g
+constexpr int kGramK = 3 * kGramB;              // dot products per iteration
+
+struct GramPairArgs {
+    int n;
+    const double *x, *g;
+    double *xp, *gp;
+    double* S[kGramM];
+    double* Y[kGramM];
+    int end;            // ring slot receiving the new pair
+    int bound;          // pairs in the ring INCLUDING the new one
+    double* gram;       // [kGramB][kGramB] resident Gram matrix, then kGramB coefficients at gram + kGramB*kGramB
+    double* partials;   // gridDim.x * kGramK
+    unsigned int* ticket;
+    double* sc;
+    P2PDev p2p;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_lbfgs_gram_pair(const GramPairArgs a) {
+    __shared__ double red[kGramK * 32];
+    double v[kGramK];
+#pragma unroll
+    for (int k = 0; k < kGramK; ++k) v[k] = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        const double x = a.x[j], g = a.g[j];
+        const double s = x - a.xp[j], y = g - a.gp[j];
+        a.xp[j] = x;
+        a.gp[j] = g;
+#pragma unroll
+        for (int t = 0; t < kGramM; ++t) {
+            double sv = 0.0, yv = 0.0;
+            if (t == a.end) {
+                a.S[t][j] = s;
+                a.Y[t][j] = y;
+                sv = s;
+                yv = y;
+            } else if (t < a.bound) {        // slots fill up in order 0, 1, ...: valid slots are [0, bound)
+                sv = a.S[t][j];
+                yv = a.Y[t][j];
+            }
+            v[3 * t + 0] = fma(s, sv, v[3 * t + 0]);
+            v[3 * t + 1] = fma(y, sv, v[3 * t + 1]);
+            v[3 * t + 2] = fma(g, sv, v[3 * t + 2]);
+            v[3 * (kGramM + t) + 0] = fma(s, yv, v[3 * (kGramM + t) + 0]);
+            v[3 * (kGramM + t) + 1] = fma(y, yv, v[3 * (kGramM + t) + 1]);
+            v[3 * (kGramM + t) + 2] = fma(g, yv, v[3 * (kGramM + t) + 2]);
+        }
+        v[3 * (kGramB - 1) + 0] = fma(s, g, v[3 * (kGramB - 1) + 0]);
+        v[3 * (kGramB - 1) + 1] = fma(y, g, v[3 * (kGramB - 1) + 1]);
+        v[3 * (kGramB - 1) + 2] = fma(g, g, v[3 * (kGramB - 1) + 2]);
+    }
+    if (!grid_sum_last<kGramK>(v, a.partials, a.ticket, red)) return;
+    if (a.p2p.nranks > 1) p2p_sum_inline<kGramK>(a.p2p, v);
+    if (threadIdx.x != 0) return;
+    // ---- the finishing thread: Gram update + the recursion on the coefficients
+    double* Gm = a.gram;
+    const int is = a.end, iy = kGramM + a.end, ig = kGramB - 1;
+    for (int k = 0; k < kGramB; ++k) {
+        Gm[is * kGramB + k] = Gm[k * kGramB + is] = v[3 * k + 0];
+        Gm[iy * kGramB + k] = Gm[k * kGramB + iy] = v[3 * k + 1];
+        Gm[ig * kGramB + k] = Gm[k * kGramB + ig] = v[3 * k + 2];
+    }
+    double c[kGramB], alpha[kGramM];
+    for (int k = 0; k < kGramB; ++k) c[k] = 0.0;
+    c[ig] = -1.0;                                             // q = -g
+    auto dotq = [&](int row) {                                 // b_row . q
+        double s = 0.0;
+        for (int k = 0; k < kGramB; ++k) s = fma(c[k], Gm[row * kGramB + k], s);
+        return s;
+    };
+    int jslot = (a.end + 1) % kGramM;                          // liblbfgs: j = end (after its increment), then --j
+    for (int i = 0; i < a.bound; ++i) {
+        jslot = (jslot + kGramM - 1) % kGramM;                 // newest ... oldest
+        const double ys = Gm[jslot * kGramB + kGramM + jslot];
+        alpha[jslot] = dotq(jslot) / ys;
+        c[kGramM + jslot] -= alpha[jslot];
+    }
+    const double ys_new = Gm[is * kGramB + iy], yy_new = Gm[iy * kGramB + iy];
+    const double h0 = ys_new / yy_new;
+    for (int k = 0; k < kGramB; ++k) c[k] *= h0;
+    for (int i = 0; i < a.bound; ++i) {                        // oldest ... newest
+        const double ys = Gm[jslot * kGramB + kGramM + jslot];
+        const double beta = dotq(kGramM + jslot) / ys;
+        c[jslot] += alpha[jslot] - beta;
+        jslot = (jslot + 1) % kGramM;
+    }
+    for (int k = 0; k < kGramB; ++k) Gm[kGramB * kGramB + k] = c[k];
+    a.sc[SC_DGINIT] = dotq(ig);
+    a.sc[SC_YS] = ys_new;
+    a.sc[SC_YY] = yy_new;
+    a.sc[SC_YS0 + a.end] = ys_new;
+}
+
+struct GramCombineArgs {
+    int n;
+    const double* S[kGramM];
+    const double* Y[kGramM];
+    const double* g;
+    const double* coef;   // kGramB coefficients (device)
+    int bound;
+    double* d;
+};
+
+__global__ void __launch_bounds__(kVecThreads) k_lbfgs_combine(const GramCombineArgs a) {
+    __shared__ double c[kGramB];
+    if (threadIdx.x < kGramB) c[threadIdx.x] = a.coef[threadIdx.x];
+    __syncthreads();
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += gridDim.x * blockDim.x) {
+        double dj = c[kGramB - 1] * a.g[j];
+#pragma unroll
+        for (int t = 0; t < kGramM; ++t) {
+            if (t < a.bound) {
+                dj = fma(c[t], a.S[t][j], dj);
+                dj = fma(c[kGramM + t], a.Y[t][j], dj);
+            }
+        }
+        a.d[j] = dj;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // In-place row-affine transform of the resident matrix:  y_ij <- scale_i * y_ij + offset_i   (columns j < n only: the
 // padding stays zero).  This is how a nuisance-parameter refit (DEER modulation depth, scattering scale factor:
 // bioen/analyze/observables/observables.py:110-143 rebuilds the whole matrix in a Python double loop) is committed

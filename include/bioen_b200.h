@@ -180,9 +180,12 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * with the row sums: one exchange per objective half).  0 restores the three separate exchanges per evaluation.
  * BIOEN_B200_OPT_PERSISTENT (default -1 = by size; 0 off; 1 on): run an evaluation as ONE persistent cooperative
  * kernel (grid barriers between its phases, yTilde kept in L2 when it fits) instead of 6-11 kernel launches; auto
- * selects it for matrices up to 2 GB per GPU (environment: BIOEN_B200_PERSISTENT, BIOEN_B200_PERSISTENT_MAX_MB). */
+ * selects it for matrices up to 2 GB per GPU (environment: BIOEN_B200_PERSISTENT, BIOEN_B200_PERSISTENT_MAX_MB).
+ * BIOEN_B200_OPT_LBFGS_GRAM (default 0; environment BIOEN_B200_LBFGS_GRAM=1): the L-BFGS direction update runs in
+ * coefficient space -- 2 kernels and 1 exchange per iteration instead of 14 and 13.  Algebraically the two-loop
+ * recursion of liblbfgs, but it rounds differently, so trajectories differ from the default path in the last bits. */
 enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
-       BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5 };
+       BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5, BIOEN_B200_OPT_LBFGS_GRAM = 6 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of

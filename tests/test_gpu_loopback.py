@@ -85,6 +85,12 @@ def test_sharded_lbfgs_on_one_gpu(oracle, world):
         grp.call(lambda r, p, lo, hi: p.set_option(4, 1))
         res2 = grp.call(lambda r, p, lo, hi: p.opt_lbfgs(P["GInit"].ravel()[lo:hi], max_iterations=30))
         assert res3[0][2] == res2[0][2] and rel(res3[0][1], res2[0][1]) < 1e-9
+        # coefficient-space direction update (opt-in): one exchange of 39 doubles per iteration instead of 13 exchanges
+        grp.call(lambda r, p, lo, hi: p.set_option(6, 1))
+        resg = grp.call(lambda r, p, lo, hi: p.opt_lbfgs(P["GInit"].ravel()[lo:hi], max_iterations=30))
+        grp.call(lambda r, p, lo, hi: p.set_option(6, 0))
+        assert resg[0][2] == res2[0][2] and rel(resg[0][1], res2[0][1]) < 1e-9
+        assert all(o[1] == resg[0][1] for o in resg)
         # forces
         grp.call(lambda r, p, lo, hi: p.set_forces(P["w0"].ravel()[lo:hi], P["YTilde"], theta))
         res = grp.call(lambda r, p, lo, hi: p.opt_lbfgs(P["forces_init"].ravel()))
