@@ -380,6 +380,23 @@ def timed_evals(prob, method, nvar, dev, warmup, steps, seed_shift=0, world=1):
     return ms, pass_ms, int(launches)
 
 
+def gram_optimum(prob, nvar, barrier=None):
+    """the same minimisation with the opt-in coefficient-space L-BFGS update (2 kernels, 1 exchange per iteration)"""
+    prob.set_option(6, 1)
+    try:
+        if barrier:
+            barrier()
+        t0 = time.perf_counter()
+        xo, fmin, code, info = prob.opt_lbfgs(np.zeros(nvar))
+        if barrier:
+            barrier()
+        return {"seconds": time.perf_counter() - t0, "code": code, "fmin": fmin, "iterations": info["iterations"],
+                "evaluations": info["evaluations"], "option": "BIOEN_B200_OPT_LBFGS_GRAM=1 (rounds differently from the "
+                                                              "default two-loop recursion)"}
+    finally:
+        prob.set_option(6, 0)
+
+
 def small_workload(name, M, N, local, dev, steps, warmup):
     """One BASELINE config that is not the headline: logw and forces f+g rates, roofline of the pass kernel and
     the device L-BFGS to the optimum, on a freshly generated synthetic problem (single GPU)."""
@@ -402,7 +419,8 @@ def small_workload(name, M, N, local, dev, steps, warmup):
             rec = {"value": steps / (ms * 1e-3), "unit": "f+g evals/s", "ms_per_step": ms / steps, "gpu_launches": launches,
                    "roofline": roofline_hbm(M, N, pass_ms, ms / steps, prob.pass_kernel_name(method)),
                    "time_to_optimum": {"seconds": secs, "code": code, "fmin": fmin, "iterations": info["iterations"],
-                                       "evaluations": info["evaluations"]}}
+                                       "evaluations": info["evaluations"]},
+                   "time_to_optimum_coefficient_space": gram_optimum(prob, nvar)}
             if M * N * 8 <= 100e6:
                 rec["roofline"]["note"] = ("yTilde (%.1f MB) is L2-resident: the second pass of a step is served from "
                                            "L2, the HBM figure is nominal" % (M * N * 8 / 1e6))
@@ -522,6 +540,7 @@ def run_b200(args):
                    "objective_only_evaluations": info["gradients_skipped"],
                    "minimizer": "device L-BFGS (liblbfgs semantics, BioEn defaults: linesearch=2, past=10, "
                                 "delta=1e-6, epsilon=1e-6)", "includes": "x0 H2D + result D2H; yTilde resident"}
+        optimum["coefficient_space_update"] = gram_optimum(prob, nvar, barrier)
         try:   # the reference arm of the same run (it runs first) left its optimum of the same problem here
             with open(T2O_FILE) as fh:
                 r = json.load(fh)
@@ -569,6 +588,14 @@ def run_b200(args):
             res = optimize.log_weights.find_optimum(GI, GI, y_host, yT_host, YT.reshape(1, -1), THETA, cfg)
             dropin["find_optimum_s"] = time.perf_counter() - t0
             dropin["find_optimum_fmin"] = float(res[4])
+            if available_ram() > 1.3 * M * N * 8:
+                y_host = 0.5 * yT_host               # a DIFFERENT m x n array (y = sigma * yTilde in BioEn's callers)
+                t0 = time.perf_counter()
+                res = optimize.log_weights.find_optimum(GI, GI, y_host, yT_host, YT.reshape(1, -1), THETA, cfg)
+                dropin["find_optimum_distinct_y_s"] = time.perf_counter() - t0
+                dropin["find_optimum_distinct_y_note"] = ("y.wopt is streamed through a 1 GB device buffer in row "
+                                                          "chunks: no second resident matrix")
+                del y_host
         del yT_host
 
     kernel = "stream_pass_kernel" if method == LOGW or args.unfused_forces else "fused_team_pass"
@@ -734,6 +761,11 @@ def sharded_record(name, M, n_arg, strong, rank, world, local, dev, steps, warmu
                 dist.barrier()
                 rec["time_to_optimum"] = {"seconds": time.perf_counter() - t0, "code": code, "fmin": fmin,
                                           "iterations": info["iterations"], "evaluations": info["evaluations"]}
+
+                def _bar():
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                rec["time_to_optimum_coefficient_space"] = gram_optimum(prob, nvar, _bar)
             out[mname] = rec
     finally:
         prob.close()

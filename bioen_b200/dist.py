@@ -182,6 +182,10 @@ class ShardedProblem:
         return self.p.theta_scan(thetas, x0=x0, method=FORCES, **cfg)
 
     def close(self):
+        cached = getattr(self, "_y_cache", None)
+        if cached is not None:
+            self._y_cache = None
+            cached[1].close()
         self.p.close()
 
 

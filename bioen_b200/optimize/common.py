@@ -28,8 +28,23 @@ def device_average(w, y, problem=None):
         return p.average(w)
 
 
-def average_like(problem, w, y):
-    """y.w on the device(s) `problem` lives on (a Problem, or a dist.ShardedProblem over all GPUs of the job)."""
+def average_like(problem, w, y, keep=False):
+    """y.w on the device(s) `problem` lives on (a Problem, or a dist.ShardedProblem over all GPUs of the job), for a
+    host matrix y that is not the resident yTilde (the reference's post-processing, log_weights.py:612-613).
+
+    keep=False (a one-off find_optimum): y is STREAMED through a small device buffer in row chunks
+    (Problem.average_streamed) -- no second resident M x N matrix.  keep=True (the caller owns `problem` and will
+    call again, e.g. a theta series): a resident problem for y is made once and cached on `problem` until it is
+    closed or a different y arrives."""
+    if keep:
+        cached = getattr(problem, "_y_cache", None)
+        if cached is None or cached[0] is not y:
+            if cached is not None:
+                cached[1].close()
+            problem._y_cache = (y, problem.like(y))
+        return problem._y_cache[1].average(w)
+    if hasattr(problem, "average_streamed"):
+        return problem.average_streamed(y, w)
     with problem.like(y) as q:
         return q.average(w)
 

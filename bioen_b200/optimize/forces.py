@@ -138,7 +138,7 @@ def find_optimum(forcesInit, w0, y, yTilde, YTilde, theta, cfg, problem=None):
         w, _ = problem.weights(forces_opt, FORCES)
         wopt = w.reshape(-1, 1)
         yavg = problem.average(w)
-        yopt = yavg if y is yTilde else common.average_like(problem, w, y)
+        yopt = yavg if y is yTilde else common.average_like(problem, w, y, keep=not own)
         # S and chi^2 at the optimum (forces.py:546): KL over w_j > 0, chi^2 from the resident yTilde
         ind = w > 0
         S = float(np.log(w[ind] / _lib.vec(w0)[ind]) @ w[ind])

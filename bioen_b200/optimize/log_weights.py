@@ -210,7 +210,7 @@ def find_optimum(GInit, G, y, yTilde, YTilde, theta, cfg, problem=None):
             print("time elapsed ", time.time() - start)
         w, _ = problem.weights(gopt, LOGW)
         wopt = w.reshape(-1, 1)
-        yopt = problem.average(w) if y is yTilde else common.average_like(problem, w, y)
+        yopt = problem.average(w) if y is yTilde else common.average_like(problem, w, y, keep=not own)
     finally:
         if own:
             problem.close()

@@ -92,6 +92,10 @@ class Problem:
         return self._h
 
     def close(self):
+        cached = getattr(self, "_y_cache", None)
+        if cached is not None:
+            self._y_cache = None
+            cached[1].close()
         if getattr(self, "_h", None):
             self._lib.bioen_b200_destroy(self._h)
             self._h = None
@@ -263,6 +267,29 @@ class Problem:
         offset = np.zeros(self.m) if offset is None else _lib.vec(offset)
         r = scale * avg + offset * sw
         return r if YTilde is None else r - _lib.vec(YTilde)
+
+    def average_streamed(self, y, w, chunk_bytes=1 << 30):
+        """y . w for a HOST matrix y (m' x n) that is needed once (the post-processing yopt = y . wopt of find_optimum,
+        bioen/optimize/log_weights.py:612-613): y is streamed through a device buffer of `chunk_bytes` in row chunks
+        and each chunk is reduced by the row-pass kernel, so no second resident copy of an M x N matrix is allocated
+        (8 GB at config 3) and a y larger than the free HBM works too."""
+        yv = _lib.mat(y)
+        w = _lib.vec(w)
+        if yv.ndim != 2 or yv.shape[1] != self.n or w.size != self.n:
+            raise ValueError("y must be (m', n) and w (n,)")
+        mp = yv.shape[0]
+        rows = max(1, min(mp, int(chunk_bytes) // (8 * self.n)))
+        out = np.empty(mp, dtype=np.float64)
+        with Problem(shape=(rows, self.n), device=self.device) as q:
+            for r0 in range(0, mp, rows):
+                blk = yv[r0:r0 + rows]
+                if blk.shape[0] < rows:                      # ragged tail: pad to the buffer's shape
+                    pad = np.zeros((rows, self.n))
+                    pad[:blk.shape[0]] = blk
+                    blk = pad
+                _lib.check(self._lib.bioen_b200_upload_ytilde(q._ctx, _lib.ptr(blk), self.n), "upload_ytilde")
+                out[r0:r0 + rows] = q.average(w)[:min(rows, mp - r0)]
+        return out
 
     def forces_from_weights(self, w, gradient=True):
         """Reference semantics of _bioen_log_posterior_forces/_grad_...: objective (, gradient) for GIVEN w."""
