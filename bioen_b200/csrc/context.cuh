@@ -219,6 +219,7 @@ class Context {
 
     ~Context() {
         if (h_sc) cudaFreeHost(h_sc);
+        release_upload_lanes();
         for (cudaEvent_t e : pass_ev) cudaEventDestroy(e);
         if (fetch_ev) cudaEventDestroy(fetch_ev);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -280,6 +281,26 @@ class Context {
     // (~10 GB/s).  Here kUpThreads host threads copy row chunks into their own pinned double buffers and push them
     // with async copies on their own streams, so the host memcpy and the PCIe transfer overlap and scale.
     static constexpr int kUpThreads = 6;
+    // page-locked staging of the upload threads: allocated on first use and kept with the context (cudaHostAlloc of
+    // 12 x 32 MB costs more than copying 1 GB; a caller that streams a large host matrix through this context chunk
+    // by chunk -- Problem.average_streamed -- would otherwise pay it per chunk)
+    struct UploadLane {
+        char* stage[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        size_t bytes = 0;
+    };
+    std::vector<UploadLane> up_lanes;
+    void release_upload_lanes() {
+        for (auto& l : up_lanes) {
+            for (int b = 0; b < 2; ++b) {
+                if (l.stage[b]) cudaFreeHost(l.stage[b]);
+                if (l.done[b]) cudaEventDestroy(l.done[b]);
+            }
+            if (l.st) cudaStreamDestroy(l.st);
+        }
+        up_lanes.clear();
+    }
     void upload_staged(const double* host, size_t ld_host) {
         const size_t row_bytes = (size_t)N * sizeof(double);
         const size_t buf_bytes = std::max(row_bytes, (size_t)32 << 20);
@@ -288,33 +309,37 @@ class Context {
         int want = kUpThreads;
         if (const char* e = getenv("BIOEN_B200_UPLOAD_THREADS")) want = std::max(1, atoi(e));
         const int nthreads = std::min(want, nchunks);
+        const size_t lane_bytes = (size_t)rows_per_chunk * row_bytes;
+        if ((int)up_lanes.size() < nthreads || (!up_lanes.empty() && up_lanes[0].bytes < lane_bytes)) {
+            release_upload_lanes();
+            up_lanes.resize(nthreads);
+            for (auto& l : up_lanes) {
+                CUDA_CHECK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+                for (int b = 0; b < 2; ++b) {
+                    CUDA_CHECK(cudaHostAlloc((void**)&l.stage[b], lane_bytes, cudaHostAllocDefault));
+                    CUDA_CHECK(cudaEventCreateWithFlags(&l.done[b], cudaEventDisableTiming));
+                }
+                l.bytes = lane_bytes;
+            }
+        }
         std::vector<std::thread> pool;
         std::vector<std::string> errors(nthreads);
         for (int t = 0; t < nthreads; ++t) {
             pool.emplace_back([&, t] {
                 try {
                     CUDA_CHECK(cudaSetDevice(device));
-                    cudaStream_t st;
-                    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-                    char* stage[2] = {nullptr, nullptr};
-                    cudaEvent_t done[2];
-                    for (int b = 0; b < 2; ++b) {
-                        CUDA_CHECK(cudaHostAlloc((void**)&stage[b], (size_t)rows_per_chunk * row_bytes, cudaHostAllocDefault));
-                        CUDA_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-                    }
+                    UploadLane& l = up_lanes[t];
                     int use = 0;
                     for (int c = t; c < nchunks; c += nthreads, use ^= 1) {
                         const int r0 = c * rows_per_chunk, nr = std::min(rows_per_chunk, M - r0);
-                        CUDA_CHECK(cudaEventSynchronize(done[use]));   // the previous copy out of this buffer
+                        CUDA_CHECK(cudaEventSynchronize(l.done[use]));   // the previous copy out of this buffer
                         for (int r = 0; r < nr; ++r)
-                            memcpy(stage[use] + (size_t)r * row_bytes, host + (size_t)(r0 + r) * ld_host, row_bytes);
-                        CUDA_CHECK(cudaMemcpy2DAsync(Y + (size_t)r0 * ld, ld * sizeof(double), stage[use], row_bytes,
-                                                     row_bytes, nr, cudaMemcpyHostToDevice, st));
-                        CUDA_CHECK(cudaEventRecord(done[use], st));
+                            memcpy(l.stage[use] + (size_t)r * row_bytes, host + (size_t)(r0 + r) * ld_host, row_bytes);
+                        CUDA_CHECK(cudaMemcpy2DAsync(Y + (size_t)r0 * ld, ld * sizeof(double), l.stage[use], row_bytes,
+                                                     row_bytes, nr, cudaMemcpyHostToDevice, l.st));
+                        CUDA_CHECK(cudaEventRecord(l.done[use], l.st));
                     }
-                    CUDA_CHECK(cudaStreamSynchronize(st));
-                    for (int b = 0; b < 2; ++b) { cudaFreeHost(stage[b]); cudaEventDestroy(done[b]); }
-                    cudaStreamDestroy(st);
+                    CUDA_CHECK(cudaStreamSynchronize(l.st));
                 } catch (const std::exception& e) {
                     errors[t] = e.what();
                 }
