@@ -90,7 +90,7 @@ def profiled_traffic(method, M, N):
     capture of this same workload (profiles/), or None when the workload differs from the profiled one."""
     if (M, N) != (1000, 1000000):
         return None
-    name = "r1_ncu_full_stream_pass.csv" if method == "logw" else "r1_ncu_full_fused_team_pass.csv"
+    name = "r2_ncu_full_stream_pass.csv" if method == "logw" else "r1_ncu_full_fused_team_pass.csv"
     try:
         import csv
         with open(os.path.join(ROOT, "profiles", name)) as fh:
