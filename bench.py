@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: --structures is the TOTAL N, split over the GPUs (default: weak, N per GPU)")
     ap.add_argument("--no-optimum", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads records (other BASELINE configs)")
     ap.add_argument("--no-find-optimum", action="store_true", help="skip the public-API find_optimum timing")
     ap.add_argument("--no-dropin", action="store_true", help="skip the host-matrix drop-in call (needs M*N*8 B of host RAM)")
@@ -446,6 +447,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    numa_cpus = None
+    if world > 1 and not args.no_numa:
+        from bioen_b200.dist import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local)      # before the pinned host vectors of the e2e leg are allocated
 
     M = args.m
     if args.strong:
@@ -607,7 +612,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfgd,
         "run_info": {"n_local": N, "global_evals_per_s": args.steps / (ms * 1e-3), "generate_s": gen_s,
-                     "exchange": prob.comm_mode(), "exchanges_per_evaluation": prob.exchanges_per_eval(method)},
+                     "exchange": prob.comm_mode(), "exchanges_per_evaluation": prob.exchanges_per_eval(method),
+                     "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
         "roofline": roofline_hbm(M, N, pass_ms, ms / args.steps, kernel, profiled_traffic(args.method, M, N),
                                  read_gbs.value),
         "e2e": {"value": e2e_value, "unit": unit(args), "h2d_bytes_per_step": nvar * 8, "d2h_bytes_per_step": nvar * 8 + 512,

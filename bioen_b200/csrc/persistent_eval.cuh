@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
                         a.msum[a.M + 3] = Mx; a.msum[a.M + 4] = S;
                     }
                     int fail;
+                    peval_mark(a, mk);
                     const double* in = p2p_deliver_and_wait(a.p2p, a.msum, a.M + 5, &fail);
+                    peval_mark(a, mk);
                     const long long cap = a.p2p.cap;
                     const int R = a.p2p.nranks;
                     if (tid == 0) {
