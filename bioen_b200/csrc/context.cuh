@@ -162,16 +162,17 @@ class Context {
             long long s = (L - 1) / chunk + 2;
             return (int)(s < grid ? s : grid);
         };
-        // tile order of the matrix passes (stream_pass.cuh, TileWalk).  The interleaved order makes the whole chip
-        // read one compact window of the matrix; a TMA-free probe gains 2-3 % from it (scripts/read_order_probe.py),
-        // the TMA passes 0.6 % per pass and nothing per step (437.5 vs 438.5 evals/s), so it is opt-in:
-        // BIOEN_B200_PASS_ORDER=interleave (both passes), =irow or =icol (one of them); needs every CTA to get tiles
-        // of every row tile: nCB >= 4 * grid
+        // tile order of the matrix passes (stream_pass.cuh, TileWalk).  Interleaved = the whole chip reads one compact
+        // window of the matrix at a time.  Measured at N = 1e6 x M = 1e3, 40 steps each, one box, back to back
+        // (round 2): contiguous 431.6 evals/s (2.3171 ms), column pass interleaved 435.4 (2.2970 ms), row pass
+        // interleaved 426.7 (2.3434 ms: 148 partial-sum slots per row tile), both 430.2.  So the COLUMN pass deals its
+        // runs round-robin by default (needs nCB >= 4 * grid), the row pass keeps contiguous chunks.
+        // BIOEN_B200_PASS_ORDER = contiguous | icol | irow | interleave overrides.
         {
             const char* e = getenv("BIOEN_B200_PASS_ORDER");
-            const bool ok = nCB >= 4LL * grid && e && e[0] == 'i';
-            interleave_row = ok && (e[1] == 'n' || e[1] == 'r');
-            interleave_col = ok && (e[1] == 'n' || e[1] == 'c');
+            const bool ok = nCB >= 4LL * grid;
+            interleave_row = ok && e && e[0] == 'i' && (e[1] == 'n' || e[1] == 'r');
+            interleave_col = ok && (!e || (e[0] == 'i' && (e[1] == 'n' || e[1] == 'c')));
         }
         slotsA = interleave_row ? grid : slots(nCB);
         slotsB = slots(nRT);
@@ -745,8 +746,8 @@ class Context {
             if (!pe_trace.p) pe_trace.alloc(64);
             a.trace = pe_trace.p;
         }
-        // the readers of the pass partials inside the kernel use the contiguous tile order
-        if (interleave_row || interleave_col) throw std::logic_error("bioen_b200: persistent kernel needs the contiguous pass order");
+        // (the kernel's own passes and their readers always use the contiguous tile order, whatever the stand-alone
+        // kernels of this context are configured for)
         const int npass = method == 0 ? (mode == kPEvalBoth ? 2 : 1) : (mode == kPEvalBoth ? 4 : 2);
         const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
