@@ -666,6 +666,18 @@ def run_b200(args):
         if not args.strong:
             extra.append(theta_scan_record(prob, LOGW, 32, M, N, n_total, YT, rank, world, local, dev,
                                            min(args.steps, 10), ew, not args.no_optimum))
+        # (b') opt-in fp32 STORAGE of the same matrix (not parity-preserving, never the default): half the bytes
+        if not args.strong:
+            prob.set_option(7, 1)
+            prob.set_logw(np.zeros(N), YT, THETA)
+            fms, fpass, flaunch = timed_evals(prob, LOGW, N, dev, ew, es, seed_shift=rank, world=world)
+            r32 = roofline_hbm(M, N, fpass, fms / es, prob.pass_kernel_name(LOGW))
+            for k in ("achieved", "frac", "bytes_per_launch", "step_frac"):
+                r32[k] = r32[k] / 2.0          # 4-byte entries: M*N*4 algorithmic bytes per pass
+            extra.append({"name": "config 3, logw with OPT-IN fp32 storage of yTilde (fp64 arithmetic; results differ "
+                                  "from the reference at the 1e-8 level -- not a parity path)",
+                          "value": units * es / (fms * 1e-3), "unit": "f+g evals/s (N-column blocks, summed over GPUs)",
+                          "ms_per_step": fms / es, "gpu_launches": flaunch, "roofline": r32})
         prob.close()
         # (c) configs 2 and 1 (ala5 shape): small, L2-resident problems, single GPU each (rank 0 reports)
         if world == 1:

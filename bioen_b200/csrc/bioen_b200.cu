@@ -291,6 +291,13 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
             case BIOEN_B200_OPT_FUSED_EXCHANGE: ctx->C.fuse_allowed = value != 0; break;
             case BIOEN_B200_OPT_PERSISTENT: ctx->C.persistent_mode = value; break;
             case BIOEN_B200_OPT_LBFGS_GRAM: ctx->C.lbfgs_gram_opt = value != 0; break;
+            case BIOEN_B200_OPT_FP32_STORAGE:
+                CUDA_CHECK(cudaSetDevice(ctx->C.device));
+                ctx->pending_gen = -1;
+                if (value) ctx->C.convert_to_fp32();
+                else if (ctx->C.storage_fp32)
+                    throw std::invalid_argument("bioen_b200: the fp64 matrix was released; upload yTilde again");
+                break;
             default: throw std::invalid_argument("bioen_b200: unknown option");
         }
     });
@@ -366,6 +373,7 @@ int bioen_b200_affine_rows(bioen_b200_ctx* ctx, const double* scale_host, const 
         ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
+        if (C.storage_fp32) throw std::logic_error("bioen_b200: row-affine transforms need the fp64 matrix (fp32 storage is on)");
         if (!C.Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         if (!C.Yown.p) throw std::logic_error("bioen_b200: an adopted matrix belongs to the caller and is not modified");
         ++C.eval_gen;
@@ -737,7 +745,7 @@ int bioen_b200_comm_init(bioen_b200_ctx* ctx, const char id[128], int rank, int 
 static void preload_kernels() {
     cudaFuncAttributes at;
 #define BIOEN_TOUCH(K) CUDA_CHECK(cudaFuncGetAttributes(&at, K))
-    BIOEN_TOUCH(k_p2p_exchange); BIOEN_TOUCH(persistent_eval_kernel);
+    BIOEN_TOUCH(k_p2p_exchange); BIOEN_TOUCH(persistent_eval_kernel<double>);
     BIOEN_TOUCH(k_update_lse); BIOEN_TOUCH(k_logw_weights); BIOEN_TOUCH(k_logw_rows_exchange_finalize);
     BIOEN_TOUCH(k_reduce_row_slots); BIOEN_TOUCH(k_finalize_rows); BIOEN_TOUCH(k_logw_grad);
     BIOEN_TOUCH(k_forces_weights); BIOEN_TOUCH(k_forces_lr_from_w); BIOEN_TOUCH(k_forces_E);
@@ -867,6 +875,7 @@ int bioen_b200_download_ytilde(bioen_b200_ctx* ctx, int row0, int nrows, long lo
     return guarded("bioen_b200_download_ytilde", [&] {
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
+        if (C.storage_fp32) throw std::logic_error("bioen_b200: the resident matrix is stored in fp32 (no fp64 copy to download)");
         if (!C.Y) throw std::logic_error("bioen_b200: no matrix");
         if (row0 < 0 || nrows < 0 || row0 + nrows > C.M || col0 < 0 || ncols < 0 || col0 + ncols > C.N)
             throw std::invalid_argument("bioen_b200: block out of range");
@@ -888,7 +897,7 @@ long long bioen_b200_query(bioen_b200_ctx* ctx, int what) {
         case 1: return C.nranks > 1 ? C.exchanges_per_eval(false) : 0;
         case 2: return C.nranks > 1 ? C.exchanges_per_eval(true) : 0;
         case 3: return C.persistent_for(what == 3 && C.have_forces) ? 1 : 0;
-        case 4: return 8;
+        case 4: return C.storage_fp32 ? 4 : 8;
         case 5: return C.persistent_launches;
         default: return -1;
     }

@@ -106,6 +106,13 @@ class Context {
     double* Y = nullptr;
     DevBuf<double> Yown;
     CUtensorMap tmap;
+    // opt-in fp32 STORAGE of the matrix (BIOEN_B200_OPT_FP32_STORAGE): the fp64 copy is released, the tile kernels
+    // read 4-byte entries (half the roofline bytes) and keep every product and sum in fp64
+    DevBuf<float> Y32;
+    long long ld32 = 0;
+    bool storage_fp32 = false;
+    bool has_matrix() const { return Y != nullptr || storage_fp32; }
+    double matrix_bytes() const { return storage_fp32 ? (double)M * ld32 * 4.0 : (double)M * (double)ld * 8.0; }
 
     DevBuf<double> partialA, partialB, ab, avg, msum, Yobs, w, aux_n, aux_n2, Gv, sc, red_partials, lse_all;
     DevBuf<unsigned int> ticket;
@@ -202,15 +209,25 @@ class Context {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
         CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytes));
-        CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kRowPass, false, float>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytesF32));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kRowPass, true, float>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytesF32));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, false, float>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytesF32));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, true, float>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytesF32));
+        CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kPassSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kPassSmemBytesF32));
         pe_part.alloc((size_t)grid * kPSlots + 16);
         pe_bar.alloc(32);   // [0] arrival counter, [16] released barrier number (separate 128-byte lines)
         {
             int coop = 0, per_sm = 0;
             CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_eval_kernel, kPEvalThreads,
-                                                                     kPassSmemBytes));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_eval_kernel<float>,
+                                                                     kPEvalThreads, kPassSmemBytesF32));
             coop_ok = coop && (long long)per_sm * num_sms >= grid;
             if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
             if (const char* e = getenv("BIOEN_B200_LBFGS_GRAM")) lbfgs_gram_opt = e[0] == '1';
@@ -243,6 +260,8 @@ class Context {
         nranks = 1;
         N_total = N;
         Y = nullptr;
+        storage_fp32 = false;
+        Y32.release();
         passes_launched = kernels_launched = 0;
         pass_timing = false;
     }
@@ -385,8 +404,40 @@ class Context {
         }
         fused_ready = false;   // the structure-major copy (if any) belongs to the previous matrix
         yt_valid = false;
+        storage_fp32 = false;  // a new fp64 matrix has arrived
+        Y32.release();
         // a matrix that fits in L2 with room to spare is kept there between the two passes
         evict_first = ((double)M * (double)ld * 8.0 > 80.0e6) ? 1 : 0;
+    }
+
+    // Replace the resident fp64 matrix by an fp32 copy (irreversible for this matrix).  The fused forces kernels
+    // and the theta scan read the structure-major fp64 copy and are not available afterwards: the forces method runs
+    // on the four tile passes (the same bytes as two fp64 passes).
+    void convert_to_fp32() {
+        if (storage_fp32) return;
+        if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        ++eval_gen;
+        ld32 = round_up(N, 32);
+        Y32.alloc((size_t)M * ld32);
+        k_convert_f32<<<num_sms * 8, 256, 0, stream>>>(Y, ld, M, N, Y32.p, ld32);
+        CUDA_CHECK(cudaGetLastError());
+        ++kernels_launched;
+        sync();
+        Yown.release();           // an adopted matrix stays with its owner
+        Y = nullptr;
+        Yt.release();
+        fused_ready = false;
+        yt_valid = false;
+        storage_fp32 = true;
+        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ld32 * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)kTileC, (cuuint32_t)kTileR};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = get_encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Y32.p, gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw CudaError("bioen_b200: cuTensorMapEncodeTiled (fp32) failed");
+        evict_first = (matrix_bytes() > 80.0e6) ? 1 : 0;
     }
 
     // ---- per-method constant data ------------------------------------------------------------------
@@ -438,13 +489,13 @@ class Context {
         aux_n2.ensure(Npad + 8);  // lr_j
         have_forces = true;
         have_logw = false;        // Gv now holds w0
-        if (allow_fused && Y && !fused_ready) prepare_fused();
+        if (allow_fused && Y && !storage_fp32 && !fused_ready) prepare_fused();
     }
 
     // ---- fused two-pass forces path ------------------------------------------------------------------------
     bool fused_eligible() const {
         const long long l = (M + 1LL) & ~1LL;
-        return M >= kFMinM && l <= kFMaxLdt;
+        return !storage_fp32 && M >= kFMinM && l <= kFMaxLdt;
     }
     // structure-major copy Yt[j][i] of the resident matrix (the reference's yTildeT cache, made on the device)
     void make_transposed() {
@@ -659,10 +710,13 @@ class Context {
         a.vN = vN; a.vMb = vMb; a.ab = ab.p;
         a.partial = (MODE == kRowPass) ? partialA.p : partialB.p;
         a.ld = (MODE == kRowPass) ? Mpad : Npad;
-        if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        if (!has_matrix()) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
-        stream_pass_kernel<MODE, SUB><<<grid, kPassThreads, kPassSmemBytes, stream>>>(tmap, a);
+        if (storage_fp32)
+            stream_pass_kernel<MODE, SUB, float><<<grid, kPassThreads, kPassSmemBytesF32, stream>>>(tmap, a);
+        else
+            stream_pass_kernel<MODE, SUB, double><<<grid, kPassThreads, kPassSmemBytes, stream>>>(tmap, a);
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
         CUDA_CHECK(cudaGetLastError());
         ++passes_launched;
@@ -721,15 +775,15 @@ class Context {
     // the stand-alone kernels remain the path for large matrices, for the fused two-pass forces kernels and for
     // in-process groups (two cooperative grids cannot be co-resident on one device).
     bool persistent_for(bool forces) const {
-        if (!coop_ok || persistent_mode == 0 || !Y) return false;
-        if (persistent_mode < 0 && (double)M * (double)ld * 8.0 > persistent_max_bytes) return false;
+        if (!coop_ok || persistent_mode == 0 || !has_matrix()) return false;
+        if (persistent_mode < 0 && matrix_bytes() > persistent_max_bytes) return false;
         if (forces) return nranks == 1 && !forces_fused_now();
         if (nranks > 1) return fuse_exchange() && !comm->is_local();
         return true;
     }
     void launch_persistent(int method, int mode, double* x, const double* xp, const double* d, double stp,
                            const double* stp_dev, double* grad, const double* ddir) {
-        if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        if (!has_matrix()) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         PEvalArgs a{};
         a.method = method; a.mode = mode; a.M = M; a.N = N;
         a.row.nRT = nRT; a.row.nCB = nCB; a.row.T = T; a.row.chunk = chunk; a.row.interleave = 0;
@@ -756,12 +810,15 @@ class Context {
         // else runs on the device (grid <= SM count, 1 CTA per SM) but is not guaranteed to be.
         static const bool plain = getenv("BIOEN_B200_PERSISTENT_PLAIN") != nullptr;
         if (plain) {
-            persistent_eval_kernel<<<grid, kPEvalThreads, kPassSmemBytes, stream>>>(tmap, a);
+            if (storage_fp32) persistent_eval_kernel<float><<<grid, kPEvalThreads, kPassSmemBytesF32, stream>>>(tmap, a);
+            else persistent_eval_kernel<double><<<grid, kPEvalThreads, kPassSmemBytes, stream>>>(tmap, a);
             CUDA_CHECK(cudaGetLastError());
         } else {
             void* args[] = {(void*)&tmap, (void*)&a};
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)persistent_eval_kernel, dim3(grid), dim3(kPEvalThreads),
-                                                   args, (size_t)kPassSmemBytes, stream));
+            const void* fn = storage_fp32 ? (const void*)persistent_eval_kernel<float>
+                                          : (const void*)persistent_eval_kernel<double>;
+            CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPEvalThreads), args,
+                                                   (size_t)(storage_fp32 ? kPassSmemBytesF32 : kPassSmemBytes), stream));
         }
         if (timed) {
             CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));

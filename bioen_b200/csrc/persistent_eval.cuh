@@ -113,16 +113,16 @@ __device__ __forceinline__ void peval_grid_barrier(const PEvalArgs& a, unsigned 
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-template <int MODE, bool SUB>
+template <int MODE, bool SUB, typename T>
 __device__ __forceinline__ void peval_pass(unsigned char* smem, const CUtensorMap* tmap, const PassArgs& pa,
                                            RingPos& prod, RingPos& cons) {
     TileWalk tw;
     tw.init(MODE, pa, (int)blockIdx.x, (int)gridDim.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == kConsumerWarps) {
-        if (lane == 0 && tw.left > 0) pass_produce<MODE, SUB>(smem, tmap, pa, tw, prod);
+        if (lane == 0 && tw.left > 0) pass_produce<MODE, SUB, T>(smem, tmap, pa, tw, prod);
     } else if (tw.left > 0) {
-        pass_consume<MODE, SUB>(smem, pa, tw, cons);
+        pass_consume<MODE, SUB, T>(smem, pa, tw, cons);
     }
 }
 
@@ -191,6 +191,7 @@ __device__ __forceinline__ void block_sum2_max(double& a0, double& a1, double& m
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kPEvalThreads, 1)
     persistent_eval_kernel(const __grid_constant__ CUtensorMap tmap, const PEvalArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
     const int j0 = b * kPEvalVec + tid, jstride = G * kPEvalVec;
     unsigned int nbar = 0;
     RingPos prod{0, 1}, cons{0, 0};
-    pass_ring_init(smem);
+    pass_ring_init<T>(smem);
     if (tid == kConsumerWarps * 32) prefetch_tensormap(&tmap);
     __syncthreads();
     double* mypart = a.part + (size_t)b * kPSlots;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
             {
                 PassArgs pa = a.row;
                 pa.vN = a.w;
-                peval_pass<kRowPass, false>(smem, &tmap, pa, prod, cons);
+                peval_pass<kRowPass, false, T>(smem, &tmap, pa, prod, cons);
             }
             { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
             // ---- V3: finish the objective.  One GPU: EVERY CTA does it (identical values, fixed order; only CTA 0
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
         {
             PassArgs pa = a.col;
             pa.ab = a.ab;
-            peval_pass<kColPass, true>(smem, &tmap, pa, prod, cons);
+            peval_pass<kColPass, true, T>(smem, &tmap, pa, prod, cons);
         }
         { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- V5: gradient and its scalars; the CTA that arrives last finishes (and exchanges, sharded)
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
         {
             PassArgs pa = a.col;
             pa.ab = a.ab;
-            peval_pass<kColPass, false>(smem, &tmap, pa, prod, cons);
+            peval_pass<kColPass, false, T>(smem, &tmap, pa, prod, cons);
         }
         { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- V2: assemble x_j, CTA-local (max, sum w0 exp(x - max))
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
         {
             PassArgs pa = a.row;
             pa.vN = a.w;
-            peval_pass<kRowPass, false>(smem, &tmap, pa, prod, cons);
+            peval_pass<kRowPass, false, T>(smem, &tmap, pa, prod, cons);
         }
         { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
         // ---- V5 (every CTA, identical values; CTA 0 writes the scalars): avg, r, chi^2, objective; ab = {r_i, 0}
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
     {
         PassArgs pa = a.col;
         pa.ab = a.ab;
-        peval_pass<kColPass, false>(smem, &tmap, pa, prod, cons);
+        peval_pass<kColPass, false, T>(smem, &tmap, pa, prod, cons);
     }
     { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
     // ---- V7: E_j = (theta (1 + lr_j) + t_j) w_j
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(kPEvalThreads, 1)
         PassArgs pa = a.row;
         pa.vN = a.aux_n;
         pa.vMb = a.avg;
-        peval_pass<kRowPass, true>(smem, &tmap, pa, prod, cons);
+        peval_pass<kRowPass, true, T>(smem, &tmap, pa, prod, cons);
     }
     { peval_mark(a, mk); peval_grid_barrier(a, nbar); peval_mark(a, mk); }
     // ---- V9 (CTA 0): gradient and its scalars

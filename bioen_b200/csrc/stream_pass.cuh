@@ -46,14 +46,26 @@ constexpr int kTileC = 128;   // columns per tile  (128 doubles = 1 KB per tile 
 #ifndef BIOEN_PASS_CTAS_PER_SM
 #define BIOEN_PASS_CTAS_PER_SM 1
 #endif
-constexpr int kStages = BIOEN_PASS_STAGES;    // ring depth
+constexpr int kStages = BIOEN_PASS_STAGES;    // ring depth (fp64 storage)
 constexpr int kPassCtasPerSM = BIOEN_PASS_CTAS_PER_SM;
 constexpr int kConsumerWarps = 8;
 constexpr int kAuxBytes = 2048;                                   // vector slices travelling with a tile
 constexpr int kTileBytes = kTileR * kTileC * (int)sizeof(double);  // 32 KB
 constexpr int kStageBytes = kTileBytes + kAuxBytes;
-constexpr int kPassSmemBytes = kStages * kStageBytes + 2 * kStages * (int)sizeof(uint64_t) + 128;
 constexpr int kPassThreads = (kConsumerWarps + 1) * 32;
+
+// Ring geometry per storage type of the matrix.  T = double is the path everything is measured and pinned on.
+// T = float is the opt-in reduced-precision STORAGE of yTilde (BIOEN_B200_OPT_FP32_STORAGE): tiles are 16 KB, the
+// ring is twice as deep so that the same ~128 KB per SM are in flight, every product and every sum is still fp64.
+template <typename T>
+struct PassGeom {
+    static constexpr int kTile = kTileR * kTileC * (int)sizeof(T);
+    static constexpr int kStage = kTile + kAuxBytes;
+    static constexpr int kNStages = kStages * (int)(sizeof(double) / sizeof(T));
+    static constexpr int kSmem = kNStages * kStage + 2 * kNStages * (int)sizeof(uint64_t) + 128;
+};
+constexpr int kPassSmemBytes = PassGeom<double>::kSmem;
+constexpr int kPassSmemBytesF32 = PassGeom<float>::kSmem;
 
 struct PassArgs {
     int nRT;            // number of row tiles     ceil(M / kTileR)
@@ -139,11 +151,13 @@ struct RingPos {
     uint32_t phase;
 };
 
+template <typename T = double>
 __device__ __forceinline__ void pass_ring_init(unsigned char* smem) {
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-    uint64_t* empty = full + kStages;
+    using Geo = PassGeom<T>;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Geo::kNStages * Geo::kStage);
+    uint64_t* empty = full + Geo::kNStages;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < Geo::kNStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kConsumerWarps);
         }
@@ -152,9 +166,11 @@ __device__ __forceinline__ void pass_ring_init(unsigned char* smem) {
 }
 
 // the producer role of one pass: called by ONE lane (warp kConsumerWarps, lane 0)
-template <int MODE, bool SUB>
+template <int MODE, bool SUB, typename T = double>
 __device__ __forceinline__ void pass_produce(unsigned char* smem, const CUtensorMap* tmap, const PassArgs& a,
                                              TileWalk tw, RingPos& rp) {
+    using Geo = PassGeom<T>;
+    constexpr int kStages = Geo::kNStages, kStageBytes = Geo::kStage, kTileBytes = Geo::kTile;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
     const uint64_t policy = a.evict_first ? l2_policy_evict_first() : l2_policy_evict_last();
@@ -184,8 +200,46 @@ __device__ __forceinline__ void pass_produce(unsigned char* smem, const CUtensor
 }
 
 // the consumer role of one pass: called by the kConsumerWarps consumer warps
-template <int MODE, bool SUB>
+// one lane's share of a tile row in the row pass -- four columns -- and the matching slice of v
+// (fp64 storage: columns {2l, 2l+1} and {64+2l, 64+2l+1}, two 16-byte loads; fp32 storage: columns 4l .. 4l+3, one)
+template <typename T>
+struct RowFrag;
+template <>
+struct RowFrag<double> {
+    double2 v0, v1;
+    __device__ __forceinline__ void load_v(const double2* vv, int lane) { v0 = vv[lane]; v1 = vv[32 + lane]; }
+    __device__ __forceinline__ double dot(const unsigned char* rowp, int lane, bool sub, double b, double s) const {
+        const double2* yr = reinterpret_cast<const double2*>(rowp);
+        double2 y0 = yr[lane], y1 = yr[32 + lane];
+        if (sub) { y0.x -= b; y0.y -= b; y1.x -= b; y1.y -= b; }
+        s = fma(y0.x, v0.x, s);
+        s = fma(y0.y, v0.y, s);
+        s = fma(y1.x, v1.x, s);
+        s = fma(y1.y, v1.y, s);
+        return s;
+    }
+};
+template <>
+struct RowFrag<float> {
+    double2 v0, v1;
+    __device__ __forceinline__ void load_v(const double2* vv, int lane) { v0 = vv[2 * lane]; v1 = vv[2 * lane + 1]; }
+    __device__ __forceinline__ double dot(const unsigned char* rowp, int lane, bool sub, double b, double s) const {
+        const float4 y = reinterpret_cast<const float4*>(rowp)[lane];
+        double y0 = (double)y.x, y1 = (double)y.y, y2 = (double)y.z, y3 = (double)y.w;
+        if (sub) { y0 -= b; y1 -= b; y2 -= b; y3 -= b; }
+        s = fma(y0, v0.x, s);
+        s = fma(y1, v0.y, s);
+        s = fma(y2, v1.x, s);
+        s = fma(y3, v1.y, s);
+        return s;
+    }
+};
+
+template <int MODE, bool SUB, typename T = double>
 __device__ __forceinline__ void pass_consume(unsigned char* smem, const PassArgs& a, TileWalk tw, RingPos& rp) {
+    using Geo = PassGeom<T>;
+    constexpr int kStages = Geo::kNStages, kStageBytes = Geo::kStage, kTileBytes = Geo::kTile;
+    constexpr int kRowBytes = kTileC * (int)sizeof(T);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty = full + kStages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,24 +254,13 @@ __device__ __forceinline__ void pass_consume(unsigned char* smem, const PassArgs
         for (; tw.left > 0; tw.advance()) {
             const unsigned char* st = smem + (size_t)stage * kStageBytes;
             mbar_wait(&full[stage], phase);
-            const double2* vv = reinterpret_cast<const double2*>(st + kTileBytes);
-            const double2 v0 = vv[lane], v1 = vv[32 + lane];
+            RowFrag<T> fr;
+            fr.load_v(reinterpret_cast<const double2*>(st + kTileBytes), lane);
             const double* bv = reinterpret_cast<const double*>(st + kTileBytes + kTileC * 8);
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
                 const int row = warp * RPW + r;
-                const double2* yr = reinterpret_cast<const double2*>(st) + (size_t)row * (kTileC / 2);
-                double2 y0 = yr[lane], y1 = yr[32 + lane];
-                if (SUB) {
-                    const double b = bv[row];
-                    y0.x -= b; y0.y -= b; y1.x -= b; y1.y -= b;
-                }
-                double s = acc[r];
-                s = fma(y0.x, v0.x, s);
-                s = fma(y0.y, v0.y, s);
-                s = fma(y1.x, v1.x, s);
-                s = fma(y1.y, v1.y, s);
-                acc[r] = s;
+                acc[r] = fr.dot(st + (size_t)row * kRowBytes, lane, SUB, SUB ? bv[row] : 0.0, acc[r]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
@@ -245,8 +288,13 @@ __device__ __forceinline__ void pass_consume(unsigned char* smem, const PassArgs
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int row = rg * 8 + q;
-                const double2 y =
-                    (reinterpret_cast<const double2*>(st) + (size_t)row * (kTileC / 2) + warp * (CPW / 2))[cp];
+                double2 y;
+                if (sizeof(T) == 8) {
+                    y = (reinterpret_cast<const double2*>(st + (size_t)row * kRowBytes) + warp * (CPW / 2))[cp];
+                } else {
+                    const float2 yf = (reinterpret_cast<const float2*>(st + (size_t)row * kRowBytes) + warp * (CPW / 2))[cp];
+                    y = make_double2((double)yf.x, (double)yf.y);
+                }
                 const double2 ab = abv[row];
                 if (SUB) {
                     acc0 = fma(ab.x, y.x - ab.y, acc0);
@@ -278,7 +326,7 @@ __device__ __forceinline__ void pass_consume(unsigned char* smem, const PassArgs
     rp.phase = phase;
 }
 
-template <int MODE, bool SUB>
+template <int MODE, bool SUB, typename T = double>
 __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
     stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -289,19 +337,19 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TileWalk tw;   // producer and consumers walk the same tile sequence
     tw.init(MODE, a, (int)blockIdx.x, (int)gridDim.x);
-    pass_ring_init(smem);
+    pass_ring_init<T>(smem);
     __syncthreads();
     if (warp == kConsumerWarps) {
         if (lane == 0 && tw.left > 0) {
             prefetch_tensormap(&tmap);
             RingPos rp{0, 1};  // a fresh barrier passes a wait on parity 1
-            pass_produce<MODE, SUB>(smem, &tmap, a, tw, rp);
+            pass_produce<MODE, SUB, T>(smem, &tmap, a, tw, rp);
         }
         return;
     }
     if (tw.left == 0) return;
     RingPos rp{0, 0};
-    pass_consume<MODE, SUB>(smem, a, tw, rp);
+    pass_consume<MODE, SUB, T>(smem, a, tw, rp);
 }
 
 }  // namespace bioen

@@ -886,6 +886,18 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_combine(const GramCombine
     }
 }
 
+// fp64 -> fp32 copy of the resident matrix (opt-in reduced-precision STORAGE, BIOEN_B200_OPT_FP32_STORAGE);
+// round-to-nearest; columns >= n of the destination stay zero
+__global__ void __launch_bounds__(256) k_convert_f32(const double* Y, long long ld, int m, int n, float* Y32, long long ld32) {
+    const long long total = (long long)m * n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n);
+        const long long j = t - (long long)i * n;
+        Y32[(size_t)i * ld32 + j] = (float)Y[(size_t)i * ld + j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // In-place row-affine transform of the resident matrix:  y_ij <- scale_i * y_ij + offset_i   (columns j < n only: the
 // padding stays zero).  This is how a nuisance-parameter refit (DEER modulation depth, scattering scale factor:

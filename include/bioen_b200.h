@@ -183,9 +183,15 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * selects it for matrices up to 2 GB per GPU (environment: BIOEN_B200_PERSISTENT, BIOEN_B200_PERSISTENT_MAX_MB).
  * BIOEN_B200_OPT_LBFGS_GRAM (default 0; environment BIOEN_B200_LBFGS_GRAM=1): the L-BFGS direction update runs in
  * coefficient space -- 2 kernels and 1 exchange per iteration instead of 14 and 13.  Algebraically the two-loop
- * recursion of liblbfgs, but it rounds differently, so trajectories differ from the default path in the last bits. */
+ * recursion of liblbfgs, but it rounds differently, so trajectories differ from the default path in the last bits.
+ * BIOEN_B200_OPT_FP32_STORAGE (default 0; set to 1 AFTER the matrix is uploaded / generated): replace the resident fp64
+ * matrix by an fp32 copy.  Halves the bytes every pass streams (the roofline of an evaluation); products and sums stay
+ * fp64, but the matrix entries carry fp32 rounding (relative 6e-8), so results are NOT within the 1e-11 parity bar
+ * (measured: objective ~1e-8, gradient ~1e-7 relative; tests/test_gpu_fp32_storage.py).  Never the default.  The fused
+ * forces kernels, the theta scan, downloads and row-affine transforms need the fp64 matrix and are unavailable. */
 enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
-       BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5, BIOEN_B200_OPT_LBFGS_GRAM = 6 };
+       BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5, BIOEN_B200_OPT_LBFGS_GRAM = 6,
+       BIOEN_B200_OPT_FP32_STORAGE = 7 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of

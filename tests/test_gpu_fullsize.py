@@ -282,3 +282,65 @@ def test_cfg2_converged_optimum_against_the_reference_liblbfgs(cfg2):
         assert 0.0 <= (fv - fmin_forces) / fmin_forces < 1e-4, (fv, fmin_forces)
     # whatever the trajectory, the objective the device reports at its end point is the reference's objective there
     assert rel(ref.logw_objective(x, cfg2["G"], cfg2["yT"], cfg2["YT"], theta), fmin) < 1e-11
+
+
+def test_cfg5_shard_device_generated_matrix_and_sub_block_parity():
+    """BASELINE config 5 (N = 1e7 x M = 5000, 400 GB) exists only sharded and only on the devices: each GPU generates
+    its 5000 x 1.25e6 block (50 GB) with the counter-based generator.  Checked here on one such shard: (a) the generated
+    entries equal the NumPy restatement of the generator (tests/util_rng.py) on a column block and on a row block that
+    spans the whole shard, at the shard's global column offset; (b) both methods evaluated on a 5000 x 32768 column
+    sub-block agree with the reference's C kernels to 1e-11; (c) the full shard evaluates reproducibly and
+    gauge-invariantly (2 * M * N * 8 = 100 GB per evaluation)."""
+    import bioen_b200
+    import torch
+    from util_rng import generic_ytilde_block
+    m, n, shard = 5000, 1_250_000, 3                  # the 4th of 8 shards
+    free_b, _ = torch.cuda.mem_get_info(0)
+    if free_b < 60e9:
+        pytest.skip("needs 60 GB of free HBM")
+    _need_host_ram(int(6e9))
+    rng = np.random.default_rng(SEED)
+    ytrue = rng.standard_normal(m)
+    YT = (ytrue + 0.5 * rng.standard_normal(m)) / 0.5
+    col0 = shard * n
+    with bioen_b200.Problem(shape=(m, n)) as p:
+        p.generate(SEED, col0, ytrue / 0.5, 2.0)
+        # (a) generator: column block (all rows) and row block (all columns of the shard)
+        c0, nc = 777_000, 2048
+        blk = p.download(0, m, c0, nc)
+        exp = generic_ytilde_block(SEED, ytrue / 0.5, 2.0, 0, m, col0 + c0, nc)
+        assert np.max(np.abs(blk - exp)) < 1e-13 * np.max(np.abs(exp))
+        r0, nr = 4321, 8
+        rows = p.download(r0, nr, 0, n)
+        exp = generic_ytilde_block(SEED, ytrue / 0.5, 2.0, r0, nr, col0, n)
+        assert np.max(np.abs(rows - exp)) < 1e-13 * np.max(np.abs(exp))
+        # (b) sub-block parity against the reference C
+        kind, logw, forces = _cpu_checker()
+        nsub = 32768
+        sub = p.download(0, m, c0, nsub)
+        r = np.random.default_rng(5)
+        g1 = 0.1 * r.standard_normal(nsub)
+        f1 = (2e-2 / np.sqrt(m)) * r.standard_normal(m)
+        w0 = np.full(nsub, 1.0 / nsub)
+        with bioen_b200.Problem(sub) as q:
+            q.set_logw(np.zeros(nsub), YT, THETA)
+            f, g = q.objective_and_gradient(g1)
+            fo, go = logw(g1, np.zeros(nsub), sub, YT, THETA)
+            assert rel(f, fo) < 1e-11 and grad_err(g, go) < 1e-11, (kind, rel(f, fo), grad_err(g, go))
+            q.set_forces(w0, YT, THETA)
+            f, g = q.objective_and_gradient(f1)
+            fo, go = forces(f1, w0, sub, YT, THETA)
+            assert rel(f, fo) < 1e-11 and grad_err(g, go) < 1e-11, (kind, rel(f, fo), grad_err(g, go))
+        # (c) the whole shard
+        gfull = 0.1 * r.standard_normal(n)
+        p.set_logw(np.zeros(n), YT, THETA)
+        fa, ga = p.objective_and_gradient(gfull)
+        fb, gb = p.objective_and_gradient(gfull)
+        assert fa == fb and np.array_equal(ga, gb)
+        assert abs(ga.sum()) < 1e-11 * np.abs(ga).sum()
+        assert rel(p.objective(gfull + 1.5), fa) < 1e-12
+        # the row pass on the whole shard against NumPy for weights supported on the downloaded block
+        w = np.zeros(n)
+        wb = r.random(nc)
+        w[c0:c0 + nc] = wb
+        assert grad_err(p.average(w), blk @ wb) < 1e-13
