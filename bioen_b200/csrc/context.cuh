@@ -790,6 +790,13 @@ class Context {
         a.row.evict_first = evict_first; a.row.partial = partialA.p; a.row.ld = Mpad;
         a.col = a.row;
         a.col.partial = partialB.p; a.col.ld = Npad;
+        // experiment (BIOEN_B200_PERSISTENT_ICOL=1): deal the runs of the column pass round-robin as the stand-alone
+        // kernel does by default.  Measured at config 2 (0.4 GB): 150.2 us vs 149.1 us contiguous -- no gain for the
+        // matrix sizes this kernel is used for, so the contiguous order stays.
+        if (nCB >= 4LL * grid && getenv("BIOEN_B200_PERSISTENT_ICOL")) {
+            a.col.interleave = 1;
+            a.col.chunk = nRT;
+        }
         a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev;
         a.Gv = Gv.p; a.w = w.p; a.aux_n = aux_n.p; a.aux_n2 = aux_n2.p; a.grad = grad; a.ddir = ddir;
         a.Yobs = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.msum = msum.p; a.theta = theta; a.sc = sc.p;
