@@ -1,24 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- BioEn optimisation hot path on B200: gradient (f+g) evaluations per second.
+"""bench.py -- BioEn optimisation hot path on B200: gradient (f+g) evaluations per second and time to optimum.
 
 Workload (BASELINE.json `metric`): log-weights method, synthetic "generic data" (seed 12345,
 sig_exp 0.5, sig_sim 1, uniform w0, G = 0), N = 1e6 structures x M = 1e3 observables per GPU, theta = 10, fp64.
 One "step" = one evaluation of the log-posterior AND its gradient at a fresh point (2 passes over yTilde).
 
-  value      steps / device time, yTilde + all vectors resident in HBM (CUDA events, max over ranks)
-  e2e        the same through the C ABI with HOST vectors (bioen_b200_eval): every step copies g from pinned
-             host memory to the device and reads the objective and the gradient back
-  roofline   the dominant kernel (stream_pass_kernel, one pass over yTilde = M*N*8 algorithmic bytes per launch),
-             timed live with CUDA events around every launch inside the timed region
-  cpu_baseline  the reference's own OpenMP C kernels (oracle/_ref, built from /root/reference by oracle/Makefile)
-             on the host cores, on a column sample of the same problem
+  value            steps / device time, yTilde + all vectors resident in HBM (CUDA events, max over ranks)
+  e2e              the same through the C ABI with HOST vectors (bioen_b200_eval): every step copies g from pinned
+                   host memory to the device and reads the objective and the gradient back
+  roofline         the dominant kernel (stream_pass_kernel, one pass over yTilde = M*N*8 algorithmic bytes per
+                   launch), timed live with CUDA events around every launch inside the timed region
+  time_to_optimum  device L-BFGS (BioEn defaults) from x0 = 0; `.reference` = what the reference arm of the same
+                   round-end run measured on the same problem (seconds, fmin, iterations) and the fmin difference;
+                   `.coefficient_space_update` = the same with the opt-in 2-kernel L-BFGS update
+  dropin_time_to_optimum  host NumPy arrays in -> optimum out through the reference-facing entry points
+                   (c_bioen.bioen_opt_lbfgs_logw, optimize.log_weights.find_optimum)
+  cpu_baseline     the reference's own OpenMP C kernels (oracle/_ref) on the host cores, bounded column sample
+  extra_workloads  the other BASELINE configs, measured after the timed region: the forces method on the same matrix,
+                   the 32-theta batched scan (config 4), the opt-in fp32 storage, config 2 (500 x 1e5), the ala5
+                   shape (config 1); at N > 1 the strong-scaled config 3 and a config-5 shard (5000 x 1.25e6) per GPU
+  sharded_checks   N > 1: the sharded result through the fused peer-memory exchange vs NCCL, identical f on all ranks,
+                   f against an independent recombination (1e-12)
 
-N > 1 (torchrun): the structure axis is sharded, every rank holds N = 1e6 columns (weak scaling), one exchange
-of M+3 doubles (+ tiny scalar reductions) per evaluation, carried by the library's peer-memory kernel over
-NVLink (`config.exchange` = "p2p"; "nccl" when peer mapping is unavailable or BIOEN_B200_P2P=0); `value` counts
-1e6-structure evaluations per second summed over ranks.
+N > 1 (torchrun): the structure axis is sharded, every rank holds N = 1e6 columns (weak scaling), ONE exchange of
+M+5 doubles per objective half and one of 4 scalars per gradient half, issued from inside the producing kernels over
+NVLink peer memory (`run_info.exchange` = "p2p"; "nccl" when peer mapping is unavailable or BIOEN_B200_P2P=0);
+`value` counts 1e6-structure evaluations per second summed over ranks.  `--strong` splits --structures over the GPUs.
 
-`--impl reference` times the reference CPU implementation alone (no GPU code on that path).
+`--impl reference` runs the UNMODIFIED reference C (BioEn's OpenMP kernels + liblbfgs, oracle/_ref) on the host cores
+on the full problem: f+g evaluations/s (mean over the steps) and liblbfgs to the optimum.  No GPU code on that path.
 """
 import argparse
 import ctypes

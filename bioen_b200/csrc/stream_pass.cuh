@@ -13,17 +13,21 @@
 //
 //   * warp NW (one elected lane) is the producer: for each R x C tile it arms an mbarrier with the byte count
 //     and issues one 2-D tiled TMA load (cp.async.bulk.tensor) for the matrix tile plus one or two 1-D bulk
-//     copies for the slices of the small vectors the tile needs.  Tiles are 32 KB, the ring holds STAGES of
-//     them (6 -> 192 KB in flight per SM).  Out-of-range rows/columns are zero-filled by the TMA unit, the
-//     vectors are zero-padded, so there is no tail code anywhere.
+//     copies for the slices of the small vectors the tile needs.  Tiles are 32 KB, the ring holds 4 of them
+//     (128 KB in flight per SM; deeper is slower, see kStages below).  Out-of-range rows/columns are zero-filled by
+//     the TMA unit, the vectors are zero-padded, so there is no tail code anywhere.
 //   * warps 0..NW-1 are consumers.  Each warp owns a fixed slice of every tile (ROW: 4 rows x all columns,
 //     COL: all rows x 16 columns) and keeps its fp64 accumulators in registers for a whole "run" of tiles
 //     (ROW: a row-tile swept along the columns; COL: a column block swept down the rows), reads shared
 //     memory with conflict-free 128-bit loads, and releases the stage with one mbarrier arrive per warp.
 //     Warps never synchronise with each other.
 //
+// The producer / consumer roles are device functions (pass_produce / pass_consume, templates on the storage type of
+// the matrix) shared by the stand-alone kernel below and by the persistent evaluation kernel (persistent_eval.cuh).
+//
 // Work split: tiles are numbered run-major and cut into `nCTA` equal contiguous chunks, so the load is
-// balanced to +-1 tile whatever M and N are.  A run that straddles a chunk border is finished by two (or
+// balanced to +-1 tile whatever M and N are (the column pass deals whole runs round-robin instead where every CTA
+// gets some: TileWalk mode 2, the default since round 2).  A run that straddles a chunk border is finished by two (or
 // more) CTAs; each writes its partial sums to its own slot (`slot = cta - first_cta_of_run`), and the small
 // finalize kernels (vector_kernels.cu) add the slots in a fixed order.  No atomics on data: results are
 // bit-reproducible run to run.
