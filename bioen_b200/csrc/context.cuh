@@ -1084,6 +1084,13 @@ class Context {
     void spin_sync() {
         if (!fetch_ev) CUDA_CHECK(cudaEventCreateWithFlags(&fetch_ev, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(fetch_ev, stream));
+        // BIOEN_B200_SPIN=0: block in the driver instead of spinning (frees the host core of every rank at the price
+        // of the driver's wake-up latency per line-search trial)
+        static const bool spin = !(getenv("BIOEN_B200_SPIN") && getenv("BIOEN_B200_SPIN")[0] == '0');
+        if (!spin) {
+            CUDA_CHECK(cudaEventSynchronize(fetch_ev));
+            return;
+        }
         cudaError_t e;
         while ((e = cudaEventQuery(fetch_ev)) == cudaErrorNotReady) {
         }

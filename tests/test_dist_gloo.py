@@ -159,8 +159,80 @@ class _StandIn:
         x = self._mine(r["x"]) if self.method == 0 else r["x"]
         return x, r["fx"], r["code"], dict(iterations=r["iterations"], evaluations=r["evaluations"])
 
+    def set_theta(self, theta):
+        self.theta = theta
+
+    def theta_scan(self, thetas, x0=None, method=None, verbose=0, **cfg):
+        """Problem.theta_scan's signature; one oracle L-BFGS per theta from the shared start."""
+        from oracle import oracle as O
+        assert method == self.method
+        X, fm, codes, its = [], [], [], []
+        keep = self.theta
+        for th in np.asarray(thetas, dtype=np.float64).ravel():
+            self.theta = float(th)
+            start = self._full(x0) if self.method == 0 else np.asarray(x0, dtype=np.float64).ravel()
+            r = O.lbfgs(self._fg, start, **cfg)
+            X.append(self._mine(r["x"]) if self.method == 0 else r["x"])
+            fm.append(r["fx"])
+            codes.append(r["code"])
+            its.append(r["iterations"])
+        self.theta = keep
+        return np.stack(X), np.array(fm), np.array(codes), dict(iterations=np.array(its), evaluations=np.array(its),
+                                                                 rounds=0, gemm_launches=0, seconds=0.0)
+
     def close(self):
         pass
+
+
+def _worker_series(rank, world, port, out):
+    """optimize.*.find_optimum_series(..., problem=ShardedProblem): the batched branch calls
+    problem.theta_scan(chunk, x0=..., method=..., **cfg) and holds the post-processing matrix y as problem.like(y)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bioen_b200 import dist as D
+        from bioen_b200 import optimize
+        from oracle import oracle as O
+        D.Problem = _StandIn
+        D.connect = lambda p, n_total, group=None, device=None: p
+        M, N = 7, 151
+        P = O.synthetic_problem(M, N, seed=8)
+        y = 0.5 * P["yTilde"] + 0.25
+        thetas = [30.0, 3.0]
+        cfg = optimize.minimize.Parameters("lbfgs")
+        cfg["verbose"] = False
+        kw = optimize.log_weights._lbfgs_kwargs(cfg)
+        sp = D.ShardedProblem(P["yTilde"], device=0)
+        res = optimize.log_weights.find_optimum_series(P["GInit"], P["G"], y, P["yTilde"], P["YTilde"], thetas, cfg,
+                                                       problem=sp)
+        assert len(res) == 2
+        for (wopt, yopt, gopt, f0, f1), th in zip(res, thetas):
+            r = O.lbfgs(lambda v: O.logw_fg_np(v, P["G"].ravel(), P["yTilde"], P["YTilde"].ravel(), th),
+                        P["GInit"].ravel(), **kw)
+            assert gopt.shape == (N,) and np.array_equal(gopt, r["x"]) and f1 == r["fx"] and f1 < f0
+            assert wopt.shape == (N, 1) and np.allclose(yopt, y @ wopt.ravel(), rtol=1e-12)
+        resf = optimize.forces.find_optimum_series(P["forces_init"], P["w0"], y, P["yTilde"], P["YTilde"], thetas, cfg,
+                                                   problem=sp)
+        for tup, th in zip(resf, thetas):
+            r = O.lbfgs(lambda v: O.forces_fg_np(v, P["w0"].ravel(), P["yTilde"], P["YTilde"].ravel(), th),
+                        P["forces_init"].ravel(), **kw)
+            assert np.array_equal(tup[2], r["x"]) and tup[4] == r["fx"] and tup[0].shape == (N, 1)
+            assert np.allclose(tup[1], y @ tup[0].ravel(), rtol=1e-12)
+        with pytest.raises(ValueError):
+            sp.theta_scan(thetas, method=D.LOGW)       # forces is the method that is set
+        sp.close()
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_find_optimum_series_on_sharded_problem_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_series, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
 
 
 def _worker_find_optimum(rank, world, port, out):
