@@ -608,7 +608,7 @@ def run_b200(args):
                 t0 = time.perf_counter()
                 res = optimize.log_weights.find_optimum(GI, GI, y_host, yT_host, YT.reshape(1, -1), THETA, cfg)
                 dropin["find_optimum_distinct_y_s"] = time.perf_counter() - t0
-                dropin["find_optimum_distinct_y_note"] = ("y.wopt is streamed through a 1 GB device buffer in row "
+                dropin["find_optimum_distinct_y_note"] = ("y.wopt is streamed through a 256 MB device buffer in row "
                                                           "chunks: no second resident matrix")
                 del y_host
         del yT_host
