@@ -278,6 +278,7 @@ int bioen_b200_set_forces_dev(bioen_b200_ctx* ctx, const double* w0_dev, const d
 
 int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
     return guarded("bioen_b200_set_option", [&] {
+        ctx->pending_gen = -1;   // a pending objective-only evaluation is not continued across a change of path
         switch (option) {
             case BIOEN_B200_OPT_FUSED_FORCES: ctx->C.allow_fused = value != 0; break;
             case BIOEN_B200_OPT_LAZY_GRADIENT: ctx->C.lazy_gradient = value != 0; break;

@@ -253,6 +253,8 @@ class Context {
         allow_fused = true;
         lazy_gradient = true;
         fuse_allowed = true;
+        eval_fused = false;
+        forces_x = nullptr;
         lbfgs_gram_opt = getenv("BIOEN_B200_LBFGS_GRAM") != nullptr && getenv("BIOEN_B200_LBFGS_GRAM")[0] == '1';
         persistent_mode = -1;
         if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
@@ -500,6 +502,9 @@ class Context {
     // structure-major copy Yt[j][i] of the resident matrix (the reference's yTildeT cache, made on the device)
     void make_transposed() {
         NvtxRange nvtx("bioen:transpose_ytilde");
+        if (storage_fp32)
+            throw std::logic_error("bioen_b200: the structure-major copy (fused forces kernels, theta scan) needs the "
+                                   "fp64 matrix; it was released by BIOEN_B200_OPT_FP32_STORAGE");
         if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         ldt = (M + 1LL) & ~1LL;
         if (Yt.n != (size_t)N * ldt || !Yt.p) {
