@@ -634,9 +634,15 @@ class Context {
             ++kernels_launched;
         }
         launch_fused<kFusedSoftmaxAvg>(nullptr, Gv.p, nullptr, aux_n.p);   // x_j, CTA-local softmax, avg partials
-        k_fused_lse_merge<<<1, 256, 0, stream>>>(f_rows, flse.p, sc.p + SC_LSE_MAX);
-        ++kernels_launched;
-        gather_lse();
+        const bool xfused = fuse_exchange_forces();
+        if (xfused) {
+            k_forces_lse_gather<<<1, 256, 0, stream>>>(f_rows, flse.p, sc.p + SC_LSE_MAX, lse_all.p, p2p_dev_raw());
+            ++kernels_launched;
+        } else {
+            k_fused_lse_merge<<<1, 256, 0, stream>>>(f_rows, flse.p, sc.p + SC_LSE_MAX);
+            ++kernels_launched;
+            gather_lse();
+        }
         {
             ForcesWeightsArgs a{};
             a.n = N; a.x = aux_n.p; a.w0 = Gv.p; a.w = w.p; a.lr = aux_n2.p; a.lse_pairs = lse_pairs();
@@ -645,12 +651,32 @@ class Context {
             k_forces_weights<<<vec_blocks_n, kVecThreads, 0, stream>>>(a);
             ++kernels_launched;
         }
+        if (xfused) {
+            rows_finish(true, 1, false, nullptr, nullptr);
+            return;
+        }
         merge_fused_rows(true, 1);
         finalize_rows_from_msum(true, false);
+    }
+    // sharded fused forces path: exchanges issued inside the producing kernels (needs the peer-memory path)
+    bool fuse_exchange_forces() const { return nranks > 1 && comm && comm->fused_ok((size_t)M + 8) && fuse_allowed; }
+    P2PDev p2p_dev_raw() const { ++comm->exchanges; return comm->dev_args(); }
+    void rows_finish(bool scaled, int ntail, bool gradient, double* grad, const double* ddir) {
+        RowsFinishArgs a{};
+        a.m = M; a.nrows = f_rows; a.part = fpart.p; a.ldp = Mpad; a.lse_rows = scaled ? flse.p : nullptr;
+        a.lse_pairs = lse_pairs(); a.nranks = nranks; a.out = msum.p; a.ntail = ntail; a.gradient = gradient ? 1 : 0;
+        a.Y = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.theta = theta; a.d = ddir; a.grad = grad;
+        a.ticket = ticket.p; a.sc = sc.p; a.p2p = p2p_dev_raw();
+        k_forces_rows_finish<<<(M + 31) / 32, 256, 0, stream>>>(a);
+        ++kernels_launched;
     }
     void forces_eval_fused_g(double* grad, const double* ddir) {
         NvtxRange nvtx("bioen:forces_eval_g(fused)");
         launch_fused<kFusedGradient>(avg.p, w.p, aux_n2.p, nullptr);       // t_j, E_j, grad partials
+        if (fuse_exchange_forces()) {
+            rows_finish(false, 0, true, grad, ddir);
+            return;
+        }
         merge_fused_rows(false, 0);
         {
             ForcesGradArgs a{};
@@ -676,7 +702,7 @@ class Context {
     int exchanges_per_eval(bool forces) const {
         if (nranks <= 1) return 0;
         if (!forces && fuse_exchange()) return 2;   // M+5 doubles (objective half) + 4 scalars (gradient half)
-        return 3;   // (max, sum) gather + M-vector sum + {3 scalars | gradient M-vector}
+        return 3;   // forces: (max, sum) gather + avg/KL sum + gradient sum (inside the producing kernels when fused)   // (max, sum) gather + M-vector sum + {3 scalars | gradient M-vector}
     }
     // Sharded log-weights evaluation with the exchanges inside the producing kernels (peer-memory path only): the
     // normalisation pair travels with the row sums, so the objective half needs ONE exchange and no exchange launch.

@@ -748,6 +748,150 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sharded forces method on the fused two-pass kernels: the three exchanges of an evaluation issued from inside the
+// kernels that produce the values (as the log-weights path does), instead of three 1-block exchange launches.
+//   k_forces_lse_gather        this rank's (max, sum) pair from the CTA rows of F1, gathered over the ranks
+//   k_forces_rows_finish       out_i = sum over the CTA rows of a fused pass (scaled by the global softmax pair for
+//                              F1); the block that finishes last sums the M (+1: KL) values over the ranks and runs
+//                              what k_finalize_rows (objective half) or k_forces_grad (gradient half) would run
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_forces_lse_gather(int nrows, const double* lse, double* sc_pair,
+                                                           double* pairs_all, const P2PDev p2p) {
+    __shared__ double sm[256], ss[256];
+    double m = -DBL_MAX, s = 0.0;
+    for (int c = threadIdx.x; c < nrows; c += 256) lse_merge(m, s, lse[2 * c], lse[2 * c + 1]);
+    sm[threadIdx.x] = m;
+    ss[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double m1 = sm[threadIdx.x], s1 = ss[threadIdx.x];
+            lse_merge(m1, s1, sm[threadIdx.x + o], ss[threadIdx.x + o]);
+            sm[threadIdx.x] = m1;
+            ss[threadIdx.x] = s1;
+        }
+        __syncthreads();
+    }
+    __shared__ double pair[2];
+    if (threadIdx.x == 0) {
+        sc_pair[0] = pair[0] = sm[0];
+        sc_pair[1] = pair[1] = ss[0];
+    }
+    __syncthreads();
+    p2p_exchange_block(p2p, pair, pairs_all, 2, kP2PGather);
+}
+
+struct RowsFinishArgs {
+    int m, nrows;
+    const double* part;
+    long long ldp;
+    const double* lse_rows;    // F1: per-row (max, sum) pairs; nullptr for F2
+    const double* lse_pairs;   // [nranks][2] gathered pairs
+    int nranks;
+    double* out;               // msum: m values (+ tail)
+    int ntail;                 // 1: out[m] holds this rank's KL part (objective half); 0: gradient half
+    int gradient;              // 0: finish the objective half, 1: finish the gradient half
+    const double* Y;
+    double* ab;
+    double* avg;
+    double theta;
+    const double* d;           // gradient half: optional direction
+    double* grad;
+    unsigned int* ticket;
+    double* sc;
+    P2PDev p2p;
+};
+
+__global__ void __launch_bounds__(256) k_forces_rows_finish(const RowsFinishArgs a) {
+    __shared__ double red[8][33];
+    __shared__ bool is_last;
+    double M = 0.0, inv = 1.0;
+    if (a.lse_rows) {
+        double S;
+        global_lse(a.lse_pairs, a.nranks, M, S);
+        inv = 1.0 / S;
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    double s = 0.0;
+    for (int c = ty; c < a.nrows; c += 8) {
+        const double scale = a.lse_rows ? exp(a.lse_rows[2 * c] - M) * inv : 1.0;
+        if (i < a.m) s = fma(a.part[(size_t)c * a.ldp + i], scale, s);
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < a.m) {
+        double t = red[0][tx];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) t += red[g][tx];
+        a.out[i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *a.ticket = 0;
+    // ---- the finishing block: sum over the ranks, then the M-vector epilogue
+    const int count = a.m + a.ntail;
+    const double* vals = a.out;
+    int fail = 0;
+    const double* in = nullptr;
+    if (a.p2p.nranks > 1) in = p2p_deliver_and_wait(a.p2p, a.out, count, &fail);
+    auto total = [&](int k) {
+        if (!in) return __ldcg(vals + k);
+        double t = 0.0;
+        for (int r = 0; r < a.p2p.nranks; ++r) t += __ldcg(in + r * a.p2p.cap + k);
+        return t;
+    };
+    double* redf = &red[0][0];
+    if (!a.gradient) {
+        double v[1] = {0.0};
+        for (int k = threadIdx.x; k < a.m; k += blockDim.x) {
+            const double sum = total(k);
+            const double r = sum - a.Y[k];
+            a.avg[k] = sum;
+            reinterpret_cast<double2*>(a.ab)[k] = make_double2(r, 0.0);
+            v[0] = fma(r, r, v[0]);
+        }
+        block_sum<1>(v, redf);
+        if (threadIdx.x == 0) {
+            const double kl = total(a.m), chi2 = 0.5 * v[0];
+            a.sc[SC_KL] = kl;
+            a.sc[SC_CHI2] = chi2;
+            a.sc[SC_PRIOR] = kl * a.theta;
+            a.sc[SC_F] = fail ? p2p_nan() : kl * a.theta + chi2;
+        }
+    } else {
+        double v[3] = {0.0, 0.0, 0.0};
+        double gi = 0.0;
+        for (int k = threadIdx.x; k < a.m; k += blockDim.x) {
+            const double sum = total(k);
+            a.grad[k] = sum;
+            if (a.d) v[0] = fma(sum, a.d[k], v[0]);
+            v[1] = fma(sum, sum, v[1]);
+            gi = fmax(gi, fabs(sum));
+        }
+        v[2] = 0.0;
+        block_sum<3>(v, redf);
+        // max |grad| over the block
+        __shared__ double gmax[8];
+        gi = warp_max(gi);
+        if ((threadIdx.x & 31) == 0) gmax[threadIdx.x >> 5] = gi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) gi = fmax(gi, gmax[w]);
+            a.sc[SC_DG] = fail ? p2p_nan() : v[0];
+            a.sc[SC_GNORM2] = fail ? p2p_nan() : v[1];
+            a.sc[SC_GINF] = gi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // L-BFGS direction update in coefficient space (opt-in, BIOEN_B200_OPT_LBFGS_GRAM).
 //
 // liblbfgs' two-loop recursion (lbfgs.c:572-598) is a chain of 2*bound+1 dot products, each of which needs the vector

@@ -26,7 +26,7 @@ def _problem(oracle, M, N, seed=12345):
 
 
 @pytest.mark.parametrize("world,M,N,theta", [(2, 37, 5001, 1.0), (3, 100, 20000, 10.0), (4, 300, 4003, 3.0),
-                                             (2, 1, 257, 2.0)])
+                                             (2, 1, 257, 2.0), (2, 1000, 2600, 5.0)])
 def test_sharded_evaluation_on_one_gpu(oracle, world, M, N, theta):
     from bioen_b200 import dist as D
     P, G, g1, w0, f1 = _problem(oracle, M, N)
@@ -60,6 +60,13 @@ def test_sharded_evaluation_on_one_gpu(oracle, world, M, N, theta):
         fo, go = oracle.forces_fg(f1, w0, P["yTilde"], P["YTilde"], theta)
         assert all(rel(f, fo) < 1e-11 and grad_err(g, go) < 1e-11 for f, g in res)
         assert all(np.array_equal(g, res[0][1]) for _, g in res)
+        # the forces exchanges as separate launches (what NCCL carries) give the same numbers
+        grp.call(lambda r, p, lo, hi: p.set_option(4, 0))
+        res3 = grp.call(lambda r, p, lo, hi: p.objective_and_gradient(f1))
+        grp.call(lambda r, p, lo, hi: p.set_option(4, 1))
+        assert rel(res3[0][0], res[0][0]) < 1e-13 and grad_err(res3[0][1], res[0][1]) < 1e-12
+        fs = grp.call(lambda r, p, lo, hi: p.objective(f1))
+        assert all(rel(f, fo) < 1e-11 for f in fs)
 
 
 @pytest.mark.parametrize("world", [2, 4])
