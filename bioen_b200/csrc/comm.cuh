@@ -88,6 +88,7 @@ struct P2PDev {
     int rank, nranks;
     long long cap;
     unsigned long long timeout_ns;
+    int ll;   // 1: flag-in-data ("LL") delivery, 0: data + fence + flag
 };
 
 struct P2PArgs {
@@ -118,8 +119,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // combines the contributions itself (in rank order: all ranks get bit-identical results) and must not start the
 // NEXT exchange before it has finished reading (guaranteed by stream order / by being the same block).
 // *fail is set when a peer did not arrive within the timeout (the caller poisons its result with NaN).
-__device__ __forceinline__ const double* p2p_deliver_and_wait(const P2PDev& a, const double* send, int count,
-                                                              int* fail) {
+__device__ __forceinline__ const double* p2p_deliver_and_wait_fenced(const P2PDev& a, const double* send, int count,
+                                                                     int* fail) {
     __shared__ unsigned long long s_epoch;
     __shared__ int s_fail;
     unsigned char* me = a.region[a.rank];
@@ -171,6 +172,81 @@ __device__ __forceinline__ const double* p2p_deliver_and_wait(const P2PDev& a, c
     __syncthreads();
     *fail = s_fail;
     return reinterpret_cast<const double*>(me + kP2PHeaderBytes) + par * R * a.cap;
+}
+
+// The same exchange with the flag travelling INSIDE the data (the idea of NCCL's LL protocol): every double is sent
+// as one 16-byte cell {lo32 | epoch32 << 32, hi32 | epoch32 << 32}; each 8-byte half is written atomically, so a
+// receiver that sees the current epoch in both halves has the value -- no system-wide fence after the stores, no
+// separate flag store, no flag poll: one NVLink one-way latency instead of store + fence round trip + flag.  The
+// received values are unpacked into the plain inbox so callers read them exactly as in the fenced variant.
+// Region: the LL cells live behind the plain inbox ([2][R][cap] doubles), [2][R][cap] cells of 16 bytes.
+__device__ __forceinline__ const double* p2p_deliver_and_wait_ll(const P2PDev& a, const double* send, int count,
+                                                                 int* fail) {
+    __shared__ unsigned long long s_epoch;
+    __shared__ int s_fail;
+    unsigned char* me = a.region[a.rank];
+    const int tid = threadIdx.x, nthr = blockDim.x, R = a.nranks;
+    __syncthreads();   // `send` may have been produced by other threads of this block
+    if (tid == 0) {
+        unsigned long long* ep = reinterpret_cast<unsigned long long*>(me + 128);
+        s_epoch = *ep + 1;
+        *ep = s_epoch;
+        s_fail = 0;
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
+    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+    const size_t par = (size_t)(epoch & 1);
+    const size_t plain_bytes = (size_t)2 * R * a.cap * sizeof(double);
+    const size_t slot = (par * R + a.rank) * a.cap;
+    for (int i0 = tid; i0 < count; i0 += 4 * nthr) {
+        unsigned long long lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * nthr;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(i < count ? send[i] : 0.0);
+            lo[u] = (bits & 0xffffffffull) | tag;
+            hi[u] = (bits >> 32) | tag;
+        }
+        for (int r = 0; r < R; ++r) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.region[r] + kP2PHeaderBytes + plain_bytes) + slot;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr;
+                if (i < count)
+                    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + i), "l"(lo[u]), "l"(hi[u])
+                                 : "memory");
+            }
+        }
+    }
+    // receive: every cell of every rank, unpacked into the plain inbox
+    double* plain = reinterpret_cast<double*>(me + kP2PHeaderBytes) + par * R * a.cap;
+    const ulonglong2* cells = reinterpret_cast<const ulonglong2*>(me + kP2PHeaderBytes + plain_bytes) + par * R * a.cap;
+    const unsigned long long t0 = global_timer_ns();
+    bool bad = false;
+    for (int r = 0; r < R && !bad; ++r) {
+        for (int i = tid; i < count; i += nthr) {
+            unsigned long long x, y;
+            unsigned int spins = 0;
+            for (;;) {
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(cells + r * a.cap + i)
+                             : "memory");
+                if ((x & 0xffffffff00000000ull) == tag && (y & 0xffffffff00000000ull) == tag) break;
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { bad = true; break; }
+            }
+            if (bad) break;
+            plain[r * a.cap + i] = __longlong_as_double((long long)((x & 0xffffffffull) | (y << 32)));
+        }
+    }
+    if (bad) s_fail = 1;
+    __syncthreads();
+    *fail = s_fail;
+    return plain;
+}
+
+__device__ __forceinline__ const double* p2p_deliver_and_wait(const P2PDev& a, const double* send, int count,
+                                                              int* fail) {
+    return a.ll ? p2p_deliver_and_wait_ll(a, send, count, fail) : p2p_deliver_and_wait_fenced(a, send, count, fail);
 }
 
 __device__ __forceinline__ double p2p_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -234,6 +310,7 @@ class Comm {
     unsigned char* mapped[kP2PMaxRanks] = {};
     long long cap = 0;
     long long p2p_launches = 0;
+    bool use_ll = true;       // flag-in-data delivery (BIOEN_B200_EXCHANGE_LL=0 selects data + fence + flag)
     int local_group_id = -1;  // >= 0: in-process group (no NCCL, no IPC)
     unsigned long long timeout_ns = 120ull * 1000000000ull;  // generous: ranks may be skewed by host-side setup
 
@@ -262,11 +339,13 @@ class Comm {
             const double sec = atof(e);
             if (sec > 0) timeout_ns = (unsigned long long)(sec * 1e9);
         }
+        if (const char* e = getenv("BIOEN_B200_EXCHANGE_LL")) use_ll = e[0] != '0';
     }
     // what the producing kernels need to run an exchange themselves; nranks = 1 switches their exchange code off
     P2PDev dev_args() const {
         P2PDev d{};
         d.rank = rank; d.nranks = (p2p && use_p2p) ? nranks : 1; d.cap = cap; d.timeout_ns = timeout_ns;
+        d.ll = use_ll ? 1 : 0;
         for (int r = 0; r < nranks && r < kP2PMaxRanks; ++r) d.region[r] = mapped[r];
         return d;
     }
@@ -275,7 +354,7 @@ class Comm {
     void enable_local(long long cap_doubles, int device) {
         read_timeout_env();
         cap = cap_doubles;
-        const size_t bytes = kP2PHeaderBytes + (size_t)2 * nranks * cap * sizeof(double);
+        const size_t bytes = kP2PHeaderBytes + (size_t)2 * nranks * cap * (sizeof(double) + 16);   // plain inbox + LL cells
         CUDA_CHECK(cudaMalloc(&region, bytes));
         CUDA_CHECK(cudaMemset(region, 0, bytes));
         CUDA_CHECK(cudaDeviceSynchronize());
@@ -306,7 +385,7 @@ class Comm {
         const char* env = getenv("BIOEN_B200_P2P");
         int fail = (env && env[0] == '0') || nranks > kP2PMaxRanks;
         cap = cap_doubles;
-        const size_t bytes = kP2PHeaderBytes + (size_t)2 * nranks * cap * sizeof(double);
+        const size_t bytes = kP2PHeaderBytes + (size_t)2 * nranks * cap * (sizeof(double) + 16);   // plain inbox + LL cells
         cudaIpcMemHandle_t mine;
         memset(&mine, 0, sizeof(mine));
         if (!fail) {
