@@ -316,10 +316,23 @@ int bioen_b200_eval(bioen_b200_ctx* ctx, int method, const double* x_host, doubl
         const int n = ctx->dim(method);
         double* x = ctx->x_for(method);
         double* g = grad_host ? ctx->g_for(method) : nullptr;
+        // Log-weights gradient into PAGE-LOCKED host memory: the column pass forms grad_j in its epilogue, so it can
+        // store it straight through the mapped host pointer while the pass is still streaming -- the 8*N bytes cross
+        // PCIe under the pass instead of in a copy after it.
+        bool direct = false;
+        if (grad_host && method == BIOEN_B200_LOGW && C.colgrad_eligible() && !getenv("BIOEN_B200_NO_ZEROCOPY")) {
+            cudaPointerAttributes attr{};
+            if (cudaPointerGetAttributes(&attr, grad_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                attr.devicePointer && (reinterpret_cast<uintptr_t>(attr.devicePointer) & 15) == 0) {
+                g = static_cast<double*>(attr.devicePointer);
+                direct = true;
+            }
+            cudaGetLastError();
+        }
         C.h2d(x, x_host, n);
         if (method == BIOEN_B200_FORCES) C.forces_eval(x, nullptr, nullptr, 0.0, g, nullptr);
         else C.logw_eval(x, nullptr, nullptr, 0.0, g, nullptr);
-        if (grad_host) C.d2h(grad_host, g, n);
+        if (grad_host && !direct) C.d2h(grad_host, g, n);
         C.fetch_scalars();
         if (f) *f = C.h_sc[SC_F];
         if (!grad_host) { ctx->pending_gen = C.eval_gen; ctx->pending_method = method; }
@@ -753,6 +766,7 @@ static void preload_kernels() {
     BIOEN_TOUCH(k_forces_grad); BIOEN_TOUCH(k_forces_update); BIOEN_TOUCH(k_dot3); BIOEN_TOUCH(k_axpby);
     BIOEN_TOUCH(k_lbfgs_pair); BIOEN_TOUCH(k_lbfgs_twoloop); BIOEN_TOUCH(k_lbfgs_gram_pair); BIOEN_TOUCH(k_lbfgs_combine); BIOEN_TOUCH(k_fused_lse_merge);
     BIOEN_TOUCH(k_fused_merge_rows); BIOEN_TOUCH(k_forces_lse_gather); BIOEN_TOUCH(k_forces_rows_finish); BIOEN_TOUCH(k_transpose); BIOEN_TOUCH(k_grid_max_abs);
+    BIOEN_TOUCH(stream_colgrad_kernel<double>); BIOEN_TOUCH(k_colgrad_finish);
     BIOEN_TOUCH((stream_pass_kernel<kRowPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kRowPass, true>));
     BIOEN_TOUCH((stream_pass_kernel<kColPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kColPass, true>));
 #undef BIOEN_TOUCH

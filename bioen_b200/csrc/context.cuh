@@ -124,6 +124,8 @@ class Context {
     int persistent_mode = -1;              // BIOEN_B200_OPT_PERSISTENT: -1 auto (by size), 0 off, 1 on
     double persistent_max_bytes = 2.0e9;   // auto: matrices up to this size per GPU (BIOEN_B200_PERSISTENT_MAX_MB)
     long long persistent_launches = 0;
+    DevBuf<double> colgrad_part;           // per-CTA scalars of the column pass with the gradient epilogue
+    bool colgrad_opt = true;               // BIOEN_B200_COLGRAD=0: column pass + separate k_logw_grad
     DevBuf<unsigned long long> pe_trace;   // BIOEN_B200_PERSISTENT_TRACE: phase-boundary timestamps of CTA 0
     double* h_sc = nullptr;  // pinned
     double* h_stp = nullptr; // pinned: step length of the next graph-replayed trial
@@ -217,6 +219,12 @@ class Context {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytesF32));
         CUDA_CHECK(cudaFuncSetAttribute(stream_pass_kernel<kColPass, true, float>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBytesF32));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_colgrad_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kPassSmemBytes));
+        CUDA_CHECK(cudaFuncSetAttribute(stream_colgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kPassSmemBytesF32));
+        colgrad_part.alloc((size_t)grid * 3 + 8);
+        if (const char* e = getenv("BIOEN_B200_COLGRAD")) colgrad_opt = e[0] != '0';
         CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kPassSmemBytes));
         CUDA_CHECK(cudaFuncSetAttribute(persistent_eval_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -931,11 +939,39 @@ class Context {
             finalize_rows(false, 3, true);
         }
     }
+    // will logw_eval_g form the gradient inside the column pass (and so stream it out while the pass runs)?
+    bool colgrad_eligible() const {
+        return colgrad_opt && nranks == 1 && interleave_col && !persistent_for(false);
+    }
     bool eval_fused = false;   // the last logw_eval_f left un-normalised e_j in `w` (fused sharded path)
     void logw_eval_g(const double* x, double* grad, const double* ddir) {
         NvtxRange nvtx("bioen:logw_eval_g");
         if (persistent_for(false) && (nranks == 1 || eval_fused)) {
             launch_persistent(0, kPEvalGradient, const_cast<double*>(x), nullptr, nullptr, 0.0, nullptr, grad, ddir);
+            eval_fused = false;
+            return;
+        }
+        // single GPU, whole runs per CTA: the column pass forms the gradient itself (stream_colgrad_kernel)
+        auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        if (colgrad_opt && nranks == 1 && interleave_col && aligned16(x) && aligned16(grad) && aligned16(Gv.p) &&
+            aligned16(w.p)) {
+            PassArgs pa{};
+            pa.nRT = nRT; pa.nCB = nCB; pa.T = T; pa.chunk = chunk; pa.interleave = 1; pa.evict_first = evict_first;
+            pa.ab = ab.p; pa.partial = partialB.p; pa.ld = Npad;
+            ColGradArgs ga{};
+            ga.n = N; ga.g = x; ga.G = Gv.p; ga.w = w.p; ga.d = ddir; ga.grad = grad; ga.theta = theta; ga.sc = sc.p;
+            ga.i_gbar = SC_GBAR; ga.i_Gbar = SC_CAPGBAR; ga.cta_part = colgrad_part.p;
+            const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
+            if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+            if (storage_fp32)
+                stream_colgrad_kernel<float><<<grid, kPassThreads, kPassSmemBytesF32, stream>>>(tmap, pa, ga);
+            else
+                stream_colgrad_kernel<double><<<grid, kPassThreads, kPassSmemBytes, stream>>>(tmap, pa, ga);
+            if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+            CUDA_CHECK(cudaGetLastError());
+            k_colgrad_finish<<<1, 256, 0, stream>>>(grid, colgrad_part.p, sc.p, SC_DG, SC_GNORM2, SC_GINF);
+            ++passes_launched;
+            kernels_launched += 2;
             eval_fused = false;
             return;
         }

@@ -330,6 +330,152 @@ __device__ __forceinline__ void pass_consume(unsigned char* smem, const PassArgs
     rp.phase = phase;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column pass of the log-weights gradient WITH its epilogue (single GPU, interleaved run order: every run -- a column
+// block swept down all row tiles -- belongs to ONE CTA, so the warp that closes a run holds the finished
+// c_j = sum_i r_i (y_ij - avg_i) of its 16 columns and can form
+//     grad_j = w_j theta (g_j - <g> - G_j + <G>) + w_j c_j          (c_bioen_kernels_logw.c:214-217)
+// right there instead of writing c_j for a separate O(N) kernel to read back: no partial-sum round trip through HBM
+// (16 MB at N = 1e6), one kernel less, and the gradient leaves the SM while the pass is still streaming -- which is
+// what lets bioen_b200_eval write it straight into page-locked host memory, overlapped with the pass.
+// grad.d, ||grad||^2 and max|grad| are accumulated per lane, combined per CTA in a fixed order and finished by
+// k_colgrad_finish.
+// ------------------------------------------------------------------------------------------------
+struct ColGradArgs {
+    int n;
+    const double* g;
+    const double* G;
+    const double* w;
+    const double* d;      // may be nullptr
+    double* grad;         // device memory, or page-locked host memory mapped into the device's address space
+    double theta;
+    const double* sc;     // scalar file: <g>, <G>
+    int i_gbar, i_Gbar;
+    double* cta_part;     // [gridDim.x][3]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
+    stream_colgrad_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a, const ColGradArgs ga) {
+    using Geo = PassGeom<T>;
+    constexpr int kNS = Geo::kNStages, kStageB = Geo::kStage, kTileB = Geo::kTile;
+    constexpr int kRowBytes = kTileC * (int)sizeof(T);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    __shared__ double s_red[3][kConsumerWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TileWalk tw;
+    tw.init(kColPass, a, (int)blockIdx.x, (int)gridDim.x);   // a.interleave must be 1 (whole runs per CTA)
+    pass_ring_init<T>(smem);
+    __syncthreads();
+    if (warp == kConsumerWarps) {
+        if (lane == 0 && tw.left > 0) {
+            prefetch_tensormap(&tmap);
+            RingPos rp{0, 1};
+            pass_produce<kColPass, true, T>(smem, &tmap, a, tw, rp);
+        }
+        return;
+    }
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kNS * kStageB);
+    uint64_t* empty = full + kNS;
+    constexpr int CPW = kTileC / kConsumerWarps;
+    const int cp = lane & 7, rg = lane >> 3;
+    const double gbar = ga.sc[ga.i_gbar], Gbar = ga.sc[ga.i_Gbar];
+    double acc0 = 0.0, acc1 = 0.0, dg = 0.0, gn = 0.0, gi = 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (; tw.left > 0; tw.advance()) {
+        const unsigned char* st = smem + (size_t)stage * kStageB;
+        mbar_wait(&full[stage], phase);
+        const double2* abv = reinterpret_cast<const double2*>(st + kTileB);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int row = rg * 8 + q;
+            double2 y;
+            if (sizeof(T) == 8) {
+                y = (reinterpret_cast<const double2*>(st + (size_t)row * kRowBytes) + warp * (CPW / 2))[cp];
+            } else {
+                const float2 yf = (reinterpret_cast<const float2*>(st + (size_t)row * kRowBytes) + warp * (CPW / 2))[cp];
+                y = make_double2((double)yf.x, (double)yf.y);
+            }
+            const double2 ab = abv[row];
+            acc0 = fma(ab.x, y.x - ab.y, acc0);
+            acc1 = fma(ab.x, y.y - ab.y, acc1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kNS) { stage = 0; phase ^= 1; }
+        if (tw.closes_run()) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 8);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
+            if (rg == 0) {
+                const long long j = tw.run * kTileC + warp * CPW + 2 * cp;
+                if (j < ga.n) {
+                    const bool two = j + 1 < ga.n;
+                    double2 gv, Gv, wv;
+                    if (two) {
+                        gv = *reinterpret_cast<const double2*>(ga.g + j);
+                        Gv = *reinterpret_cast<const double2*>(ga.G + j);
+                        wv = *reinterpret_cast<const double2*>(ga.w + j);
+                    } else {   // last column of an odd N: no access past the end of caller-owned vectors
+                        gv = make_double2(ga.g[j], 0.0);
+                        Gv = make_double2(ga.G[j], 0.0);
+                        wv = make_double2(ga.w[j], 0.0);
+                    }
+                    const double g0 = wv.x * ga.theta * (gv.x - gbar - Gv.x + Gbar) + wv.x * acc0;
+                    const double g1 = two ? wv.y * ga.theta * (gv.y - gbar - Gv.y + Gbar) + wv.y * acc1 : 0.0;
+                    if (two) *reinterpret_cast<double2*>(ga.grad + j) = make_double2(g0, g1);
+                    else ga.grad[j] = g0;
+                    if (ga.d) {
+                        dg = fma(g0, ga.d[j], dg);
+                        if (two) dg = fma(g1, ga.d[j + 1], dg);
+                    }
+                    gn = fma(g0, g0, gn);
+                    gn = fma(g1, g1, gn);
+                    gi = fmax(gi, fmax(fabs(g0), fabs(g1)));
+                }
+            }
+            acc0 = acc1 = 0.0;
+        }
+    }
+    // per-CTA partial of the three scalars (consumer warps only: the producer warp has left), fixed order
+    dg = warp_sum(dg);
+    gn = warp_sum(gn);
+    gi = warp_max(gi);
+    if (lane == 0) { s_red[0][warp] = dg; s_red[1][warp] = gn; s_red[2][warp] = gi; }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < kConsumerWarps; ++w) { t0 += s_red[0][w]; t1 += s_red[1][w]; t2 = fmax(t2, s_red[2][w]); }
+        ga.cta_part[3 * blockIdx.x + 0] = t0;
+        ga.cta_part[3 * blockIdx.x + 1] = t1;
+        ga.cta_part[3 * blockIdx.x + 2] = t2;
+    }
+}
+
+// sums the per-CTA partials of stream_colgrad_kernel in CTA order
+__global__ void __launch_bounds__(256) k_colgrad_finish(int ncta, const double* cta_part, double* sc, int i_dg,
+                                                        int i_gn, int i_gi) {
+    __shared__ double red[3][8];
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int b = threadIdx.x; b < ncta; b += 256) {
+        t0 += cta_part[3 * b];
+        t1 += cta_part[3 * b + 1];
+        t2 = fmax(t2, cta_part[3 * b + 2]);
+    }
+    t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_max(t2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = t0; red[1][threadIdx.x >> 5] = t1; red[2][threadIdx.x >> 5] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 = fmax(t2, red[2][w]); }
+        sc[i_dg] = t0;
+        sc[i_gn] = t1;
+        sc[i_gi] = t2;
+    }
+}
+
 template <int MODE, bool SUB, typename T = double>
 __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
     stream_pass_kernel(const __grid_constant__ CUtensorMap tmap, const PassArgs a) {

@@ -11,8 +11,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-11
 OPT_PERSISTENT = 5
 
+# the last three are wide enough (>= 4 x 148 column blocks) for the stand-alone column pass to deal whole runs to the
+# CTAs and form the gradient in its epilogue (stream_colgrad_kernel); 80001 / 100003 are odd (pair-load tail)
 SHAPES = [(1, 1), (2, 1), (3, 5), (31, 127), (32, 128), (33, 129), (64, 4096), (5, 20000), (28, 50001),
-          (257, 3001), (500, 2049), (1000, 777), (300, 40000)]
+          (257, 3001), (500, 2049), (1000, 777), (300, 40000), (5, 80001), (64, 100003), (40, 76000)]
 
 
 @pytest.mark.parametrize("M,N", SHAPES)
