@@ -766,7 +766,7 @@ static void preload_kernels() {
     BIOEN_TOUCH(k_forces_grad); BIOEN_TOUCH(k_forces_update); BIOEN_TOUCH(k_dot3); BIOEN_TOUCH(k_axpby);
     BIOEN_TOUCH(k_lbfgs_pair); BIOEN_TOUCH(k_lbfgs_twoloop); BIOEN_TOUCH(k_lbfgs_gram_pair); BIOEN_TOUCH(k_lbfgs_combine); BIOEN_TOUCH(k_fused_lse_merge);
     BIOEN_TOUCH(k_fused_merge_rows); BIOEN_TOUCH(k_forces_lse_gather); BIOEN_TOUCH(k_forces_rows_finish); BIOEN_TOUCH(k_transpose); BIOEN_TOUCH(k_grid_max_abs);
-    BIOEN_TOUCH(stream_colgrad_kernel<double>); BIOEN_TOUCH(k_colgrad_finish);
+    BIOEN_TOUCH(stream_colgrad_kernel<double>); BIOEN_TOUCH(k_colgrad_finish); BIOEN_TOUCH(k_colgrad_finish_sharded);
     BIOEN_TOUCH((stream_pass_kernel<kRowPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kRowPass, true>));
     BIOEN_TOUCH((stream_pass_kernel<kColPass, false>)); BIOEN_TOUCH((stream_pass_kernel<kColPass, true>));
 #undef BIOEN_TOUCH

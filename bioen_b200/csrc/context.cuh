@@ -941,7 +941,7 @@ class Context {
     }
     // will logw_eval_g form the gradient inside the column pass (and so stream it out while the pass runs)?
     bool colgrad_eligible() const {
-        return colgrad_opt && nranks == 1 && interleave_col && !persistent_for(false);
+        return colgrad_opt && (nranks == 1 || fuse_exchange()) && interleave_col && !persistent_for(false);
     }
     bool eval_fused = false;   // the last logw_eval_f left un-normalised e_j in `w` (fused sharded path)
     void logw_eval_g(const double* x, double* grad, const double* ddir) {
@@ -953,14 +953,17 @@ class Context {
         }
         // single GPU, whole runs per CTA: the column pass forms the gradient itself (stream_colgrad_kernel)
         auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-        if (colgrad_opt && nranks == 1 && interleave_col && aligned16(x) && aligned16(grad) && aligned16(Gv.p) &&
-            aligned16(w.p)) {
+        const bool sharded_fused = nranks > 1 && eval_fused;
+        if (colgrad_opt && (nranks == 1 || sharded_fused) && interleave_col && aligned16(x) && aligned16(grad) &&
+            aligned16(Gv.p) && aligned16(w.p)) {
             PassArgs pa{};
             pa.nRT = nRT; pa.nCB = nCB; pa.T = T; pa.chunk = chunk; pa.interleave = 1; pa.evict_first = evict_first;
             pa.ab = ab.p; pa.partial = partialB.p; pa.ld = Npad;
             ColGradArgs ga{};
             ga.n = N; ga.g = x; ga.G = Gv.p; ga.w = w.p; ga.d = ddir; ga.grad = grad; ga.theta = theta; ga.sc = sc.p;
             ga.i_gbar = SC_GBAR; ga.i_Gbar = SC_CAPGBAR; ga.cta_part = colgrad_part.p;
+            ga.i_wscale = sharded_fused ? SC_WSCALE : -1;
+            ga.wio = w.p;
             const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
             if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
             if (storage_fp32)
@@ -969,7 +972,8 @@ class Context {
                 stream_colgrad_kernel<double><<<grid, kPassThreads, kPassSmemBytes, stream>>>(tmap, pa, ga);
             if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
             CUDA_CHECK(cudaGetLastError());
-            k_colgrad_finish<<<1, 256, 0, stream>>>(grid, colgrad_part.p, sc.p, SC_DG, SC_GNORM2, SC_GINF);
+            if (sharded_fused) k_colgrad_finish_sharded<<<1, 256, 0, stream>>>(grid, colgrad_part.p, sc.p, p2p_dev());
+            else k_colgrad_finish<<<1, 256, 0, stream>>>(grid, colgrad_part.p, sc.p, SC_DG, SC_GNORM2, SC_GINF);
             ++passes_launched;
             kernels_launched += 2;
             eval_fused = false;

@@ -352,6 +352,8 @@ struct ColGradArgs {
     const double* sc;     // scalar file: <g>, <G>
     int i_gbar, i_Gbar;
     double* cta_part;     // [gridDim.x][3]
+    int i_wscale;         // >= 0 (sharded run, one exchange per half): w holds e_j, w_j = e_j * sc[i_wscale] is
+    double* wio;          //      formed here and written back to wio
 };
 
 template <typename T>
@@ -381,6 +383,7 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
     constexpr int CPW = kTileC / kConsumerWarps;
     const int cp = lane & 7, rg = lane >> 3;
     const double gbar = ga.sc[ga.i_gbar], Gbar = ga.sc[ga.i_Gbar];
+    const double wscale = ga.i_wscale >= 0 ? ga.sc[ga.i_wscale] : 1.0;
     double acc0 = 0.0, acc1 = 0.0, dg = 0.0, gn = 0.0, gi = 0.0;
     int stage = 0;
     uint32_t phase = 0;
@@ -424,6 +427,12 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
                         Gv = make_double2(ga.G[j], 0.0);
                         wv = make_double2(ga.w[j], 0.0);
                     }
+                    if (ga.i_wscale >= 0) {
+                        wv.x *= wscale;
+                        wv.y *= wscale;
+                        if (two) *reinterpret_cast<double2*>(ga.wio + j) = wv;
+                        else ga.wio[j] = wv.x;
+                    }
                     const double g0 = wv.x * ga.theta * (gv.x - gbar - Gv.x + Gbar) + wv.x * acc0;
                     const double g1 = two ? wv.y * ga.theta * (gv.y - gbar - Gv.y + Gbar) + wv.y * acc1 : 0.0;
                     if (two) *reinterpret_cast<double2*>(ga.grad + j) = make_double2(g0, g1);
@@ -455,7 +464,8 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSM)
     }
 }
 
-// sums the per-CTA partials of stream_colgrad_kernel in CTA order
+// sums the per-CTA partials of stream_colgrad_kernel in CTA order; the sharded variant (with the exchange of
+// {grad.d, ||grad||^2, ||x||^2, max|grad|} between the ranks) is k_colgrad_finish_sharded in vector_kernels.cuh
 __global__ void __launch_bounds__(256) k_colgrad_finish(int ncta, const double* cta_part, double* sc, int i_dg,
                                                         int i_gn, int i_gi) {
     __shared__ double red[3][8];

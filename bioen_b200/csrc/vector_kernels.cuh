@@ -747,6 +747,38 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
     }
 }
 
+// sharded twin of k_colgrad_finish (stream_pass.cuh): per-CTA partials summed in CTA order, then ONE exchange of
+// {grad.d, ||grad||^2, ||x||^2, max|grad|} between the ranks from this block
+__global__ void __launch_bounds__(256) k_colgrad_finish_sharded(int ncta, const double* cta_part, double* sc,
+                                                                const P2PDev p2p) {
+    __shared__ double red[3][8];
+    __shared__ double xs[4];
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int b = threadIdx.x; b < ncta; b += 256) {
+        t0 += cta_part[3 * b];
+        t1 += cta_part[3 * b + 1];
+        t2 = fmax(t2, cta_part[3 * b + 2]);
+    }
+    t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_max(t2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = t0; red[1][threadIdx.x >> 5] = t1; red[2][threadIdx.x >> 5] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 = fmax(t2, red[2][w]); }
+        xs[0] = t0; xs[1] = t1; xs[2] = sc[SC_XNORM2]; xs[3] = t2;
+    }
+    int fail;
+    const double* in = p2p_deliver_and_wait(p2p, xs, 4, &fail);
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int r = 0; r < p2p.nranks; ++r) {
+            const double* q = in + r * p2p.cap;
+            s0 += __ldcg(q); s1 += __ldcg(q + 1); s2 += __ldcg(q + 2); s3 = fmax(s3, __ldcg(q + 3));
+        }
+        if (fail) s0 = s1 = s2 = s3 = p2p_nan();
+        sc[SC_DG] = s0; sc[SC_GNORM2] = s1; sc[SC_XNORM2] = s2; sc[SC_GINF] = s3;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sharded forces method on the fused two-pass kernels: the three exchanges of an evaluation issued from inside the
 // kernels that produce the values (as the log-weights path does), instead of three 1-block exchange launches.

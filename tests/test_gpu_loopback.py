@@ -26,7 +26,8 @@ def _problem(oracle, M, N, seed=12345):
 
 
 @pytest.mark.parametrize("world,M,N,theta", [(2, 37, 5001, 1.0), (3, 100, 20000, 10.0), (4, 300, 4003, 3.0),
-                                             (2, 1, 257, 2.0), (2, 1000, 2600, 5.0)])
+                                             (2, 1, 257, 2.0), (2, 1000, 2600, 5.0),
+                                             (2, 8, 160001, 2.0)])   # wide shards: gradient formed in the column pass
 def test_sharded_evaluation_on_one_gpu(oracle, world, M, N, theta):
     from bioen_b200 import dist as D
     P, G, g1, w0, f1 = _problem(oracle, M, N)
