@@ -100,3 +100,28 @@ def test_against_reference_library_if_built(oracle):
     f = oracle.forces_fg(f1, P["w0"], P["yTilde"], P["YTilde"], 3.0)
     assert rel(f[0], ref.forces_objective(f1, P["w0"], P["yTilde"], P["YTilde"], 3.0)) < F_TOL
     assert grad_err(f[1], ref.forces_gradient(f1, P["w0"], P["yTilde"], P["YTilde"], 3.0)) < G_TOL
+
+
+def test_host_generator_matches_the_numpy_restatement_of_the_device_generator():
+    """oracle/hostgen.c (the matrix of bench.py's reference arm) against tests/util_rng.py (the NumPy restatement of
+    the device's k_generate, which tests/test_gpu_fullsize.py checks against the device itself): same counter-based
+    law, entries equal to a few ulp (libm cos/log vs NumPy's)."""
+    import ctypes as C
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import oracle as O
+    from util_rng import generic_ytilde_block
+    lib = O.hostgen()
+    dp = C.POINTER(C.c_double)
+    m, n, col0 = 37, 5001, 123_456_789
+    a = np.random.default_rng(0).standard_normal(m)
+    Y = np.empty((m, n))
+    lib.hostgen_generic_ytilde(Y.ctypes.data_as(dp), n, m, n, 12345, col0, a.ctypes.data_as(dp), 2.0)
+    R = generic_ytilde_block(12345, a, 2.0, 0, m, col0, n)
+    assert np.max(np.abs(Y - R)) < 1e-13
+    assert abs(Y.std() - np.sqrt(4.0 + a.var())) < 0.05          # N(a_i, 2^2) entries
+    # a sub-block generated with an offset is the same block of the big matrix
+    Y2 = np.empty((m, 100))
+    lib.hostgen_generic_ytilde(Y2.ctypes.data_as(dp), 100, m, 100, 12345, col0 + 700, a.ctypes.data_as(dp), 2.0)
+    assert np.array_equal(Y2, Y[:, 700:800])
