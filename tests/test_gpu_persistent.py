@@ -127,3 +127,26 @@ def test_lbfgs_coefficient_space_update(oracle, M, N, theta):
         ro = oracle.lbfgs(lambda v: oracle.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], theta), P["forces_init"])
         tol = 1e-8 if ro["iterations"] < 150 else 1e-4
         assert out[1][3][2] == ro["code"] and rel(out[1][3][1], ro["fx"]) < tol
+
+
+def test_gradient_streamed_into_pinned_host_memory(oracle):
+    """bioen_b200_eval with a page-locked gradient buffer: the column pass stores grad_j through the mapped host
+    pointer while it streams (no device->host copy afterwards).  Same bits as the copy path and as the pageable path."""
+    import ctypes as C
+    import bioen_b200
+    from bioen_b200 import _lib
+    M, N, theta = 40, 80003, 3.0
+    P = oracle.synthetic_problem(M, N, seed=21)
+    g1 = 0.1 * np.random.default_rng(2).standard_normal(N)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        p.set_option(OPT_PERSISTENT, 0)            # the stand-alone kernels (what large matrices use)
+        p.set_logw(P["G"], P["YTilde"], theta)
+        f_ref, g_ref = p.objective_and_gradient(g1)            # pageable NumPy buffer: staged copy
+        gpin = bioen_b200.pinned_empty(N)
+        gpin[:] = -7.0
+        f = C.c_double()
+        x = np.ascontiguousarray(g1)
+        _lib.check(_lib.load().bioen_b200_eval(p._ctx, 0, _lib.ptr(x), C.byref(f), _lib.ptr(gpin)), "eval")
+        assert f.value == f_ref and np.array_equal(gpin, g_ref)
+        fo, go = oracle.logw_fg(g1, P["G"], P["yTilde"], P["YTilde"], theta)
+        assert rel(f.value, fo) < TOL and grad_err(gpin, go) < TOL
