@@ -17,8 +17,32 @@ import numpy as np
 
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.modules.setdefault("h5py", types.ModuleType("h5py"))
 sys.path.insert(0, REF)
+
+
+def _load_reference_stack():
+    """The reference package with ITS compiled extension: `make -C oracle refext` links the reference's Cython module
+    against the reference's own C library; it is injected under the name the package imports."""
+    import glob
+    import importlib
+    import importlib.util
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "refext"])
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "cpu", "c_bioen*.so"))[0]
+    import bioen.optimize.ext as E
+    spec = importlib.util.spec_from_file_location("bioen.optimize.ext.c_bioen", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules["bioen.optimize.ext.c_bioen"] = mod
+    E.c_bioen = mod
+    import bioen.optimize
+    importlib.reload(bioen.optimize)
+    return bioen.optimize
+
+
+OPT = _load_reference_stack()
 from bioen.analyze.observables import observables as RO  # noqa: E402
 
 
@@ -118,6 +142,76 @@ def scattering():
     print("scattering: rows", len(exp), "models", n, "fitted", out["fitted"], out["fitted_from_initial"])
 
 
+def workflow(obs, payload_get, payload_set, start_value, thetas, iterations, n):
+    """The reference's iteration of bioen/analyze/procedure.py:40-83 (log-weights method, liblbfgs through the
+    reference's own C stack, tight stop so that the optimum -- not the stop rule -- defines the result)."""
+    optimize = OPT
+    params = optimize.minimize.Parameters("lbfgs")
+    params["verbose"] = False
+    params["params"]["epsilon"] = 1e-7
+    params["params"]["delta"] = 1e-10
+    params["params"]["max_iterations"] = 20000
+    w0 = np.matrix(np.full((n, 1), 1.0 / n))
+    winit = w0.copy()
+    wopt = winit.copy()
+    log_w0 = optimize.log_weights.getGs(w0)
+    exp = obs.exp.copy()
+    payload_set(start_value)
+    sim, sim_init = obs.update_sim_init(wopt)
+    log_wopt = optimize.log_weights.getGs(winit)
+    values, weights, fmins = [float(np.ravel(payload_get())[0])], [], []
+    for theta in thetas:
+        for i in range(iterations):
+            out = optimize.log_weights.find_optimum(log_wopt, log_w0, sim_init, sim, exp, theta, params)
+            wopt = out[0]
+            wopt_md = np.matrix(wopt.copy())
+            wopt_md[wopt_md == 0.0] = 1e-150
+            sim, sim_init = obs.update_sim(wopt_md)
+            values.append(float(np.ravel(payload_get())[0]))
+            weights.append(np.asarray(wopt).ravel().copy())
+            fmins.append(float(out[4]))
+    return dict(wf_values=np.array(values), wf_weights=np.stack(weights), wf_fmin=np.array(fmins),
+                wf_thetas=np.array(thetas, dtype=float), wf_iterations=iterations)
+
+
+def add_workflows():
+    """Append the weights <-> nuisance iteration to both fixtures."""
+    for kind in ("deer", "scattering"):
+        fn = os.path.join(HERE, "nuisance_%s.npz" % kind)
+        d = dict(np.load(fn))
+        n = d["raw"].shape[1]
+        models = np.arange(float(n))
+        bag = Bag()
+        bag.nrestraints = d["raw"].shape[0]
+        if kind == "deer":
+            ln = "319-259"
+            bag.labels = [[319, 259]]
+            exp = np.zeros((bag.nrestraints, 3))
+            exp[:, 1], exp[:, 2] = d["exp_fit"], d["exp_opt"]
+            bag.exp_tmp = {ln: exp}
+            bag.exp_err_tmp = {ln: d["err"].copy()}
+            bag.moddepth = {ln: float(d["m0"])}
+            bag.sim_tmp = {m: {ln: d["raw"][:, j].copy()} for j, m in enumerate(models)}
+            get = lambda: bag.moddepth[ln]
+            setv = lambda v: bag.moddepth.__setitem__(ln, v)
+            start = float(d["m0"])
+        else:
+            exp = np.zeros((bag.nrestraints, 3))
+            exp[:, 1], exp[:, 2] = d["exp_fit"], d["err"]
+            bag.exp_tmp = exp
+            bag.exp_err_tmp = d["err"].copy()
+            bag.scaling_factor = float(d["c0"])
+            bag.sim_tmp = {m: d["raw"][:, j].copy() for j, m in enumerate(models)}
+            get = lambda: bag.scaling_factor
+            setv = lambda v: setattr(bag, "scaling_factor", v)
+            start = "initial-optimization"
+        obs = make_obs(kind, bag, models)
+        d.update(workflow(obs, get, setv, start, [10.0, 1.0], 4, n))
+        np.savez_compressed(fn, **d)
+        print(kind, "workflow values", d["wf_values"], "fmin", d["wf_fmin"])
+
+
 if __name__ == "__main__":
     deer()
     scattering()
+    add_workflows()

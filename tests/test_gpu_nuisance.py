@@ -78,3 +78,44 @@ def test_residual_helper_and_iterated_refits():
             q = bioen_b200.Problem(shape=(4, 16))
             q.adopt(t.data_ptr(), 16)
             q.affine_rows(np.ones(4), np.zeros(4))       # caller-owned matrix: refused
+
+
+@pytest.mark.parametrize("kind", ["deer", "scattering"])
+def test_weights_nuisance_iteration_matches_the_reference_workflow(kind):
+    """The loop of bioen/analyze/procedure.py:40-83 -- optimise the weights, refit the nuisance parameter against
+    them, rebuild the matrix, repeat; two theta values x four iterations -- recorded with the COMPLETE reference stack
+    (its Python, its Cython module, its OpenMP kernels, liblbfgs; make_nuisance_golden.py) and repeated here on ONE
+    resident matrix: device L-BFGS through the public find_optimum(problem=...), refit + in-place row-affine commit."""
+    import bioen_b200
+    from bioen_b200 import optimize
+    from bioen_b200 import nuisance as NU
+    d = load_golden("nuisance_" + kind)
+    n = d["raw"].shape[1]
+    start = float(d["m0"]) if kind == "deer" else NU.INITIAL
+    NUm, blocks = _blocks(kind, d, value=start)
+    base = NU.base_matrix(d["raw"], d["err"])
+    cfg = optimize.minimize.Parameters("lbfgs")
+    cfg["verbose"] = False
+    cfg["params"]["epsilon"] = 1e-7
+    cfg["params"]["delta"] = 1e-10
+    cfg["params"]["max_iterations"] = 20000
+    w0 = np.full((n, 1), 1.0 / n)
+    log_w0 = optimize.log_weights.getGs(w0)
+    log_wopt = optimize.log_weights.getGs(w0.copy())
+    YT = d["YTilde"].reshape(1, -1)
+    with bioen_b200.Problem(NU.proc_sim(base, blocks)) as P:
+        refit = NU.NuisanceRefit(P, blocks)
+        values = [refit.update(w0.ravel())[kind]]                         # update_sim_init
+        k = 0
+        for theta in d["wf_thetas"]:
+            for it in range(int(d["wf_iterations"])):
+                yT = P.download()                                         # only for the shape checks of the public API
+                res = optimize.log_weights.find_optimum(log_wopt, log_w0, yT, yT, YT, float(theta), cfg, problem=P)
+                wopt = res[0].ravel()
+                assert rel(res[4], d["wf_fmin"][k]) < 1e-7, (theta, it, res[4], d["wf_fmin"][k])
+                assert np.max(np.abs(wopt - d["wf_weights"][k])) < 1e-5, (theta, it)
+                wmd = wopt.copy()
+                wmd[wmd == 0.0] = 1e-150
+                values.append(refit.update(wmd)[kind])
+                k += 1
+    assert np.max(np.abs(np.array(values) / d["wf_values"] - 1.0)) < 1e-5, (values, d["wf_values"])
