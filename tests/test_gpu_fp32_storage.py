@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 OPT_FP32, OPT_PERSISTENT = 7, 5
 
 
-@pytest.mark.parametrize("M,N", [(3, 5), (33, 129), (64, 4096), (28, 50001), (257, 3001), (300, 40000)])
+# (8, 80001) is wide enough for the stand-alone column pass to carry the gradient epilogue (stream_colgrad_kernel<float>)
+@pytest.mark.parametrize("M,N", [(3, 5), (33, 129), (64, 4096), (28, 50001), (257, 3001), (300, 40000), (8, 80001)])
 @pytest.mark.parametrize("persistent", [0, 1])
 def test_fp32_storage_computes_fp64_on_the_rounded_matrix(oracle, M, N, persistent):
     import bioen_b200
