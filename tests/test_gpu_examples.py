@@ -31,3 +31,11 @@ def test_c_abi_demo_runs(tmp_path):
                     "-o", str(exe), "-L", libdir, "-lbioen_b200", "-lm", "-Wl,-rpath," + libdir], check=True)
     res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "c_abi_demo ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("kind", ["deer", "scattering"])
+def test_nuisance_refit_example(kind):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "nuisance_refit.py"), kind],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "reference stack, same loop" in res.stdout and res.stdout.count("iteration") == 8
