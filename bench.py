@@ -294,6 +294,11 @@ def cpu_reference(M, N_full, steps, warmup, method, want_optimum, max_cols=None)
             xo, fmin, code = ref.opt_lbfgs_forces(x0, w0, yT, YT, THETA, caching=caching)
             its = ctypes.c_size_t.in_dll(ref.lib(), "iterations_lbfgs_forces").value
         secs = time.perf_counter() - t0
+        try:   # the end point itself, for the B200 arm of the same run (it evaluates ITS objective there)
+            os.makedirs(os.path.dirname(T2O_FILE), exist_ok=True)
+            np.save(T2O_FILE[:-5] + "_x.npy", xo)
+        except OSError:
+            pass
         optimum = {"seconds": secs, "fmin": fmin, "code": int(code), "iterations": int(its),
                    "minimizer": "the reference's _opt_lbfgs_%s (liblbfgs 1.10, BioEn defaults) on the full problem, "
                                 "%d OpenMP threads, yTildeT cache %s" % (method, used, "on" if caching else "off"),
@@ -567,6 +572,16 @@ def run_b200(args):
                                         "speedup": r["seconds"] / optimum["seconds"]}
                 # sanity bound only: liblbfgs's stop rule leaves the log-weights end point of an N >= 1e5 problem
                 # defined to ~1e-6 (the reference's own two reduction modes end 2.8e-7 apart at config 2)
+                try:   # per-evaluation parity AT the reference's own optimum: the device objective at its end point
+                    xr = np.load(T2O_FILE[:-5] + "_x.npy")
+                    if xr.size == nvar:
+                        f_at, g_at = prob.objective_and_gradient(xr)
+                        optimum["reference"]["device_objective_at_reference_optimum"] = f_at
+                        optimum["reference"]["objective_rel_diff_at_reference_optimum"] = abs(f_at - r["fmin"]) / abs(r["fmin"])
+                        optimum["reference"]["device_gnorm_over_xnorm_at_reference_optimum"] = float(
+                            np.linalg.norm(g_at) / max(1.0, np.linalg.norm(xr)))
+                except (OSError, ValueError):
+                    pass
                 optimum["reference"]["note"] = ("north_star bar 1e-8; the reference's own fast_openmp 0/1 end points differ by "
                                                 "~3e-7 on such problems (stop rule delta=1e-6), see DESIGN.md section 7")
                 if d > 1e-4:
