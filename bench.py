@@ -208,6 +208,10 @@ def host_generate(M, cols, col0=0):
     on the host cores; entries agree with the device's to 1-2 ulp."""
     from oracle import oracle as O
     lib = O.hostgen()
+    try:   # torchrun exports OMP_NUM_THREADS=1 to its ranks; the generator should use the host's cores all the same
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(host_cores())
+    except OSError:
+        pass
     a, _ = observations(M)
     yT = np.empty((M, cols))
     lib.hostgen_generic_ytilde(yT.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), cols, M, cols, SEED, col0,
