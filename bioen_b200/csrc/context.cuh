@@ -122,7 +122,7 @@ class Context {
     unsigned long long pe_bar_base = 0;
     bool coop_ok = false;
     int persistent_mode = -1;              // BIOEN_B200_OPT_PERSISTENT: -1 auto (by size), 0 off, 1 on
-    double persistent_max_bytes = 2.0e9;   // auto: matrices up to this size per GPU (BIOEN_B200_PERSISTENT_MAX_MB)
+    double persistent_max_bytes = 0.6e9;   // auto: matrices up to this size per GPU (BIOEN_B200_PERSISTENT_MAX_MB)
     long long persistent_launches = 0;
     DevBuf<double> colgrad_part;           // per-CTA scalars of the column pass with the gradient epilogue
     bool colgrad_opt = true;               // BIOEN_B200_COLGRAD=0: column pass + separate k_logw_grad
@@ -809,8 +809,11 @@ class Context {
     }
 
     // ---- persistent cooperative evaluation (persistent_eval.cuh) ------------------------------------------------
-    // One kernel per evaluation (or per half).  Used when the matrix is small enough that launch gaps, kernel
-    // ramp-up / tail and separate exchange kernels are a visible share of an evaluation (auto: <= 2 GB per GPU);
+    // One kernel per evaluation (or per half).  Used when the matrix is small enough that launch gaps and kernel
+    // ramp-up / tail are a visible share of an evaluation.  Auto threshold 0.6 GB per GPU, measured at M = 1000 after
+    // the stand-alone path got the interleaved column pass with the gradient epilogue: 0.4 GB 0.1539 vs 0.1652 ms
+    // (persistent wins), 1 GB 0.3351 vs 0.3319, 2 GB 0.6262 vs 0.6127, 4 GB 1.1869 vs 1.1670 (stand-alone wins);
+    // sharded over 2 GPUs the same: 0.4 GB per GPU 0.1674 vs 0.1815, 1 GB 0.3539 vs 0.3446, 2 GB 0.6423 vs 0.6281;
     // the stand-alone kernels remain the path for large matrices, for the fused two-pass forces kernels and for
     // in-process groups (two cooperative grids cannot be co-resident on one device).
     bool persistent_for(bool forces) const {

@@ -180,7 +180,7 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * with the row sums: one exchange per objective half).  0 restores the three separate exchanges per evaluation.
  * BIOEN_B200_OPT_PERSISTENT (default -1 = by size; 0 off; 1 on): run an evaluation as ONE persistent cooperative
  * kernel (grid barriers between its phases, yTilde kept in L2 when it fits) instead of 6-11 kernel launches; auto
- * selects it for matrices up to 2 GB per GPU (environment: BIOEN_B200_PERSISTENT, BIOEN_B200_PERSISTENT_MAX_MB).
+ * selects it for matrices up to 0.6 GB per GPU (environment: BIOEN_B200_PERSISTENT, BIOEN_B200_PERSISTENT_MAX_MB).
  * BIOEN_B200_OPT_LBFGS_GRAM (default 0; environment BIOEN_B200_LBFGS_GRAM=1): the L-BFGS direction update runs in
  * coefficient space -- 2 kernels and 1 exchange per iteration instead of 14 and 13.  Algebraically the two-loop
  * recursion of liblbfgs, but it rounds differently, so trajectories differ from the default path in the last bits.
