@@ -119,7 +119,6 @@ class Context {
     // persistent cooperative evaluation kernel (persistent_eval.cuh)
     DevBuf<double> pe_part;
     DevBuf<unsigned long long> pe_bar;
-    unsigned long long pe_bar_base = 0;
     bool coop_ok = false;
     int persistent_mode = -1;              // BIOEN_B200_OPT_PERSISTENT: -1 auto (by size), 0 off, 1 on
     double persistent_max_bytes = 0.6e9;   // auto: matrices up to this size per GPU (BIOEN_B200_PERSISTENT_MAX_MB)
@@ -842,7 +841,7 @@ class Context {
         a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev;
         a.Gv = Gv.p; a.w = w.p; a.aux_n = aux_n.p; a.aux_n2 = aux_n2.p; a.grad = grad; a.ddir = ddir;
         a.Yobs = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.msum = msum.p; a.theta = theta; a.sc = sc.p;
-        a.part = pe_part.p; a.bar = pe_bar.p; a.bar_base = pe_bar_base; a.ticket = ticket.p;
+        a.part = pe_part.p; a.bar = pe_bar.p; a.ticket = ticket.p;
         if (method == 0 && nranks > 1) a.p2p = p2p_dev(); else a.p2p.nranks = 1;
         static const bool want_trace = getenv("BIOEN_B200_PERSISTENT_TRACE") != nullptr;
         if (want_trace) {
@@ -873,7 +872,6 @@ class Context {
             CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
             pass_ev_passes += npass - 1;   // one event pair brackets npass passes
         }
-        pe_bar_base += (unsigned long long)peval_num_barriers(method, mode, a.p2p.nranks > 1) * (unsigned long long)grid;
         passes_launched += npass;
         ++kernels_launched;
         ++persistent_launches;

@@ -462,19 +462,26 @@ class Lbfgs {
     // one line-search trial at x = xp + stp*d: evaluation + scalar read-back (host side of lbfgs.c:645-1001)
     void trial(double stp, const LineSearchState& ls) {
         if (use_graphs) {
+            // BIOEN_B200_GRAPHS_NOMEMCPY=1 (diagnostics): keep the two tiny copies (step length in, scalar file out)
+            // OUTSIDE the graph, so that it holds kernel nodes only
+            static const bool nomemcpy = getenv("BIOEN_B200_GRAPHS_NOMEMCPY") != nullptr;
             if (!g_trial) {
                 g_trial = capture([&] {
-                    CUDA_CHECK(cudaMemcpyAsync(C.sc.p + SC_STP, C.h_stp, sizeof(double), cudaMemcpyHostToDevice, C.stream));
+                    if (!nomemcpy)
+                        CUDA_CHECK(cudaMemcpyAsync(C.sc.p + SC_STP, C.h_stp, sizeof(double), cudaMemcpyHostToDevice, C.stream));
                     if (forces) C.forces_eval(x, xp, d, 0.0, g, d, C.sc.p + SC_STP);
                     else C.logw_eval(x, xp, d, 0.0, g, d, C.sc.p + SC_STP);
-                    C.d2h(C.h_sc, C.sc.p, SC_COUNT);
+                    if (!nomemcpy) C.d2h(C.h_sc, C.sc.p, SC_COUNT);
                 }, &g_trial_kernels);
                 if (!g_trial) use_graphs = false;   // capture not possible here: plain launches from now on
             }
             if (g_trial) {
                 *C.h_stp = stp;
                 const auto t0 = std::chrono::steady_clock::now();
+                if (nomemcpy)
+                    CUDA_CHECK(cudaMemcpyAsync(C.sc.p + SC_STP, C.h_stp, sizeof(double), cudaMemcpyHostToDevice, C.stream));
                 CUDA_CHECK(cudaGraphLaunch(g_trial, C.stream));
+                if (nomemcpy) C.d2h(C.h_sc, C.sc.p, SC_COUNT);
                 const auto t1 = std::chrono::steady_clock::now();
                 C.kernels_launched += g_trial_kernels;
                 C.spin_sync();

@@ -57,8 +57,7 @@ struct PEvalArgs {
     double theta;
     double* sc;
     double* part;        // [gridDim.x][kPSlots]
-    unsigned long long* bar;
-    unsigned long long bar_base;   // counter value when this launch starts (host-tracked)
+    unsigned long long* bar;       // [0] arrival count, [16] generation (grid barrier)
     unsigned int* ticket;
     P2PDev p2p;          // nranks > 1: sharded log-weights run, exchanges inside the kernel
     unsigned long long* trace;   // optional: CTA 0 stores %globaltimer at every phase boundary (diagnostics)
@@ -69,7 +68,7 @@ __device__ __forceinline__ void peval_mark(const PEvalArgs& a, int& k) {
     ++k;
 }
 
-// barriers a launch passes (the host advances bar_base by this times the grid size)
+// barriers a launch passes (diagnostics)
 __host__ __device__ inline int peval_num_barriers(int method, int mode, bool sharded) {
     if (method == 0) return mode == kPEvalObjective ? 3 : mode == kPEvalBoth ? (sharded ? 5 : 4) : 1;
     return mode == kPEvalObjective ? 4 : mode == kPEvalBoth ? 7 : 3;
@@ -96,15 +95,20 @@ __device__ __forceinline__ void peval_grid_barrier(const PEvalArgs& a, unsigned 
     __syncthreads();
     ++nbar;
     if (threadIdx.x == 0) {
-        // arrivals are counted on a.bar[0]; the CTA that completes the count publishes the barrier's number on
-        // a.bar[1] (its own cache line), which is what the others poll: the spinning loads do not contend with
-        // the arriving atomics
-        const unsigned long long target = a.bar_base + (unsigned long long)nbar * gridDim.x;
+        // Sense-reversing barrier that needs no state from the host (so captured CUDA graphs replay it correctly):
+        // a.bar[0] counts arrivals, a.bar[16] (its own cache line) is the generation.  Every CTA reads the generation
+        // BEFORE it arrives; the CTA that completes the count resets it and publishes generation + 1; the others poll
+        // the generation word, so the spinning loads do not contend with the arriving atomics.
+        unsigned long long* count = a.bar;
+        unsigned long long* gen = a.bar + 16;
+        const unsigned long long my_gen = ld_acquire_gpu_u64(gen);
         __threadfence();
-        if (atomicAdd(a.bar, 1ULL) + 1 == target) {
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.bar + 16), "l"(target) : "memory");
+        if (atomicAdd(count, 1ULL) + 1 == (unsigned long long)gridDim.x) {
+            *count = 0;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(gen), "l"(my_gen + 1) : "memory");
         } else {
-            while (ld_acquire_gpu_u64(a.bar + 16) < target) {
+            while (ld_acquire_gpu_u64(gen) == my_gen) {
             }
         }
         __threadfence();
