@@ -6,8 +6,8 @@
 // passes over the matrix are ~0.03 ms; at config 2 (500 x 1e5) the small kernels are 25 % of a step; and with N = 1e6
 // split over 8 GPUs (1 GB per GPU) launch gaps, kernel ramp-up / tail and the separate exchange kernels cost 0.07 ms
 // next to 0.30 ms of passes.  Here one persistent CTA per SM runs the phases of the evaluation back to back, separated
-// by grid barriers (a monotonic counter in global memory; the kernel is launched cooperatively so all CTAs are
-// resident):
+// by grid barriers (sense-reversing: an arrival count and a generation word in global memory, no state from the
+// host; the kernel is launched cooperatively so all CTAs are resident):
 //
 //   log-weights   V0 x = xp + stp d, local (max, sum exp)  | V1 global (max, S), w_j, prior sums | P2 row pass  avg
 //                 V3 (CTA 0) slots -> avg, r, chi^2, f [+ the ONE exchange of a sharded run]   -- objective done --
