@@ -292,6 +292,7 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
             case BIOEN_B200_OPT_FUSED_EXCHANGE: ctx->C.fuse_allowed = value != 0; break;
             case BIOEN_B200_OPT_PERSISTENT: ctx->C.persistent_mode = value; break;
             case BIOEN_B200_OPT_LBFGS_GRAM: ctx->C.lbfgs_gram_opt = value != 0; break;
+            case BIOEN_B200_OPT_SLICE: ctx->C.slice_mode = value; break;
             case BIOEN_B200_OPT_FP32_STORAGE:
                 CUDA_CHECK(cudaSetDevice(ctx->C.device));
                 ctx->pending_gen = -1;
@@ -914,6 +915,8 @@ long long bioen_b200_query(bioen_b200_ctx* ctx, int what) {
         case 3: return C.persistent_for(what == 3 && C.have_forces) ? 1 : 0;
         case 4: return C.storage_fp32 ? 4 : 8;
         case 5: return C.persistent_launches;
+        case 6: return C.slice_launches;
+        case 7: return C.slice_ok() ? 1 : 0;
         default: return -1;
     }
 }

@@ -21,6 +21,7 @@
 #include "comm.cuh"
 #include "fused_pass.cuh"
 #include "persistent_eval.cuh"
+#include "slice_eval.cuh"
 #include "stream_pass.cuh"
 #include "vector_kernels.cuh"
 
@@ -126,6 +127,12 @@ class Context {
     DevBuf<double> colgrad_part;           // per-CTA scalars of the column pass with the gradient epilogue
     bool colgrad_opt = true;               // BIOEN_B200_COLGRAD=0: column pass + separate k_logw_grad
     DevBuf<unsigned long long> pe_trace;   // BIOEN_B200_PERSISTENT_TRACE: phase-boundary timestamps of CTA 0
+    // shared-memory-resident evaluation kernel for small matrices (slice_eval.cuh)
+    DevBuf<double> slice_tab, slice_gtab, slice_part;
+    SlicePlan slice_pl;
+    bool slice_coop = false;
+    int slice_mode = -1;                   // BIOEN_B200_OPT_SLICE: -1 / 1 on when the problem is eligible, 0 off
+    long long slice_launches = 0;
     double* h_sc = nullptr;  // pinned
     double* h_stp = nullptr; // pinned: step length of the next graph-replayed trial
 
@@ -239,6 +246,25 @@ class Context {
             if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
             if (const char* e = getenv("BIOEN_B200_LBFGS_GRAM")) lbfgs_gram_opt = e[0] == '1';
             if (const char* e = getenv("BIOEN_B200_PERSISTENT_MAX_MB")) persistent_max_bytes = atof(e) * 1.0e6;
+            // slice kernel: plan once per context (M, N are fixed), tables only when the problem is eligible
+            cudaFuncAttributes fa{};
+            int optin = 0;
+            CUDA_CHECK(cudaFuncGetAttributes(&fa, slice_eval_kernel));
+            CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            const long long max_dyn = (long long)optin - (long long)fa.sharedSizeBytes - 256;
+            if (max_dyn > 0) slice_pl = slice_plan(M, N, num_sms, (size_t)max_dyn);
+            if (slice_pl.ok) {
+                CUDA_CHECK(cudaFuncSetAttribute(slice_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)max_dyn));
+                int occ = 0;
+                CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, slice_eval_kernel, kSliceThreads,
+                                                                         slice_pl.smem));
+                slice_coop = coop && (long long)occ * num_sms >= slice_pl.grid;
+                slice_tab.alloc((size_t)(kSliceHdr + M) * kSliceGP);
+                slice_gtab.alloc((size_t)M * kSliceGP);
+                slice_part.alloc((size_t)kSliceGP * 3 + 8);
+            }
+            if (const char* e = getenv("BIOEN_B200_SLICE")) slice_mode = atoi(e);
         }
     }
 
@@ -265,6 +291,8 @@ class Context {
         lbfgs_gram_opt = getenv("BIOEN_B200_LBFGS_GRAM") != nullptr && getenv("BIOEN_B200_LBFGS_GRAM")[0] == '1';
         persistent_mode = -1;
         if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
+        slice_mode = -1;
+        if (const char* e = getenv("BIOEN_B200_SLICE")) slice_mode = atoi(e);
         comm = nullptr;
         nranks = 1;
         N_total = N;
@@ -815,7 +843,55 @@ class Context {
     // sharded over 2 GPUs the same: 0.4 GB per GPU 0.1674 vs 0.1815, 1 GB 0.3539 vs 0.3446, 2 GB 0.6423 vs 0.6281;
     // the stand-alone kernels remain the path for large matrices, for the fused two-pass forces kernels and for
     // in-process groups (two cooperative grids cannot be co-resident on one device).
+    // slice_eval.cuh: the matrix dealt column-wise into the CTAs' shared memory, 1 grid barrier per evaluation.  Takes
+    // precedence over the persistent kernel AND over the fused two-pass forces kernels whenever the problem is small
+    // enough (slice_plan); BIOEN_B200_OPT_PERSISTENT = 0 (stand-alone kernels) switches it off as well.
+    bool slice_ok() const {
+        return slice_pl.ok && slice_coop && slice_mode != 0 && persistent_mode != 0 && nranks == 1 && Y != nullptr &&
+               !storage_fp32 && (ld % 2) == 0 && ld >= N && (reinterpret_cast<uintptr_t>(Y) & 15) == 0;
+    }
+    void launch_slice(int method, int mode, double* x, const double* xp, const double* d, double stp,
+                      const double* stp_dev, double* grad, const double* ddir) {
+        SliceArgs a{};
+        a.method = method; a.mode = mode; a.M = M; a.N = N;
+        a.nc = slice_pl.nc; a.cx_log2 = slice_pl.cx_log2; a.l_log2 = slice_pl.l_log2;
+        a.Y = Y; a.ld = ld;
+        a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev;
+        a.Gv = Gv.p; a.w = w.p; a.aux_n = aux_n.p; a.aux_n2 = aux_n2.p; a.grad = grad; a.ddir = ddir;
+        a.Yobs = Yobs.p; a.ab = ab.p; a.avg = avg.p; a.theta = theta; a.sc = sc.p;
+        a.tab = slice_tab.p; a.gtab = slice_gtab.p; a.part = slice_part.p; a.bar = pe_bar.p; a.ticket = ticket.p;
+        static const bool want_trace = getenv("BIOEN_B200_PERSISTENT_TRACE") != nullptr;
+        if (want_trace) {
+            if (!pe_trace.p) pe_trace.alloc(64);
+            a.trace = pe_trace.p;
+        }
+        const int npass = method == 0 ? (mode == kPEvalBoth ? 2 : 1) : (mode == kPEvalBoth ? 4 : 2);
+        const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
+        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+        void* args[] = {(void*)&a};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)slice_eval_kernel, dim3(slice_pl.grid), dim3(kSliceThreads),
+                                               args, slice_pl.smem, stream));
+        if (timed) {
+            CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
+            pass_ev_passes += npass - 1;
+        }
+        passes_launched += npass;
+        ++kernels_launched;
+        ++persistent_launches;
+        ++slice_launches;
+        if (want_trace && (slice_launches % 16) == 0) {
+            unsigned long long h[40];
+            sync();
+            CUDA_CHECK(cudaMemcpy(h, pe_trace.p, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[slice trace] method %d mode %d grid %d nc %d: phase boundaries (us since kernel start):",
+                    method, mode, slice_pl.grid, slice_pl.nc);
+            for (int k = 1; k < 40 && h[k] >= h[0] && h[k] - h[0] < 10000000ull; ++k) fprintf(stderr, " %.1f", (h[k] - h[0]) * 1e-3);
+            fprintf(stderr, "\n");
+            CUDA_CHECK(cudaMemset(pe_trace.p, 0, 64 * sizeof(unsigned long long)));
+        }
+    }
     bool persistent_for(bool forces) const {
+        if (slice_ok()) return true;
         if (!coop_ok || persistent_mode == 0 || !has_matrix()) return false;
         if (persistent_mode < 0 && matrix_bytes() > persistent_max_bytes) return false;
         if (forces) return nranks == 1 && !forces_fused_now();
@@ -825,6 +901,10 @@ class Context {
     void launch_persistent(int method, int mode, double* x, const double* xp, const double* d, double stp,
                            const double* stp_dev, double* grad, const double* ddir) {
         if (!has_matrix()) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
+        if (slice_ok()) {
+            launch_slice(method, mode, x, xp, d, stp, stp_dev, grad, ddir);
+            return;
+        }
         PEvalArgs a{};
         a.method = method; a.mode = mode; a.M = M; a.N = N;
         a.row.nRT = nRT; a.row.nCB = nCB; a.row.T = T; a.row.chunk = chunk; a.row.interleave = 0;
@@ -1026,7 +1106,7 @@ class Context {
     void forces_eval_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev = nullptr) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         ++eval_gen;
-        if (forces_fused_now()) {
+        if (forces_fused_now() && !slice_ok()) {
             forces_eval_fused_f(x, xp, d, stp, stp_dev);
             return;
         }
@@ -1056,7 +1136,7 @@ class Context {
     }
     // gradient of the point forces_eval_f was last called for
     void forces_eval_g(double* grad, const double* ddir) {
-        if (forces_fused_now()) {
+        if (forces_fused_now() && !slice_ok()) {
             forces_eval_fused_g(grad, ddir);
             return;
         }

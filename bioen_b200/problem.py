@@ -381,6 +381,8 @@ class Problem:
     def pass_kernel_name(self, method=None):
         """Name of the kernel that streams yTilde for `method` (bench.py's roofline record)."""
         method = self.method if method is None else method
+        if self.query(7) == 1:
+            return "slice_eval_kernel"
         if self.query(3):
             return "persistent_eval_kernel"
         return "fused_team_pass" if (method == FORCES and self.query(0)) else "stream_pass_kernel"
@@ -391,6 +393,13 @@ class Problem:
 
     def kernels_launched(self):
         return int(self._lib.bioen_b200_kernels_launched(self._ctx))
+
+    def debug_read(self, what, count):
+        """Device vectors an evaluation leaves behind (tests): 1 weights, 2 averages, 3 / 4 the forces method's
+        per-structure vectors (E_j or x_j; guarded log-ratio)."""
+        out = np.empty(int(count), dtype=np.float64)
+        _lib.check(self._lib.bioen_b200_debug_read(self._ctx, int(what), _lib.ptr(out), int(count)), "debug_read")
+        return out
 
     def scalars(self):
         out = np.empty(64, dtype=np.float64)

@@ -188,10 +188,15 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * matrix by an fp32 copy.  Halves the bytes every pass streams (the roofline of an evaluation); products and sums stay
  * fp64, but the matrix entries carry fp32 rounding (relative 6e-8), so results are NOT within the 1e-11 parity bar
  * (measured: objective ~1e-8, gradient ~1e-7 relative; tests/test_gpu_fp32_storage.py).  Never the default.  The fused
- * forces kernels, the theta scan, downloads and row-affine transforms need the fp64 matrix and are unavailable. */
+ * forces kernels, the theta scan, downloads and row-affine transforms need the fp64 matrix and are unavailable.
+ * BIOEN_B200_OPT_SLICE (default -1 = on when eligible; 0 off; environment BIOEN_B200_SLICE): problems small enough for
+ * the CTAs to hold their columns of yTilde in shared memory (up to ~30 MB in all, e.g. every fixture of the
+ * reference's test-suite and the ala5 example) run an evaluation as ONE cooperative kernel with ONE grid barrier: the
+ * matrix is read once per launch and every sweep runs out of shared memory (csrc/slice_eval.cuh).  Takes precedence
+ * over the persistent kernel and the fused forces kernels; BIOEN_B200_OPT_PERSISTENT = 0 disables it as well. */
 enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
        BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5, BIOEN_B200_OPT_LBFGS_GRAM = 6,
-       BIOEN_B200_OPT_FP32_STORAGE = 7 };
+       BIOEN_B200_OPT_FP32_STORAGE = 7, BIOEN_B200_OPT_SLICE = 8 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
@@ -299,8 +304,9 @@ long long bioen_b200_kernels_launched(bioen_b200_ctx *ctx);
 /* facts about how the context evaluates (bench.py, tests): what = 0: 1 if the forces method runs on the fused
  * two-pass kernels; 1 / 2: exchanges between the ranks per log-weights / forces f+g evaluation (0 on one GPU);
  * 3: 1 if evaluations run as ONE persistent cooperative kernel with yTilde held in L2 (small problems);
- * 4: bytes per element of the resident matrix (8, or 4 with BIOEN_B200_OPT_FP32_STORAGE); 5: persistent-kernel launches
- * so far.  Returns -1 for an unknown `what`. */
+ * 4: bytes per element of the resident matrix (8, or 4 with BIOEN_B200_OPT_FP32_STORAGE); 5: one-launch evaluations
+ * (persistent or slice kernel) so far; 6: of those, launches of the shared-memory slice kernel; 7: 1 if evaluations
+ * run on the slice kernel now.  Returns -1 for an unknown `what`. */
 long long bioen_b200_query(bioen_b200_ctx *ctx, int what);
 int bioen_b200_debug_read(bioen_b200_ctx *ctx, int what, double *out_host, size_t count);
 /* the context's cudaStream_t (for callers that enqueue their own work around the device entry points) */

@@ -38,3 +38,13 @@ def grad_err(a, b):
     """max|a-b| / max|b| -- the norm-relative gradient metric ('parity metric')."""
     a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def select_eval_path(p, mode):
+    """How a Problem launches its evaluations: 0 stand-alone kernels, 1 persistent kernel (csrc/persistent_eval.cuh),
+    2 shared-memory slice kernel (csrc/slice_eval.cuh; the default for every problem small enough -- all fixtures
+    of the reference's test-suite are).  Skips the test when the slice kernel cannot take the problem."""
+    p.set_option(5, 1 if mode else 0)
+    p.set_option(8, 1 if mode == 2 else 0)
+    if mode == 2 and p.query(7) != 1:
+        pytest.skip("problem not eligible for the slice kernel")

@@ -6,7 +6,7 @@ Tolerances (north_star): same final objective to 1e-8 relative, converged weight
 import numpy as np
 import pytest
 
-from conftest import FORCES_FIXTURES, LOGW_FIXTURES, load_golden, rel
+from conftest import FORCES_FIXTURES, LOGW_FIXTURES, load_golden, rel, select_eval_path
 
 pytestmark = pytest.mark.gpu
 
@@ -39,13 +39,13 @@ def _bound(d, key):
 
 @pytest.mark.parametrize("name", LOGW_FIXTURES + FORCES_FIXTURES)
 @pytest.mark.parametrize("ls", [0, 1, 2, 3])
-@pytest.mark.parametrize("persistent", [0, 1])
+@pytest.mark.parametrize("persistent", [0, 1, 2])
 def test_lbfgs_matches_reference_endpoint(name, ls, persistent):
     import bioen_b200
     d = load_golden(name)
     key = "lbfgs%d" % ls
     with bioen_b200.Problem(d["yTilde"]) as p:
-        p.set_option(5, persistent)
+        select_eval_path(p, persistent)
         x0 = _setup(p, d)
         x, fmin, code, info = p.opt_lbfgs(x0, linesearch=ls)
         assert code == d[key + "_code"], (code, info)
@@ -74,7 +74,7 @@ SENSITIVE_END_POINTS = {("conjugate_fr", "data_potra_part_1_logw_M808xN80"): 3e-
                                   "data_potra_part_1_logw_M808xN80", "data_forces_M64xN64",
                                   "data_deer_test_forces_M808xN10"])
 @pytest.mark.parametrize("alg", GSL_ALGS)
-@pytest.mark.parametrize("persistent", [0, 1])
+@pytest.mark.parametrize("persistent", [0, 1, 2])
 def test_gsl_matches_reference_endpoint(name, alg, persistent):
     """Both evaluation paths (stand-alone kernels / persistent kernel: different partial-sum cuts, i.e. different
     rounding) against the reference's end point."""
@@ -83,7 +83,7 @@ def test_gsl_matches_reference_endpoint(name, alg, persistent):
     d = load_golden(name)
     key = "gsl_" + alg
     with bioen_b200.Problem(d["yTilde"]) as p:
-        p.set_option(5, persistent)
+        select_eval_path(p, persistent)
         x0 = _setup(p, d)
         x, fmin, code, info = p.opt_gsl(x0, algorithm=c_bioen.get_gsl_method(alg))
         assert code == d[key + "_code"], (code, info)

@@ -1,7 +1,8 @@
-"""GPU: the persistent cooperative evaluation kernel (one launch per evaluation, csrc/persistent_eval.cuh) against
-the stand-alone kernels (6-11 launches) and the CPU oracle.  Small matrices take the persistent kernel by default,
-so this file is where the stand-alone kernels keep their small-shape coverage (option 5 = 0) and where the two paths
-are played against each other: same objective and gradient to rounding, same minimiser end points."""
+"""GPU: the one-launch evaluation kernels -- the persistent cooperative kernel (csrc/persistent_eval.cuh) and the
+shared-memory slice kernel (csrc/slice_eval.cuh) -- against the stand-alone kernels (6-11 launches) and the CPU
+oracle.  Small matrices take the one-launch kernels by default, so this file is where the stand-alone kernels keep
+their small-shape coverage (option 5 = 0) and where the three paths are played against each other: same objective
+and gradient to rounding, same minimiser end points.  Modes: 0 stand-alone, 1 persistent, 2 slice (when eligible)."""
 import numpy as np
 import pytest
 
@@ -10,6 +11,16 @@ from conftest import grad_err, rel
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
 OPT_PERSISTENT = 5
+OPT_SLICE = 8
+
+
+def select_path(p, mode):
+    """0: stand-alone kernels, 1: persistent kernel, 2: slice kernel; False when the problem is not eligible"""
+    p.set_option(OPT_PERSISTENT, 1 if mode else 0)
+    p.set_option(OPT_SLICE, 1 if mode == 2 else 0)
+    p.set_option(1, 0)                         # forces on the tile kernels (the persistent kernel's path)
+    return mode != 2 or p.query(7) == 1
+
 
 # the last three are wide enough (>= 4 x 148 column blocks) for the stand-alone column pass to deal whole runs to the
 # CTAs and form the gradient in its epilogue (stream_colgrad_kernel); 80001 / 100003 are odd (pair-load tail)
@@ -32,12 +43,12 @@ def test_persistent_vs_standalone_vs_oracle(oracle, M, N):
     fo_f, go_f = oracle.forces_fg(f1, w0, P["yTilde"], P["YTilde"], theta)
     res = {}
     with bioen_b200.Problem(P["yTilde"]) as p:
-        for mode in (0, 1):
-            p.set_option(OPT_PERSISTENT, mode)
-            p.set_option(1, 0)                         # forces on the tile kernels (the persistent kernel's path)
+        for mode in (0, 1, 2):
+            if not select_path(p, mode):
+                continue
             p.set_logw(G, P["YTilde"], theta)
-            assert p.query(3) == mode
-            n0 = p.query(5)
+            assert p.query(3) == (1 if mode else 0) and p.query(7) == (1 if mode == 2 else 0)
+            n0, s0 = p.query(5), p.query(6)
             f, g = p.objective_and_gradient(g1)
             assert rel(f, fo_l) < TOL and grad_err(g, go_l) < TOL, (mode, "logw")
             fonly = p.objective(g1)
@@ -50,12 +61,16 @@ def test_persistent_vs_standalone_vs_oracle(oracle, M, N):
             g2 = p.gradient(f1)
             assert rel(fonly, fo_f) < TOL and np.array_equal(g2, gf), (mode, "forces split")
             assert (p.query(5) - n0 > 0) == bool(mode)
+            assert p.query(6) - s0 == (p.query(5) - n0 if mode == 2 else 0)
             # run-to-run bit reproducibility
             ff2, gf2 = p.objective_and_gradient(f1)
             assert ff2 == ff and np.array_equal(gf2, gf)
             res[mode] = (f, g, ff, gf)
-    assert rel(res[0][0], res[1][0]) < 1e-13 and grad_err(res[0][1], res[1][1]) < 1e-12
-    assert rel(res[0][2], res[1][2]) < 1e-13 and grad_err(res[0][3], res[1][3]) < 1e-12
+    for mode in sorted(res)[1:]:
+        assert rel(res[0][0], res[mode][0]) < 1e-13 and grad_err(res[0][1], res[mode][1]) < 1e-12, mode
+        assert rel(res[0][2], res[mode][2]) < 1e-13 and grad_err(res[0][3], res[mode][3]) < 1e-12, mode
+    if (M, N) in ((28, 50001), (64, 4096), (5, 20000), (1000, 777), (500, 2049), (257, 3001), (3, 5), (1, 1)):
+        assert 2 in res, "shape expected to run on the slice kernel"
 
 
 @pytest.mark.parametrize("M,N,theta", [(28, 50001, 10.0), (100, 20000, 1.0), (37, 5001, 100.0)])
@@ -66,9 +81,8 @@ def test_minimisers_on_both_paths(oracle, M, N, theta):
     P = oracle.synthetic_problem(M, N, seed=12345)
     out = {}
     with bioen_b200.Problem(P["yTilde"]) as p:
-        for mode in (0, 1):
-            p.set_option(OPT_PERSISTENT, mode)
-            p.set_option(1, 0)
+        for mode in (0, 1, 2):
+            assert select_path(p, mode)
             p.set_logw(P["G"], P["YTilde"], theta)
             a = p.opt_lbfgs(P["GInit"], max_iterations=60)
             b = p.opt_lbfgs(P["GInit"], linesearch=0, max_iterations=60)
@@ -82,17 +96,18 @@ def test_minimisers_on_both_paths(oracle, M, N, theta):
     noise = {-998, -1001, -1000, -999, -996}
     for k in range(4):
         x0, f0, c0, _ = out[0][k]
-        x1, f1, c1, _ = out[1][k]
-        if k == 3 and (c0 in noise or c1 in noise):
-            assert rel(f1, f0) < 1e-6, (k, f0, f1, c0, c1)
-            continue
-        assert c0 == c1, (k, c0, c1)
-        assert rel(f1, f0) < 1e-8, (k, f0, f1)
+        for mode in (1, 2):
+            x1, f1, c1, _ = out[mode][k]
+            if k == 3 and (c0 in noise or c1 in noise):
+                assert rel(f1, f0) < 1e-6, (mode, k, f0, f1, c0, c1)
+                continue
+            assert c0 == c1, (mode, k, c0, c1)
+            assert rel(f1, f0) < 1e-8, (mode, k, f0, f1)
     # converged forces run: rounding differences grow along a long trajectory (tests/test_gpu_fullsize.py), so the
     # end points are compared with the bound the other minimiser tests use
     ro = oracle.lbfgs(lambda v: oracle.forces_fg(v, P["w0"], P["yTilde"], P["YTilde"], theta), P["forces_init"])
     tol = 1e-8 if ro["iterations"] < 150 else 1e-4
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         code = out[mode][4][2]
         assert code == ro["code"] or code in noise or ro["code"] in noise, (mode, code, ro["code"])
         assert rel(out[mode][4][1], ro["fx"]) < tol, (mode, out[mode][4][1], ro["fx"])
