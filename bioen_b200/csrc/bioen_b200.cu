@@ -864,7 +864,9 @@ int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double
         CUDA_CHECK(cudaEventElapsedTime(&total, e0, e1));
         if (ms) *ms = total;
         if (launches) *launches = bioen_b200_kernels_launched(ctx) - k0;
-        const float pm = C.end_pass_timing();
+        float pm = C.end_pass_timing();
+        // slice kernel: a launch is a whole evaluation (no per-pass events); report the step's share per algorithmic pass
+        if (pm == 0.f && C.slice_ok() && steps > 0) pm = total / (float)steps / (forces ? 4.f : 2.f);
         if (pass_ms) *pass_ms = pm;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);

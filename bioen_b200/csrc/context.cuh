@@ -260,8 +260,8 @@ class Context {
                 CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, slice_eval_kernel, kSliceThreads,
                                                                          slice_pl.smem));
                 slice_coop = coop && (long long)occ * num_sms >= slice_pl.grid;
-                slice_tab.alloc((size_t)(kSliceHdr + M) * kSliceGP);
-                slice_gtab.alloc((size_t)M * kSliceGP);
+                slice_tab.alloc((size_t)slice_pl.grid * slice_pl.ms);
+                slice_gtab.alloc((size_t)slice_pl.grid * slice_pl.ms);
                 slice_part.alloc((size_t)kSliceGP * 3 + 8);
             }
             if (const char* e = getenv("BIOEN_B200_SLICE")) slice_mode = atoi(e);
@@ -854,7 +854,8 @@ class Context {
                       const double* stp_dev, double* grad, const double* ddir) {
         SliceArgs a{};
         a.method = method; a.mode = mode; a.M = M; a.N = N;
-        a.nc = slice_pl.nc; a.cx_log2 = slice_pl.cx_log2; a.l_log2 = slice_pl.l_log2;
+        a.nc = slice_pl.nc; a.ncs = slice_pl.ncs; a.ms = slice_pl.ms;
+        a.cx_log2 = slice_pl.cx_log2; a.l_log2 = slice_pl.l_log2; a.lt_log2 = slice_pl.lt_log2;
         a.Y = Y; a.ld = ld;
         a.x = x; a.xp = xp; a.d = d; a.stp = stp; a.stp_dev = stp_dev;
         a.Gv = Gv.p; a.w = w.p; a.aux_n = aux_n.p; a.aux_n2 = aux_n2.p; a.grad = grad; a.ddir = ddir;
@@ -865,16 +866,12 @@ class Context {
             if (!pe_trace.p) pe_trace.alloc(64);
             a.trace = pe_trace.p;
         }
+        // algorithmic passes of the evaluation (the kernel reads the matrix once).  No per-pass events here: a launch is
+        // a whole evaluation of ~20 us, and two timing events around it cost a visible share of that.
         const int npass = method == 0 ? (mode == kPEvalBoth ? 2 : 1) : (mode == kPEvalBoth ? 4 : 2);
-        const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
-        if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
         void* args[] = {(void*)&a};
         CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)slice_eval_kernel, dim3(slice_pl.grid), dim3(kSliceThreads),
                                                args, slice_pl.smem, stream));
-        if (timed) {
-            CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
-            pass_ev_passes += npass - 1;
-        }
         passes_launched += npass;
         ++kernels_launched;
         ++persistent_launches;

@@ -30,18 +30,22 @@
 
 namespace bioen {
 
-constexpr int kSliceThreads = 256;
+constexpr int kSliceThreads = 512;   // one CTA per SM: 16 warps hide the latency of the dependent sweeps (8 do not)
 constexpr int kSliceWarps = kSliceThreads / 32;
-constexpr int kSliceGP = 160;    // row stride of the [row][cta] tables (>= max CTAs, multiple of 32)
-constexpr int kSliceHdr = 8;     // scalar rows ahead of the M row sums: m_c, S_c, and the prior sums
+constexpr int kSliceGP = 160;    // most CTAs of a launch
+constexpr int kSliceHdr = 8;     // scalars ahead of the M row sums in a CTA's table record: m_c, S_c, the prior sums
 constexpr int kSliceMinCols = 8; // fewest columns per CTA
 
 struct SliceArgs {
     int method, mode;    // method 0 log-weights / 1 forces; mode = PEvalMode
     int M, N;
     int nc;              // columns per CTA (even)
-    int cx_log2;         // column reduce: 2^cx_log2 threads along the columns, 256 >> cx_log2 row groups
+    int ncs;             // row stride of the slice in shared memory (even, = 2 mod 4: at most 2-way bank conflicts
+                         // when the lanes of a warp walk down a column)
+    int ms;              // stride of a CTA's record in the tables (>= kSliceHdr + M)
+    int cx_log2;         // column reduce: 2^cx_log2 threads along the columns, kSliceThreads >> cx_log2 row groups
     int l_log2;          // row reduce: 2^l_log2 lanes per row
+    int lt_log2;         // table rows: 2^lt_log2 lanes per row
     const double* Y;
     long long ld;
     double* x;           // variables: N (logw) / M (forces)
@@ -60,8 +64,8 @@ struct SliceArgs {
     double* avg;
     double theta;
     double* sc;
-    double* tab;         // [(kSliceHdr + M)][kSliceGP]   phase A
-    double* gtab;        // [M][kSliceGP]                 forces: gradient contributions
+    double* tab;         // [grid][ms]   phase A: {m_c, S_c, prior sums ..., A_c,i}
+    double* gtab;        // [grid][ms]   forces: gradient contributions g_c,i
     double* part;        // [grid][3]                     scalars of the final grid reduction
     unsigned long long* bar;
     unsigned int* ticket;
@@ -121,8 +125,8 @@ __device__ __forceinline__ double slice_block_max(double v, double* red) {
     return m;
 }
 
-// out_j = sum_i coef_i (y_ij - sub_i), j < nv.   Threads are laid out CX along the columns x RS = 256 / CX row groups
-// (tall, narrow slices keep all threads busy); the row groups are added in a fixed order through `scratch`.
+// out_j = sum_i coef_i (y_ij - sub_i), j < nv.   Threads are laid out CX along the columns x RS = threads / CX row
+// groups (tall, narrow slices keep all threads busy); the row groups are added in a fixed order through `scratch`.
 template <bool SUB>
 __device__ __forceinline__ void slice_col_reduce(const double* __restrict__ sl, int ncs, int M, int nv,
                                                  const double* __restrict__ coef, const double* __restrict__ sub,
@@ -149,16 +153,18 @@ __device__ __forceinline__ void slice_col_reduce(const double* __restrict__ sl, 
     if (RS > 1) {
         __syncthreads();
         if (tid < nv) {
-            double s = 0.0;
-            for (int q = 0; q < RS; ++q) s += scratch[q * CX + tid];
-            out[tid] = s;
+            double s0 = 0.0, s1 = 0.0;
+            int q = 0;
+            for (; q + 1 < RS; q += 2) { s0 += scratch[q * CX + tid]; s1 += scratch[(q + 1) * CX + tid]; }
+            out[tid] = s0 + s1;   // RS is a power of two >= 2
         }
     }
     __syncthreads();
 }
 
-// f(i, sum_j (y_ij - sub_i) v_j) for every row i < M, called by one lane.  L = 2^l_log2 lanes share a row (L < 32 for
-// narrow slices: a warp then takes 32 / L rows at a time); fixed-order shuffle sum.
+// f(i, sum_j (y_ij - sub_i) v_j) for every row i < M, called by one lane.  L = 2^l_log2 lanes share a row (the host
+// picks L so that one sweep of the CTA covers about all rows: L = 1, a thread per row, for tall slices; a whole warp
+// per row for flat ones); fixed-order shuffle sum.
 template <bool SUB, class F>
 __device__ __forceinline__ void slice_row_reduce(const double* __restrict__ sl, int ncs, int M, int nv,
                                                  const double* __restrict__ v, const double* __restrict__ sub,
@@ -186,44 +192,41 @@ __device__ __forceinline__ void slice_row_reduce(const double* __restrict__ sl, 
     }
 }
 
-// f(i, sum_c tab[i][c] * scale[c]) for every row i < M of a [row][cta] table (scale == nullptr: plain sums), the
-// contributions added in CTA order.  Many CTAs: a warp per row, four rows in flight; few CTAs: a thread per row.
+// f(i, sum_c rec_c[i] * scale[c]) for every row i < M of the per-CTA records `tab` (stride ms; scale == nullptr: plain
+// sums), the contributions added in CTA order.  LT = 2^lt_log2 lanes share a row (LT = 1 for tall problems: consecutive
+// threads read consecutive entries of one record, the G loads of a thread are independent and pipeline).
 template <bool SCALE, class F>
-__device__ __forceinline__ void slice_table_rows(const double* __restrict__ tab, int M, int G,
-                                                 const double* __restrict__ scale, F f) {
+__device__ __forceinline__ void slice_table_rows(const double* __restrict__ tab, int ms, int M, int G,
+                                                 const double* __restrict__ scale, int lt_log2, F f) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (G >= 16) {
-        for (int i0 = wid; i0 < M; i0 += 4 * kSliceWarps) {
-            double s[4];
+    const int L = 1 << lt_log2, RPW = 32 >> lt_log2;
+    const int lc = lane & (L - 1), sr = lane >> lt_log2;
+    const int rows_per_sweep = kSliceWarps * RPW;
+    for (int base = 0; base < M; base += rows_per_sweep) {
+        const int i = base + wid * RPW + sr;
+        double acc0 = 0.0, acc1 = 0.0;
+        if (i < M) {
+            // 8 independent loads in flight per thread: every CTA reads the whole table right after the barrier, and
+            // with two loads per dependent step this phase was pure L2 latency (19 us at 1000 x 777)
+            const double* col = tab + i;
+            for (int c = lc; c < G; c += 8 * L) {
+                double t[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kSliceWarps;
-                s[u] = 0.0;
-                if (i < M) {
-                    const double* row = tab + (size_t)i * kSliceGP;
-                    for (int c = lane; c < G; c += 32) {
-                        const double t = __ldcg(row + c);
-                        s[u] = SCALE ? fma(t, scale[c], s[u]) : s[u] + t;
-                    }
+                for (int u = 0; u < 8; ++u) {
+                    const int cc = c + u * L;
+                    t[u] = cc < G ? __ldcg(col + (size_t)cc * ms) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const int ca = c + u * L, cb = ca + L;
+                    if (ca < G) acc0 = SCALE ? fma(t[u], scale[ca], acc0) : acc0 + t[u];
+                    if (cb < G) acc1 = SCALE ? fma(t[u + 1], scale[cb], acc1) : acc1 + t[u + 1];
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kSliceWarps;
-                const double t = warp_sum(s[u]);
-                if (lane == 0 && i < M) f(i, t);
-            }
         }
-    } else {
-        for (int i = tid; i < M; i += kSliceThreads) {
-            const double* row = tab + (size_t)i * kSliceGP;
-            double s = 0.0;
-            for (int c = 0; c < G; ++c) {
-                const double t = __ldcg(row + c);
-                s = SCALE ? fma(t, scale[c], s) : s + t;
-            }
-            f(i, s);
-        }
+        double acc = acc0 + acc1;
+        for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lc == 0 && i < M) f(i, acc);
     }
 }
 
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
     __shared__ double s_val[16];
     __shared__ bool s_last;
     const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
-    const int M = a.M, nc = a.nc, ncs = a.nc;
+    const int M = a.M, nc = a.nc, ncs = a.ncs, ms = a.ms;
     const int Mp = (M + 1) & ~1;
     const int c0 = b * nc;
     const int nv = min(nc, a.N - c0);   // >= 1: the host launches ceil(N / nc) CTAs
@@ -245,10 +248,14 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
     double* vc = ve + nc;                                 // [nc]  column sums
     double* vr = vc + nc;                                 // [Mp]  coefficients of the column reduce: f_i, later r_i
     double* vavg = vr + Mp;                               // [Mp]  avg_i
+    double* vobs = vavg + Mp;                             // [Mp]  Yobs_i
+    double* vg = vobs + Mp;                               // [nc]  G_j (logw) / w0_j (forces)
+    double* vd = vg + nc;                                 // [nc]  logw: direction d_j of the slope grad . d
+    double* mytab = a.tab + (size_t)b * ms;
     int mk = 0;
     slice_mark(a, mk);
 
-    // ---- the slice: M rows x ceil2(nv) columns, 16-byte cp.async (row starts are 16-byte aligned: ld and c0 even)
+    // ---- the slice: M rows x ceil2(nv) columns, 16-byte cp.async (row starts are 16-byte aligned: ld, c0, ncs even)
     {
         const int hw = (nv + 1) >> 1;
         const double* src = a.Y + c0;
@@ -260,10 +267,13 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
     }
     const double stp = a.stp_dev ? __ldg(a.stp_dev) : a.stp;
     const double theta = a.theta;
+    if (a.mode != kPEvalGradient)
+        for (int i = tid; i < M; i += kSliceThreads) vobs[i] = a.Yobs[i];
 
     if (a.method == 0) {
         // =========================================================================== log-weights
         double gbar, Gbar;
+        const double logS0 = (tid == 0 && b == 0) ? a.sc[SC_LOGS0] : 0.0;   // constant of the problem: fetched early
         if (a.mode != kPEvalGradient) {
             // ---- A: trial point, CTA-local maximum, e_j, S_c and the prior sums, ||x||^2
             double m = -DBL_MAX, xn = 0.0;
@@ -273,13 +283,15 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
                 if (a.xp) { x = fma(stp, a.d[j], a.xp[j]); a.x[j] = x; }
                 else x = a.x[j];
                 vx[jj] = x;
+                vg[jj] = a.Gv[j];
+                vd[jj] = a.ddir ? a.ddir[j] : 0.0;
                 xn = fma(x, x, xn);
                 m = fmax(m, x);
             }
             const double mloc = slice_block_max(m, red);
             double v[5] = {0.0, 0.0, 0.0, 0.0, xn};
             for (int jj = tid; jj < nv; jj += kSliceThreads) {
-                const double g = vx[jj], Gj = a.Gv[c0 + jj];
+                const double g = vx[jj], Gj = vg[jj];
                 const double e = exp(g - mloc);
                 ve[jj] = e;
                 v[0] += e;
@@ -289,34 +301,29 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
             }
             block_sum<5>(v, red);
             if (tid == 0) {
-                a.tab[0 * kSliceGP + b] = mloc;
-                a.tab[1 * kSliceGP + b] = v[0];
-                a.tab[2 * kSliceGP + b] = v[1];
-                a.tab[3 * kSliceGP + b] = v[2];
-                a.tab[4 * kSliceGP + b] = v[3];
-                a.tab[5 * kSliceGP + b] = v[4];
+                mytab[0] = mloc; mytab[1] = v[0]; mytab[2] = v[1]; mytab[3] = v[2]; mytab[4] = v[3]; mytab[5] = v[4];
             }
             cp_async_commit_wait_all();
             __syncthreads();
             slice_mark(a, mk);
-            slice_row_reduce<false>(sl, ncs, M, nv, ve, nullptr, a.l_log2, [&](int i, double sum) {
-                a.tab[(size_t)(kSliceHdr + i) * kSliceGP + b] = sum;
-            });
+            slice_row_reduce<false>(sl, ncs, M, nv, ve, nullptr, a.l_log2,
+                                    [&](int i, double sum) { mytab[kSliceHdr + i] = sum; });
             slice_mark(a, mk);
             const bool ok = slice_grid_barrier(a.bar);
             slice_mark(a, mk);
             // ---- B: every CTA combines the G contributions in CTA order (identical values everywhere)
-            const double mc = tid < G ? __ldcg(a.tab + 0 * kSliceGP + tid) : -DBL_MAX;
+            double mc = -DBL_MAX, t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (tid < G) {   // the six scalars of CTA `tid`, one L2 round trip
+                const double* rec = a.tab + (size_t)tid * ms;
+                mc = __ldcg(rec);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) t[k] = __ldcg(rec + 1 + k);
+            }
             const double mx = slice_block_max(mc, red);
-            double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             if (tid < G) {
                 const double s = exp(mc - mx);
                 s_scale[tid] = s;
-                t[0] = __ldcg(a.tab + 1 * kSliceGP + tid) * s;
-                t[1] = __ldcg(a.tab + 2 * kSliceGP + tid) * s;
-                t[2] = __ldcg(a.tab + 3 * kSliceGP + tid) * s;
-                t[3] = __ldcg(a.tab + 4 * kSliceGP + tid) * s;
-                t[4] = __ldcg(a.tab + 5 * kSliceGP + tid);
+                t[0] *= s; t[1] *= s; t[2] *= s; t[3] *= s;
             }
             block_sum<5>(t, red);
             if (tid == 0) {
@@ -328,9 +335,9 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
             const double S = s_val[0], inv = s_val[1];
             gbar = s_val[3]; Gbar = s_val[4];
             double c[1] = {0.0};
-            slice_table_rows<true>(a.tab + (size_t)kSliceHdr * kSliceGP, M, G, s_scale, [&](int i, double sum) {
+            slice_table_rows<true>(a.tab + kSliceHdr, ms, M, G, s_scale, a.lt_log2, [&](int i, double sum) {
                 const double av = sum * inv;
-                const double r = av - a.Yobs[i];
+                const double r = av - vobs[i];
                 vavg[i] = av;
                 vr[i] = r;
                 if (b == 0) {
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
             block_sum<1>(c, red);
             if (tid == 0 && b == 0) {
                 const double chi2 = 0.5 * c[0];
-                const double prior = (s_val[2] - (mx + log(S)) + a.sc[SC_LOGS0]) * theta;
+                const double prior = (s_val[2] - (mx + log(S)) + logS0) * theta;
                 a.sc[SC_LSE_MAX] = mx; a.sc[SC_LSE_SUM] = S; a.sc[SC_XNORM2] = s_val[5];
                 a.sc[SC_GMAX] = mx; a.sc[SC_S] = S;
                 a.sc[SC_GBAR] = gbar; a.sc[SC_CAPGBAR] = Gbar;
@@ -364,6 +371,8 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
             for (int jj = tid; jj < nv; jj += kSliceThreads) {
                 vx[jj] = a.x[c0 + jj];
                 ve[jj] = a.w[c0 + jj];
+                vg[jj] = a.Gv[c0 + jj];
+                vd[jj] = a.ddir ? a.ddir[c0 + jj] : 0.0;
             }
             for (int i = tid; i < M; i += kSliceThreads) {
                 const double2 q = reinterpret_cast<const double2*>(a.ab)[i];
@@ -380,9 +389,9 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
         for (int jj = tid; jj < nv; jj += kSliceThreads) {
             const int j = c0 + jj;
             const double w = ve[jj];
-            const double gr = w * theta * (vx[jj] - gbar - a.Gv[j] + Gbar) + w * vc[jj];
+            const double gr = w * theta * (vx[jj] - gbar - vg[jj] + Gbar) + w * vc[jj];
             a.grad[j] = gr;
-            if (a.ddir) dg = fma(gr, a.ddir[j], dg);
+            dg = fma(gr, vd[jj], dg);
             gn = fma(gr, gr, gn);
             gi = fmax(gi, fabs(gr));
         }
@@ -406,6 +415,7 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
                 vr[i] = x;
                 c[0] = fma(x, x, c[0]);
             }
+            for (int jj = tid; jj < nv; jj += kSliceThreads) vg[jj] = a.Gv[c0 + jj];
             block_sum<1>(c, red);
             if (tid == 0 && b == 0) a.sc[SC_XNORM2] = c[0];
         }
@@ -419,34 +429,32 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
         double v[2] = {0.0, 0.0};
         for (int jj = tid; jj < nv; jj += kSliceThreads) {
             const double xr = vx[jj] - mloc;
-            const double u = a.Gv[c0 + jj] * exp(xr);
+            const double u = vg[jj] * exp(xr);
             ve[jj] = u;
             v[0] += u;
             v[1] = fma(xr, u, v[1]);
         }
         block_sum<2>(v, red);
-        if (tid == 0) {
-            a.tab[0 * kSliceGP + b] = mloc;
-            a.tab[1 * kSliceGP + b] = v[0];
-            a.tab[2 * kSliceGP + b] = v[1];
-        }
+        if (tid == 0) { mytab[0] = mloc; mytab[1] = v[0]; mytab[2] = v[1]; }
         __syncthreads();   // ve complete
-        slice_row_reduce<false>(sl, ncs, M, nv, ve, nullptr, a.l_log2, [&](int i, double sum) {
-            a.tab[(size_t)(kSliceHdr + i) * kSliceGP + b] = sum;
-        });
+        slice_row_reduce<false>(sl, ncs, M, nv, ve, nullptr, a.l_log2,
+                                [&](int i, double sum) { mytab[kSliceHdr + i] = sum; });
         slice_mark(a, mk);
         const bool ok = slice_grid_barrier(a.bar);
         slice_mark(a, mk);
         // ---- B: global (max, S), KL, avg, r, chi^2, objective -- in every CTA, CTA order
-        const double mc = tid < G ? __ldcg(a.tab + 0 * kSliceGP + tid) : -DBL_MAX;
+        double mc = -DBL_MAX, Sc = 0.0, Kc = 0.0;
+        if (tid < G) {
+            const double* rec = a.tab + (size_t)tid * ms;
+            mc = __ldcg(rec); Sc = __ldcg(rec + 1); Kc = __ldcg(rec + 2);
+        }
         const double mx = slice_block_max(mc, red);
         double t[2] = {0.0, 0.0};
         if (tid < G) {
             const double s = exp(mc - mx);
-            const double Sc = __ldcg(a.tab + 1 * kSliceGP + tid);
             s_scale[tid] = s;
             t[0] = Sc * s;
-            t[1] = s * fma(mc - mx, Sc, __ldcg(a.tab + 2 * kSliceGP + tid));
+            t[1] = s * fma(mc - mx, Sc, Kc);
         }
         block_sum<2>(t, red);
         if (tid == 0) {
@@ -457,9 +465,9 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
         __syncthreads();
         const double S = s_val[0], inv = s_val[1], logS = s_val[2];
         double c[1] = {0.0};
-        slice_table_rows<true>(a.tab + (size_t)kSliceHdr * kSliceGP, M, G, s_scale, [&](int i, double sum) {
+        slice_table_rows<true>(a.tab + kSliceHdr, ms, M, G, s_scale, a.lt_log2, [&](int i, double sum) {
             const double av = sum * inv;
-            const double r = av - a.Yobs[i];
+            const double r = av - vobs[i];
             vavg[i] = av;
             vr[i] = r;
             if (b == 0) {
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
         const double wscale = s_scale[b] * inv;
         for (int jj = tid; jj < nv; jj += kSliceThreads) {
             const int j = c0 + jj;
-            const double x = vx[jj], w0 = a.Gv[j];
+            const double x = vx[jj], w0 = vg[jj];
             const double w = ve[jj] * wscale;
             const double lr = (w >= DBL_MIN && w0 >= DBL_MIN) ? (x - mx - logS) : 0.0;
             ve[jj] = w;
@@ -511,9 +519,10 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
         a.aux_n[c0 + jj] = E;
     }
     __syncthreads();
-    slice_row_reduce<true>(sl, ncs, M, nv, ve, vavg, a.l_log2, [&](int i, double sum) {
-        a.gtab[(size_t)i * kSliceGP + b] = sum;
-    });
+    {
+        double* myg = a.gtab + (size_t)b * ms;
+        slice_row_reduce<true>(sl, ncs, M, nv, ve, vavg, a.l_log2, [&](int i, double sum) { myg[i] = sum; });
+    }
     slice_mark(a, mk);
     // the CTA that arrives last adds the contributions in CTA order
     __syncthreads();
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
     __threadfence();
     {
         double dg = 0.0, gn = 0.0, gi = 0.0;
-        slice_table_rows<false>(a.gtab, M, G, nullptr, [&](int i, double sum) {
+        slice_table_rows<false>(a.gtab, ms, M, G, nullptr, a.lt_log2, [&](int i, double sum) {
             a.grad[i] = sum;
             if (a.ddir) dg = fma(sum, a.ddir[i], dg);
             gn = fma(sum, sum, gn);
@@ -553,35 +562,44 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_eval_kernel(const Slic
 // ---- host side: geometry of a launch -------------------------------------------------------------------------
 struct SlicePlan {
     bool ok = false;
-    int nc = 0, grid = 0, cx_log2 = 0, l_log2 = 0;
+    int nc = 0, ncs = 0, ms = 0, grid = 0, cx_log2 = 0, l_log2 = 0, lt_log2 = 0;
     size_t smem = 0;
 };
 
-// Columns per CTA: at least N / SMs (one CTA per SM), at least ~0.75 sqrt(N) -- the combination after the barrier reads
-// grid x M table entries per CTA, the sweeps M x nc slice entries, so narrow problems use fewer, wider CTAs -- and
-// at least kSliceMinCols.  Not eligible when the slice does not fit in shared memory or the table gets large.
+// Columns per CTA: at least N / SMs (one CTA per SM), at least ~sqrt(N) / 2 -- after the barrier every CTA reads
+// grid x M table entries, the sweeps touch M x nc slice entries, so narrow problems use fewer, wider CTAs -- and at
+// least kSliceMinCols.  Not eligible when the slice does not fit in shared memory or the table gets large.
 inline SlicePlan slice_plan(int M, int N, int num_sms, size_t max_dyn_smem) {
     SlicePlan p;
     auto even_up = [](long long v) { return (int)((v + 1) & ~1LL); };
+    auto pow2_floor_log2 = [](long long v) { int c = 0; while ((2LL << c) <= v) ++c; return c; };
     const int sms = num_sms < kSliceGP ? num_sms : kSliceGP;
     int nc = even_up((N + sms - 1) / sms);
     int root = 1;
     while ((long long)root * root < N) ++root;
-    nc = std::max(nc, even_up((3LL * root + 3) / 4));
+    nc = std::max(nc, even_up((root + 1) / 2));
     nc = std::max(nc, kSliceMinCols);
+    const int ncs = (nc % 4 == 0) ? nc + 2 : nc;
     const int grid = (N + nc - 1) / nc;
     const size_t Mp = ((size_t)M + 1) & ~(size_t)1;
-    const size_t smem = ((size_t)M * nc + 3 * (size_t)nc + 2 * Mp) * sizeof(double);
+    const size_t smem = ((size_t)M * ncs + 5 * (size_t)nc + 3 * Mp) * sizeof(double);
+    const int ms = (int)((kSliceHdr + (size_t)M + 15) & ~(size_t)15);
     if (smem > max_dyn_smem || grid > sms) return p;
-    if ((size_t)grid * (size_t)(M + kSliceHdr) * sizeof(double) > ((size_t)512 << 10)) return p;
+    if ((size_t)grid * (size_t)ms * sizeof(double) > ((size_t)1 << 20)) return p;
     p.ok = true;
     p.nc = nc;
+    p.ncs = ncs;
+    p.ms = ms;
     p.grid = grid;
     p.smem = smem;
     int c = 0;
-    while ((1 << c) < nc && c < 8) ++c;
-    p.cx_log2 = c;              // min(256, pow2ceil(nc))
-    p.l_log2 = c < 5 ? c : 5;   // min(32, pow2ceil(nc))
+    while ((1 << c) < nc && (1 << c) < kSliceThreads) ++c;
+    p.cx_log2 = c;                                  // min(threads, pow2ceil(nc)) threads along the columns
+    const int per_row = pow2_floor_log2(std::max(1, kSliceThreads / M));   // lanes per row so that one sweep covers M
+    p.l_log2 = std::min(std::min(per_row, 5), c);   // ... at most a warp, at most pow2ceil(nc)
+    int g = 0;
+    while ((1 << g) < grid) ++g;
+    p.lt_log2 = std::min(std::min(per_row, 5), g);
     return p;
 }
 

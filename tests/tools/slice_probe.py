@@ -14,13 +14,16 @@ import bioen_b200  # noqa: E402
 dev = torch.device("cuda", 0)
 steps = int(os.environ.get("STEPS", "200"))
 shapes = ((28, 50001), (808, 10), (808, 100), (64, 64), (100, 20000), (500, 2049), (1000, 777), (40, 76000))
+if os.environ.get("SLICE_PROBE_SHAPES"):      # e.g. "28x50001,808x10"
+    shapes = tuple(tuple(int(v) for v in s.split("x")) for s in os.environ["SLICE_PROBE_SHAPES"].split(","))
+only = [int(v) for v in os.environ.get("SLICE_PROBE_PATHS", "2,1,0").split(",")]
 for (M, N) in shapes:
     rng = np.random.default_rng(1)
     a = rng.standard_normal(M)
     YT = a + rng.standard_normal(M)
     with bioen_b200.Problem(shape=(M, N)) as p:
         p.generate(12345, 0, a, 2.0)
-        for mode in (2, 1, 0):
+        for mode in only:
             p.set_option(5, 1 if mode else 0)
             p.set_option(8, 1 if mode == 2 else 0)
             if mode == 2 and p.query(7) != 1:
@@ -39,7 +42,7 @@ for (M, N) in shapes:
                       (M, N, name, mode, p.pass_kernel_name(meth), 1e3 * ms / steps, launches // steps), flush=True)
         # whole minimisations (host loop included)
         import time
-        for mode in (2, 1):
+        for mode in [m for m in only if m]:
             p.set_option(5, 1)
             p.set_option(8, 1 if mode == 2 else 0)
             if mode == 2 and p.query(7) != 1:
