@@ -293,6 +293,8 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
             case BIOEN_B200_OPT_PERSISTENT: ctx->C.persistent_mode = value; break;
             case BIOEN_B200_OPT_LBFGS_GRAM: ctx->C.lbfgs_gram_opt = value != 0; break;
             case BIOEN_B200_OPT_SLICE: ctx->C.slice_mode = value; break;
+            case BIOEN_B200_OPT_LBFGS_SMALL: ctx->C.lbfgs_small_opt = value != 0; break;
+            case BIOEN_B200_OPT_LBFGS_SPECULATIVE: ctx->C.lbfgs_speculative = value != 0; break;
             case BIOEN_B200_OPT_FP32_STORAGE:
                 CUDA_CHECK(cudaSetDevice(ctx->C.device));
                 ctx->pending_gen = -1;

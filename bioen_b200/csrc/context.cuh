@@ -141,6 +141,8 @@ class Context {
     DevBuf<double> lbfgs_store;   // g, xp, gp, d, s[m], y[m] of the device L-BFGS (lbfgs.cuh)
     DevBuf<double> lbfgs_gram, lbfgs_gram_partials;   // coefficient-space update (BIOEN_B200_OPT_LBFGS_GRAM)
     bool lbfgs_gram_opt = false;
+    bool lbfgs_small_opt = true;     // BIOEN_B200_OPT_LBFGS_SMALL: single-kernel update for n <= 1024
+    bool lbfgs_speculative = true;   // BIOEN_B200_LBFGS_SPECULATIVE=0: fetch the initial slope before the first trial
     long long ldt = 0, f_nslab = 0, f_chunk = 0;
     int f_C = 0, f_stages = 0, f_grid = 0, f_KI = 0, f_smem = 0, f_T = 1, f_rows = 0, f_rows_per_cta = 1;
     bool f_team = false;
@@ -245,6 +247,8 @@ class Context {
             coop_ok = coop && (long long)per_sm * num_sms >= grid;
             if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
             if (const char* e = getenv("BIOEN_B200_LBFGS_GRAM")) lbfgs_gram_opt = e[0] == '1';
+            if (const char* e = getenv("BIOEN_B200_LBFGS_SMALL")) lbfgs_small_opt = e[0] != '0';
+            if (const char* e = getenv("BIOEN_B200_LBFGS_SPECULATIVE")) lbfgs_speculative = e[0] != '0';
             if (const char* e = getenv("BIOEN_B200_PERSISTENT_MAX_MB")) persistent_max_bytes = atof(e) * 1.0e6;
             // slice kernel: plan once per context (M, N are fixed), tables only when the problem is eligible
             cudaFuncAttributes fa{};
@@ -289,6 +293,7 @@ class Context {
         eval_fused = false;
         forces_x = nullptr;
         lbfgs_gram_opt = getenv("BIOEN_B200_LBFGS_GRAM") != nullptr && getenv("BIOEN_B200_LBFGS_GRAM")[0] == '1';
+        lbfgs_small_opt = !(getenv("BIOEN_B200_LBFGS_SMALL") && getenv("BIOEN_B200_LBFGS_SMALL")[0] == '0');
         persistent_mode = -1;
         if (const char* e = getenv("BIOEN_B200_PERSISTENT")) persistent_mode = atoi(e);
         slice_mode = -1;

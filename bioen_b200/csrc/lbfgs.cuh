@@ -417,6 +417,10 @@ class Lbfgs {
             if (forces) C.forces_eval_f(x, xp_, dir, stp);
             else C.logw_eval_f(x, xp_, dir, stp);
             C.fetch_scalars();
+            if (take_spec_slope()) {
+                ++stats.evaluations;
+                return true;
+            }
             if (ls->needs_slope(C.h_sc[SC_F])) {
                 if (forces) C.forces_eval_g(g, ddir);
                 else C.logw_eval_g(x, g, ddir);
@@ -493,7 +497,21 @@ class Lbfgs {
             }
         }
         // More-Thuente reads the slope of every trial: plain f+g evaluation, one read-back
-        if (!eval(xp, d, stp, d, (prm.linesearch != 0 && C.lazy_gradient) ? &ls : nullptr)) C.fetch_scalars();
+        if (!eval(xp, d, stp, d, (prm.linesearch != 0 && C.lazy_gradient) ? &ls : nullptr)) {
+            C.fetch_scalars();
+            take_spec_slope();
+        }
+    }
+    // first trial of a search whose initial slope was not fetched beforehand: it is in the scalar file just read
+    bool spec_slope = false, spec_bad = false;
+    LineSearchState* spec_ls = nullptr;
+    bool take_spec_slope() {
+        if (!spec_slope) return false;
+        spec_slope = false;
+        const double dg0 = C.h_sc[SC_DGINIT];
+        spec_ls->set_slope(dg0);
+        spec_bad = 0 < dg0;
+        return spec_bad;
     }
 
     void enqueue_update(int end_old, int bound, int m) {
@@ -529,9 +547,26 @@ class Lbfgs {
         // sharded runs need the in-kernel exchange (the peer-memory path); m is liblbfgs' default 6
         return C.lbfgs_gram_opt && prm.m == kGramM && (!reduce || C.fuse_exchange());
     }
+    // small problems (n <= 1024): pair + two-loop recursion as ONE single-CTA kernel (k_lbfgs_update_small)
+    bool small_mode() const {
+        return C.lbfgs_small_opt && n <= kSmallUpdateMaxN && prm.m == kSmallUpdateM && !reduce;
+    }
+    void enqueue_update_small(int end_old, int bound) {
+        NvtxRange nvtx("bioen:lbfgs_update(small)");
+        SmallUpdateArgs a{};
+        a.n = n; a.x = x; a.g = g; a.xp = xp; a.gp = gp; a.d = d;
+        for (int t = 0; t < kSmallUpdateM; ++t) { a.S[t] = S[t]; a.Y[t] = Yv[t]; }
+        a.end = end_old; a.bound = bound; a.sc = C.sc.p;
+        k_lbfgs_update_small<<<1, ((n + 31) / 32) * 32, 0, C.stream>>>(a);
+        ++C.kernels_launched;
+    }
     void update_direction(int end_old, int bound, int m) {
         if (gram_mode()) {
             enqueue_update_gram(end_old, bound);
+            return;
+        }
+        if (small_mode()) {
+            enqueue_update_small(end_old, bound);
             return;
         }
         if (use_graphs) {
@@ -605,18 +640,31 @@ class Lbfgs {
     int linesearch(double& f, double& stp, double& dginit, bool& dginit_known) {
         const double* h = C.h_sc;
         if (stp <= 0.) return LBFGSERR_INVALIDPARAMETERS;
-        if (!dginit_known) {
-            // g.d of the new direction was left in the scalar file by the last two-loop kernel
+        // g.d of the new direction was left in the scalar file (SC_DGINIT) by the update kernels.  The first trial
+        // point xp + stp*d does not depend on it, so the trial is enqueued right behind the update and the slope
+        // arrives with the trial's own scalars: one host round trip per iteration instead of two.  (The one case
+        // where the slope matters beforehand -- 0 < g.d, LBFGSERR_INCREASEGRADIENT -- then costs one evaluation
+        // that liblbfgs would not have made; x and g are restored by the caller as after any failed search.)
+        spec_slope = !dginit_known && !use_graphs && C.lbfgs_speculative;
+        if (!dginit_known && !spec_slope) {
             C.fetch_scalars();
             dginit = h[SC_DGINIT];
             dginit_known = true;
         }
-        if (0 < dginit) return LBFGSERR_INCREASEGRADIENT;
+        if (dginit_known && 0 < dginit) return LBFGSERR_INCREASEGRADIENT;
         LineSearchState ls;
-        ls.start(prm, f, dginit, stp);
+        ls.start(prm, f, dginit_known ? dginit : 0.0, stp);
+        spec_ls = &ls;
         for (;;) {
             stp = ls.prepare();
             trial(stp, ls);
+            if (spec_bad) {   // the slope that came with the first trial is positive
+                spec_bad = false;
+                dginit = h[SC_DGINIT];
+                dginit_known = true;
+                return LBFGSERR_INCREASEGRADIENT;
+            }
+            if (!dginit_known) { dginit = ls.dginit; dginit_known = true; }
             f = h[SC_F];
             const int verdict = ls.update(f, h[SC_DG]);
             if (verdict != 0) return verdict;

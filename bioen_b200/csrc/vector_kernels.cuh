@@ -747,6 +747,126 @@ __global__ void __launch_bounds__(kVecThreads) k_lbfgs_twoloop(const TwoLoopArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// L-BFGS update for SMALL n (n <= 1024: the forces method, and log-weights problems with few structures -- every
+// fixture of the reference's test-suite): k_lbfgs_pair + the 2*bound+1 kernels of the two-loop recursion as ONE
+// single-CTA kernel.  Thread j owns element j of every vector and keeps d_j, g_j and the six (s, y) pairs in
+// registers; the 2*bound+2 dot products are block reductions (one __syncthreads each), the coefficients are formed from
+// the same raw dot products in the same order as k_lbfgs_twoloop does, and the same scalar-file slots are written.
+// 15 launches of ~3 us become one of ~5 us -- at these sizes the update, not the evaluation, was most of an iteration.
+// For n <= 256 (one block in the multi-kernel path as well) the result is bit-identical to that path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallUpdateMaxN = 1024;
+constexpr int kSmallUpdateM = 6;   // history length (liblbfgs default; BioEn never changes it)
+
+struct SmallUpdateArgs {
+    int n;
+    const double *x, *g;
+    double *xp, *gp, *d;
+    double* S[kSmallUpdateM];
+    double* Y[kSmallUpdateM];
+    int end;     // ring slot that receives the new pair
+    int bound;   // pairs in use (including the new one)
+    double* sc;
+};
+
+// all threads of the block get the sum; `red` is [2][32] and toggles so that one barrier per reduction is enough
+__device__ __forceinline__ double small_block_sum(double v, double (*red)[32], int& phase) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[phase][wid] = v;
+    __syncthreads();
+    const double t = warp_sum(lane < nw ? red[phase][lane] : 0.0);
+    phase ^= 1;
+    return t;
+}
+
+__device__ __forceinline__ double small_pick(const double (&v)[kSmallUpdateM], int k) {
+    double r = v[0];
+#pragma unroll
+    for (int t = 1; t < kSmallUpdateM; ++t) r = (k == t) ? v[t] : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(kSmallUpdateMaxN, 1) k_lbfgs_update_small(const SmallUpdateArgs a) {
+    __shared__ double red[2][32];
+    __shared__ double s_alpha[kSmallUpdateM], s_ys[kSmallUpdateM];
+    const int j = threadIdx.x;
+    const bool on = j < a.n;
+    int phase = 0;
+    double sv[kSmallUpdateM], yv[kSmallUpdateM];
+    // pairs already in the ring: slots end-1, end-2, ... (bound - 1 of them)
+#pragma unroll
+    for (int t = 0; t < kSmallUpdateM; ++t) {
+        const int age = (a.end - t + kSmallUpdateM) % kSmallUpdateM;   // 0 = the new pair
+        const bool used = on && age != 0 && age < a.bound;
+        sv[t] = used ? a.S[t][j] : 0.0;
+        yv[t] = used ? a.Y[t][j] : 0.0;
+    }
+    if (j < kSmallUpdateM) s_ys[j] = a.sc[SC_YS0 + j];
+    double g = 0.0, s_new = 0.0, y_new = 0.0;
+    if (on) {
+        const double x = a.x[j];
+        g = a.g[j];
+        s_new = x - a.xp[j];
+        y_new = g - a.gp[j];
+        a.xp[j] = x;
+        a.gp[j] = g;
+    }
+#pragma unroll
+    for (int t = 0; t < kSmallUpdateM; ++t) {
+        if (t == a.end) {
+            sv[t] = s_new;
+            yv[t] = y_new;
+            if (on) { a.S[t][j] = s_new; a.Y[t][j] = y_new; }
+        }
+    }
+    // ys = y.s, yy = y.y of the new pair (lbfgs.c:543-555)
+    const double ys = small_block_sum(y_new * s_new + 0.0, red, phase);
+    const double yy = small_block_sum(y_new * y_new + 0.0, red, phase);
+    if (j == 0) {
+        s_ys[a.end] = ys;
+        a.sc[SC_YS] = ys;
+        a.sc[SC_YY] = yy;
+        a.sc[SC_YS0 + a.end] = ys;
+    }
+    // two-loop recursion (lbfgs.c:572-598); slot of the i-th newest pair: (end - i) mod m
+    double dj = -g;
+    int slot = a.end;
+    double alpha_raw = small_block_sum(small_pick(sv, slot) * dj + 0.0, red, phase);   // also publishes s_ys
+    double beta_raw = 0.0;
+    for (int i = 0; i < a.bound; ++i) {
+        if (j == 0) { s_alpha[slot] = alpha_raw; a.sc[SC_ALPHA0 + slot] = alpha_raw; }
+        const double coef = -1.0 * (alpha_raw / s_ys[slot]);
+        dj = fma(coef, small_pick(yv, slot), dj);
+        if (i + 1 < a.bound) {
+            slot = (slot + kSmallUpdateM - 1) % kSmallUpdateM;
+            alpha_raw = small_block_sum(small_pick(sv, slot) * dj + 0.0, red, phase);
+        } else {
+            dj *= ys / yy;
+            beta_raw = small_block_sum(small_pick(yv, slot) * dj + 0.0, red, phase);
+        }
+    }
+    // slot = oldest pair now; s_alpha is complete (the last store is ordered by the barrier of the reduction above
+    // only for i + 1 < bound, so read the oldest alpha from the register)
+    double dginit = 0.0;
+    for (int i = a.bound - 1; i >= 0; --i) {
+        const double al = (i == a.bound - 1) ? alpha_raw : s_alpha[slot];
+        const double ysl = s_ys[slot];
+        double coef = 1.0 * (al / ysl);
+        coef += -1.0 * (beta_raw / ysl);
+        dj = fma(coef, small_pick(sv, slot), dj);
+        if (i > 0) {
+            slot = (slot + 1) % kSmallUpdateM;
+            beta_raw = small_block_sum(small_pick(yv, slot) * dj + 0.0, red, phase);
+        } else {
+            dginit = small_block_sum(g * dj + 0.0, red, phase);
+        }
+    }
+    if (on) a.d[j] = dj;
+    if (j == 0) a.sc[SC_DGINIT] = dginit;
+}
+
 // sharded twin of k_colgrad_finish (stream_pass.cuh): per-CTA partials summed in CTA order, then ONE exchange of
 // {grad.d, ||grad||^2, ||x||^2, max|grad|} between the ranks from this block
 __global__ void __launch_bounds__(256) k_colgrad_finish_sharded(int ncta, const double* cta_part, double* sc,

@@ -193,10 +193,18 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * the CTAs to hold their columns of yTilde in shared memory (up to ~30 MB in all, e.g. every fixture of the
  * reference's test-suite and the ala5 example) run an evaluation as ONE cooperative kernel with ONE grid barrier: the
  * matrix is read once per launch and every sweep runs out of shared memory (csrc/slice_eval.cuh).  Takes precedence
- * over the persistent kernel and the fused forces kernels; BIOEN_B200_OPT_PERSISTENT = 0 disables it as well. */
+ * over the persistent kernel and the fused forces kernels; BIOEN_B200_OPT_PERSISTENT = 0 disables it as well.
+ * BIOEN_B200_OPT_LBFGS_SMALL (default 1; environment BIOEN_B200_LBFGS_SMALL=0): minimisations over at most 1024
+ * variables (the forces method; log-weights with few structures) run the L-BFGS update -- the new (s, y) pair and the
+ * two-loop recursion -- as ONE single-CTA kernel instead of 15 launches; same arithmetic, bit-identical up to 256
+ * variables.
+ * BIOEN_B200_OPT_LBFGS_SPECULATIVE (default 1; environment BIOEN_B200_LBFGS_SPECULATIVE=0): the first trial of a line
+ * search is enqueued behind the update without fetching the initial slope first (it arrives with the trial's scalars):
+ * one host round trip per iteration instead of two.  Results are identical. */
 enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
        BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5, BIOEN_B200_OPT_LBFGS_GRAM = 6,
-       BIOEN_B200_OPT_FP32_STORAGE = 7, BIOEN_B200_OPT_SLICE = 8 };
+       BIOEN_B200_OPT_FP32_STORAGE = 7, BIOEN_B200_OPT_SLICE = 8, BIOEN_B200_OPT_LBFGS_SMALL = 9,
+       BIOEN_B200_OPT_LBFGS_SPECULATIVE = 10 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of

@@ -303,7 +303,12 @@ def test_theta_scan_forces_matches_single_runs(oracle, M, N, K):
             for q in sorted({0, K // 2, K - 1}):
                 p.set_theta(thetas[q])
                 x1, f1, c1, i1 = p.opt_lbfgs(np.zeros(M), linesearch=ls)
-                tol = 1e-8 if i1["iterations"] < 50 else 1e-6 if i1["iterations"] < 150 else 1e-4
+                # Runs that end on liblbfgs' progress rule ((f[k-10] - f[k]) / f[k] < delta = 1e-6) stop somewhere on
+                # a slow tail, and WHERE depends on the last bits of the trajectory: measured on the 1000 x 3001
+                # problem at theta = 3, the batched scan stops after 876 iterations at 380.0918, the single run
+                # after 646 at 380.1745 (2.2e-4 apart, both code 1) -- the tail still gains ~1e-6 per 10 iterations.
+                its = max(i1["iterations"], int(info["iterations"][q]))
+                tol = 1e-8 if its < 50 else 1e-6 if its < 150 else 1e-4 if its < 500 else 1e-3
                 # At large theta the forces problem converges to rounding level, where liblbfgs' line search
                 # fails or succeeds on the last bits of f (-998 / -1001 vs 0; the reference behaves the same,
                 # SURVEY.md section 7): then only the end point is compared.
@@ -371,3 +376,49 @@ def test_lazy_gradient_is_bit_identical(oracle):
                 p.set_option(3, 1)
     # the short cuts were actually taken (steepest descent only when one of its steps was rejected)
     assert skipped > 0 and all(c > 0 for c in continued[:4]), (skipped, continued)
+
+
+def test_small_update_kernel_and_speculative_trial(oracle):
+    """BIOEN_B200_OPT_LBFGS_SMALL (9): the (s, y) pair and the two-loop recursion as ONE single-CTA kernel for
+    n <= 1024 -- bit-identical to the 15-kernel path up to 256 variables (one block there as well), same end point
+    beyond.  BIOEN_B200_OPT_LBFGS_SPECULATIVE (10): the first trial of a line search enqueued before the initial
+    slope is fetched -- must not move a bit or an evaluation count, for any n."""
+    import bioen_b200
+    OPT_SMALL, OPT_SPEC = 9, 10
+    cases = []
+    d = load_golden("data_forces_M64xN64")
+    cases.append(("forces 64", d["yTilde"], lambda p: p.set_forces(d["w0"], d["YTilde"], d["theta"]),
+                  d["forces_init"].ravel(), True))
+    d2 = load_golden("data_potra_part_1_logw_M808xN80")
+    cases.append(("logw 80", d2["yTilde"], lambda p: p.set_logw(d2["G"], d2["YTilde"], d2["theta"]),
+                  d2["GInit"].ravel(), True))
+    d3 = load_golden("data_deer_test_forces_M808xN10")
+    cases.append(("forces 808", d3["yTilde"], lambda p: p.set_forces(d3["w0"], d3["YTilde"], d3["theta"]),
+                  d3["forces_init"].ravel(), False))
+    P = oracle.synthetic_problem(1000, 777, seed=5)
+    cases.append(("forces 1000", P["yTilde"], lambda p: p.set_forces(P["w0"], P["YTilde"], 10.0),
+                  P["forces_init"], False))
+    P2 = oracle.synthetic_problem(28, 5001, seed=6)
+    cases.append(("logw 5001 (speculative only)", P2["yTilde"], lambda p: p.set_logw(P2["G"], P2["YTilde"], 10.0),
+                  P2["GInit"], True))
+    for name, yT, setter, x0, bitwise in cases:
+        with bioen_b200.Problem(yT) as p:
+            setter(p)
+            for ls in (0, 2):
+                res = {}
+                for small, spec in ((0, 0), (0, 1), (1, 0), (1, 1)):
+                    p.set_option(OPT_SMALL, small)
+                    p.set_option(OPT_SPEC, spec)
+                    k0 = p.kernels_launched()
+                    res[small, spec] = p.opt_lbfgs(x0, linesearch=ls, max_iterations=50) + (p.kernels_launched() - k0,)
+                for small in (0, 1):      # speculative trial: identical bits and counts
+                    a, b = res[small, 0], res[small, 1]
+                    assert a[2] == b[2] and a[1] == b[1] and np.array_equal(a[0], b[0]), (name, ls, small)
+                    assert a[3] == b[3], (name, ls, small)
+                a, b = res[0, 1], res[1, 1]
+                if x0.size <= 1024:
+                    assert b[4] < a[4], (name, "fewer launches", a[4], b[4])
+                if bitwise:
+                    assert a[2] == b[2] and a[1] == b[1] and np.array_equal(a[0], b[0]), (name, ls)
+                else:
+                    assert a[2] == b[2] and rel(b[1], a[1]) < 1e-8, (name, ls, a[1], b[1], a[2], b[2])

@@ -48,10 +48,16 @@ for (M, N) in shapes:
             if mode == 2 and p.query(7) != 1:
                 continue
             p.set_forces(np.full(N, 1.0 / N), YT, 10.0)
-            best = 1e9
-            for _ in range(3):
-                t0 = time.perf_counter()
-                x, fmin, code, info = p.opt_lbfgs(np.zeros(M))
-                best = min(best, time.perf_counter() - t0)
-            print("M=%d N=%d forces L-BFGS path=%d: %.3f ms (%d it, %d evals, code %d, fmin %.10g)" %
-                  (M, N, mode, best * 1e3, info["iterations"], info["evaluations"], code, fmin), flush=True)
+            for small, spec in ((1, 1), (0, 0)):
+                p.set_option(9, small)
+                p.set_option(10, spec)
+                best = 1e9
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    x, fmin, code, info = p.opt_lbfgs(np.zeros(M))
+                    best = min(best, time.perf_counter() - t0)
+                print("M=%d N=%d forces L-BFGS path=%d small-update=%d speculative=%d: %.3f ms (%d it, %d evals, code %d, "
+                      "fmin %.10g)" % (M, N, mode, small, spec, best * 1e3, info["iterations"], info["evaluations"], code,
+                                       fmin), flush=True)
+            p.set_option(9, 1)
+            p.set_option(10, 1)
