@@ -146,7 +146,13 @@ def test_forces_find_optimum_series(oracle):
         assert rel(f1, r["fx"]) < (1e-8 if r["iterations"] < 150 else 1e-4)
         assert rel(thetas[q] * S + chi2, f1) < 1e-9
         assert np.allclose(yopt, P["y"] @ wopt.ravel(), rtol=1e-12, atol=1e-12)
-    seq = optimize.forces.find_optimum_series(P["forces_init"], P["w0"], P["y"], P["yTilde"], P["YTilde"], thetas[:3],
-                                              cfg, batched=False)
-    for a, b in zip(seq, out[:3]):
-        assert rel(a[4], b[4]) < 1e-6
+    # Warm-started sequential runs at large theta start next to their optimum: whether liblbfgs reports convergence or
+    # exhausts its line search at rounding level there (-998, objective equal to the optimum to 15 digits; measured
+    # at theta = 88.9 with the slice kernel's rounding, code 0 with the tile kernels') depends on the last bits --
+    # the reference raises in that case as well (c_bioen.pyx:516-520).  strict=False yields None for such a theta.
+    seq = optimize.forces.find_optimum_series(P["forces_init"], P["w0"], P["y"], P["yTilde"], P["YTilde"], thetas[:4],
+                                              cfg, batched=False, strict=False)
+    assert sum(a is not None for a in seq) >= 3
+    for a, b in zip(seq, out[:4]):
+        if a is not None:
+            assert rel(a[4], b[4]) < 1e-6
