@@ -358,6 +358,10 @@ def roofline_hbm(M, N, pass_ms, step_ms, kernel, traffic=None, read_gbs=None):
     r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
          "peak_source": peak_src, "kernel": kernel + " (one pass over yTilde)", "bytes_per_launch": alg,
          "ms_per_launch": pass_ms, "step_frac": (2 * alg) / (step_ms * 1e-3) / 1e9 / peak if step_ms > 0 else None}
+    if kernel in ("persistent_eval_kernel", "slice_eval_kernel"):
+        r["kernel"] = kernel + " (one launch per evaluation)"
+        r["ms_per_launch_is"] = "the step time divided by the algorithmic passes of an evaluation (2 log-weights, " \
+                                "4 forces on the tile path): the launch is not bracketed by events of its own"
     if read_gbs:
         r["read_only_stream"] = {"gbs": read_gbs, "frac_of_it": ach / read_gbs,
                                  "what": "plain 16-byte-load read kernel over the same yTilde, mean of 10 launches, "
@@ -441,7 +445,11 @@ def small_workload(name, M, N, local, dev, steps, warmup):
                    "time_to_optimum": {"seconds": secs, "code": code, "fmin": fmin, "iterations": info["iterations"],
                                        "evaluations": info["evaluations"]},
                    "time_to_optimum_coefficient_space": gram_optimum(prob, nvar)}
-            if M * N * 8 <= 100e6:
+            if prob.query(7) == 1:
+                rec["roofline"]["note"] = ("yTilde (%.1f MB) is dealt column-wise into the CTAs' shared memory and read "
+                                           "ONCE per evaluation (from L2 when resident there); every sweep runs out of "
+                                           "shared memory, the HBM figure is nominal" % (M * N * 8 / 1e6))
+            elif M * N * 8 <= 100e6:
                 rec["roofline"]["note"] = ("yTilde (%.1f MB) is L2-resident: the second pass of a step is served from "
                                            "L2, the HBM figure is nominal" % (M * N * 8 / 1e6))
             out[mname] = rec

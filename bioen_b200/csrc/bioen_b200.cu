@@ -111,6 +111,24 @@ __global__ void __launch_bounds__(256) k_generate(double* Y, long long ld, int m
     }
 }
 
+// the same matrix written structure-major (BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY): Yt[j][i] = yTilde_ij
+__global__ void __launch_bounds__(256) k_generate_t(double* Yt, long long ldt, int m, int n, unsigned long long seed,
+                                                     long long col_offset, const double* a, double b) {
+    const long long total = (long long)m * n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t / m);
+        const int i = (int)(t - (long long)j * m);
+        const unsigned long long ctr = ((unsigned long long)i << 40) + (unsigned long long)(col_offset + j);
+        const unsigned long long h1 = mix64(seed + 0x9E3779B97F4A7C15ULL * (ctr + 1));
+        const unsigned long long h2 = mix64(h1 + 0x9E3779B97F4A7C15ULL);
+        const double u1 = ((double)(h1 >> 11) + 1.0) * 0x1.0p-53;  // (0, 1]
+        const double u2 = (double)(h2 >> 11) * 0x1.0p-53;          // [0, 1)
+        const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        Yt[(size_t)j * ldt + i] = fma(b, z, a[i]);
+    }
+}
+
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------------
@@ -189,7 +207,13 @@ int bioen_b200_upload_ytilde(bioen_b200_ctx* ctx, const double* yTilde_host, siz
     return guarded("bioen_b200_upload_ytilde", [&] {
         ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
-        ctx->C.upload_matrix(yTilde_host, ld);
+        if (ctx->C.yt_only) {
+            if (ld < (size_t)ctx->C.N) throw std::invalid_argument("bioen_b200: row stride smaller than N");
+            ctx->C.alloc_yt();
+            ctx->C.upload_rows_yt(0, ctx->C.M, yTilde_host, ld);
+        } else {
+            ctx->C.upload_matrix(yTilde_host, ld);
+        }
         ctx->C.sync();
     });
 }
@@ -198,6 +222,7 @@ int bioen_b200_adopt_ytilde(bioen_b200_ctx* ctx, double* yTilde_dev, size_t ld) 
     return guarded("bioen_b200_adopt_ytilde", [&] {
         ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
+        ctx->C.require_row_major("adopting a row-major device matrix");
         ctx->C.adopt_matrix(yTilde_dev, ld);
     });
 }
@@ -207,9 +232,14 @@ int bioen_b200_upload_rows(bioen_b200_ctx* ctx, int row0, int nrows, const doubl
         ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
-        if (!C.Y) C.alloc_matrix();
         if (row0 < 0 || nrows < 0 || row0 + nrows > C.M) throw std::invalid_argument("bioen_b200: rows out of range");
         if (ld < (size_t)C.N) throw std::invalid_argument("bioen_b200: row stride smaller than N");
+        if (C.yt_only) {
+            C.upload_rows_yt(row0, nrows, rows_host, ld);
+            C.fused_ready = false;
+            return;
+        }
+        if (!C.Y) C.alloc_matrix();
         CUDA_CHECK(cudaMemcpy2DAsync(C.Y + (size_t)row0 * C.ld, C.ld * sizeof(double), rows_host, ld * sizeof(double),
                                      (size_t)C.N * sizeof(double), nrows, cudaMemcpyHostToDevice, C.stream));
         C.sync();
@@ -232,7 +262,8 @@ int bioen_b200_alloc_ytilde(bioen_b200_ctx* ctx) {
     return guarded("bioen_b200_alloc_ytilde", [&] {
         ctx->pending_gen = -1;
         CUDA_CHECK(cudaSetDevice(ctx->C.device));
-        ctx->C.alloc_matrix();
+        if (ctx->C.yt_only) ctx->C.alloc_yt();
+        else ctx->C.alloc_matrix();
     });
 }
 
@@ -295,6 +326,12 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
             case BIOEN_B200_OPT_SLICE: ctx->C.slice_mode = value; break;
             case BIOEN_B200_OPT_LBFGS_SMALL: ctx->C.lbfgs_small_opt = value != 0; break;
             case BIOEN_B200_OPT_LBFGS_SPECULATIVE: ctx->C.lbfgs_speculative = value != 0; break;
+            case BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY:
+                CUDA_CHECK(cudaSetDevice(ctx->C.device));
+                if (value) ctx->C.enter_yt_only();
+                else if (ctx->C.yt_only)
+                    throw std::invalid_argument("bioen_b200: the row-major matrix is gone; create a new context");
+                break;
             case BIOEN_B200_OPT_FP32_STORAGE:
                 CUDA_CHECK(cudaSetDevice(ctx->C.device));
                 ctx->pending_gen = -1;
@@ -390,6 +427,7 @@ int bioen_b200_affine_rows(bioen_b200_ctx* ctx, const double* scale_host, const 
         ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
+        C.require_row_major("a row-affine transform");
         if (C.storage_fp32) throw std::logic_error("bioen_b200: row-affine transforms need the fp64 matrix (fp32 storage is on)");
         if (!C.Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         if (!C.Yown.p) throw std::logic_error("bioen_b200: an adopted matrix belongs to the caller and is not modified");
@@ -570,6 +608,7 @@ int bioen_b200_theta_scan(bioen_b200_ctx* ctx, int method, int K, const double* 
         ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
+        C.require_row_major("the batched theta scan");
         const auto t0 = std::chrono::steady_clock::now();
         ThetaScan scan(C, K, to_params(config), method == BIOEN_B200_FORCES);
         scan.verbose = (int)visual.verbose;
@@ -867,8 +906,10 @@ int bioen_b200_time_evals(bioen_b200_ctx* ctx, int method, double* x_dev, double
         if (ms) *ms = total;
         if (launches) *launches = bioen_b200_kernels_launched(ctx) - k0;
         float pm = C.end_pass_timing();
-        // slice kernel: a launch is a whole evaluation (no per-pass events); report the step's share per algorithmic pass
-        if (pm == 0.f && C.slice_ok() && steps > 0) pm = total / (float)steps / (forces ? 4.f : 2.f);
+        // one-launch evaluations (slice kernel): no per-pass events; report the step's share per algorithmic pass
+        // (the same for the persistent kernel: its launches are not bracketed by events either)
+        if (pm == 0.f && steps > 0 && C.persistent_for(forces) && (!forces || C.have_forces))
+            pm = total / (float)steps / (forces ? 4.f : 2.f);
         if (pass_ms) *pass_ms = pm;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
@@ -881,6 +922,16 @@ int bioen_b200_generate_ytilde(bioen_b200_ctx* ctx, unsigned long long seed, lon
         ctx->pending_gen = -1;
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
+        if (C.yt_only) {
+            C.alloc_yt();
+            C.h2d(C.avg.p, ytrue_over_sigma_host, C.M);
+            k_generate_t<<<C.num_sms * 8, 256, 0, C.stream>>>(C.Yt.p, C.ldt, C.M, C.N, seed, col_offset, C.avg.p, inv_sigma);
+            CUDA_CHECK(cudaGetLastError());
+            ++C.kernels_launched;
+            ++C.eval_gen;
+            C.sync();
+            return;
+        }
         if (!C.Y) C.alloc_matrix();
         C.h2d(C.avg.p, ytrue_over_sigma_host, C.M);
         k_generate<<<C.num_sms * 8, 256, 0, C.stream>>>(C.Y, C.ld, C.M, C.N, seed, col_offset, C.avg.p, inv_sigma);
@@ -896,6 +947,12 @@ int bioen_b200_download_ytilde(bioen_b200_ctx* ctx, int row0, int nrows, long lo
         Context& C = ctx->C;
         CUDA_CHECK(cudaSetDevice(C.device));
         if (C.storage_fp32) throw std::logic_error("bioen_b200: the resident matrix is stored in fp32 (no fp64 copy to download)");
+        if (C.yt_only) {
+            if (row0 < 0 || nrows <= 0 || row0 + nrows > C.M || col0 < 0 || ncols <= 0 || col0 + ncols > C.N)
+                throw std::invalid_argument("bioen_b200: block out of range");
+            C.download_yt(row0, nrows, col0, ncols, out_host);
+            return;
+        }
         if (!C.Y) throw std::logic_error("bioen_b200: no matrix");
         if (row0 < 0 || nrows < 0 || row0 + nrows > C.M || col0 < 0 || ncols < 0 || col0 + ncols > C.N)
             throw std::invalid_argument("bioen_b200: block out of range");
@@ -921,6 +978,8 @@ long long bioen_b200_query(bioen_b200_ctx* ctx, int what) {
         case 5: return C.persistent_launches;
         case 6: return C.slice_launches;
         case 7: return C.slice_ok() ? 1 : 0;
+        case 8: return (long long)((C.Yown.p ? C.Yown.n * 8 : 0) + (C.Yt.p ? C.Yt.n * 8 : 0) + (C.Y32.p ? C.Y32.n * 4 : 0));
+        case 9: return C.yt_only ? 1 : 0;
         default: return -1;
     }
 }

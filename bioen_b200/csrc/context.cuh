@@ -304,6 +304,7 @@ class Context {
         Y = nullptr;
         storage_fp32 = false;
         Y32.release();
+        yt_only = false;
         passes_launched = kernels_launched = 0;
         pass_timing = false;
     }
@@ -499,6 +500,7 @@ class Context {
 
     // logw: reference log-weights G (this rank's slice); log s0 = log sum_j exp(G_j) over ALL ranks
     void set_logw(const double* G_host, bool on_device = false) {
+        require_row_major("the log-weights method");
         ++eval_gen;
         Gv.ensure(Npad + 8);
         if (on_device) d2d(Gv.p, G_host, N); else h2d(Gv.p, G_host, N);
@@ -531,7 +533,10 @@ class Context {
         aux_n2.ensure(Npad + 8);  // lr_j
         have_forces = true;
         have_logw = false;        // Gv now holds w0
-        if (allow_fused && Y && !storage_fp32 && !fused_ready) prepare_fused();
+        if (allow_fused && (Y || yt_only) && !storage_fp32 && !fused_ready) prepare_fused();
+        if (yt_only && !fused_ready)
+            throw std::logic_error("bioen_b200: structure-major-only mode: the fused forces kernels are not available "
+                                   "for this problem (BIOEN_B200_OPT_FUSED_FORCES = 0, or M outside 256..~5500)");
     }
 
     // ---- fused two-pass forces path ------------------------------------------------------------------------
@@ -539,6 +544,85 @@ class Context {
         const long long l = (M + 1LL) & ~1LL;
         return !storage_fp32 && M >= kFMinM && l <= kFMaxLdt;
     }
+    // ---- structure-major ONLY (BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY) ----------------------------------------------
+    // The forces method on the fused two-pass kernels reads nothing but Yt.  In this mode the context never holds
+    // the row-major matrix: uploads are transposed chunk by chunk through a small staging buffer, the generator
+    // writes Yt directly, an existing matrix is transposed once and released.  Half the HBM of the default forces
+    // set-up (both layouts): N = 1e6 x M = 1e3 needs 8 GB instead of 16, config 5 (400 GB) fits 4 GPUs.  Available:
+    // forces evaluations and minimisers, weights, averages (through the fused kernels), downloads.  Everything that
+    // streams the row-major matrix (log-weights method, tile / persistent / slice kernels, theta scan, row-affine
+    // transforms, given-weights entry points) raises.
+    bool yt_only = false;
+    DevBuf<double> yt_stage;
+    void require_row_major(const char* what) const {
+        if (yt_only)
+            throw std::logic_error(std::string("bioen_b200: ") + what + " needs the row-major matrix, which this context "
+                                   "does not hold (BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY: forces method on the fused kernels only)");
+    }
+    void alloc_yt() {
+        ldt = (M + 1LL) & ~1LL;
+        if (Yt.n != (size_t)N * ldt || !Yt.p) {
+            Yt.release();
+            CUDA_CHECK(cudaMalloc(&Yt.p, (size_t)N * ldt * sizeof(double)));
+            Yt.n = (size_t)N * ldt;
+        }
+        CUDA_CHECK(cudaMemsetAsync(Yt.p, 0, (size_t)N * ldt * sizeof(double), stream));   // pad column (odd M) stays 0
+        yt_valid = true;
+        fused_ready = false;
+        evict_first = ((double)N * (double)ldt * 8.0 > 80.0e6) ? 1 : 0;
+    }
+    void enter_yt_only() {
+        if (yt_only) return;
+        if (storage_fp32) throw std::logic_error("bioen_b200: structure-major-only mode needs the fp64 matrix");
+        if (!fused_eligible())
+            throw std::invalid_argument("bioen_b200: structure-major-only mode needs the fused forces kernels "
+                                        "(256 <= M <= 8192)");
+        ++eval_gen;
+        if (Y) {   // a row-major matrix is resident: one transposition, then it goes (an adopted one stays with its owner)
+            if (!yt_valid) make_transposed();
+            sync();
+            Y = nullptr;
+            fused_ready = false;
+        }
+        Yown.release();   // also the allocation a reused (cached) context kept from its previous problem
+        yt_only = true;
+        have_logw = false;
+    }
+    // rows [row0, row0 + nrows) of the HOST matrix -> Yt, staged through <= 256 MB of device memory
+    void upload_rows_yt(int row0, int nrows, const double* host, size_t ld_host) {
+        if (!Yt.p || !yt_valid) alloc_yt();
+        const long long lds = round_up(N, 2);
+        const int rows_per_chunk = (int)std::max<long long>(1, std::min<long long>(nrows, ((long long)256 << 20) / (lds * 8)));
+        yt_stage.reserve((size_t)rows_per_chunk * lds);
+        for (int r = 0; r < nrows; r += rows_per_chunk) {
+            const int nr = std::min(rows_per_chunk, nrows - r);
+            CUDA_CHECK(cudaMemcpy2DAsync(yt_stage.p, lds * sizeof(double), host + (size_t)r * ld_host,
+                                         ld_host * sizeof(double), (size_t)N * sizeof(double), nr,
+                                         cudaMemcpyHostToDevice, stream));
+            dim3 g((unsigned)((N + 31) / 32), (unsigned)((nr + 31) / 32));
+            k_transpose_block<<<g, 256, 0, stream>>>(yt_stage.p, lds, nr, N, Yt.p, ldt, row0 + r);
+            CUDA_CHECK(cudaGetLastError());
+            ++kernels_launched;
+            sync();   // the staging buffer is reused by the next chunk (and the host rows may be pageable)
+        }
+        ++eval_gen;
+    }
+    // block [row0, row0+nrows) x [col0, col0+ncols) of Yt -> host, row-major
+    void download_yt(int row0, int nrows, long long col0, long long ncols, double* out_host) {
+        if (!Yt.p || !yt_valid) throw std::logic_error("bioen_b200: no matrix");
+        const int rows_per_chunk = (int)std::max<long long>(1, std::min<long long>(nrows, ((long long)256 << 20) / (ncols * 8)));
+        yt_stage.reserve((size_t)rows_per_chunk * ncols);
+        for (int r = 0; r < nrows; r += rows_per_chunk) {
+            const int nr = std::min(rows_per_chunk, nrows - r);
+            dim3 g((unsigned)((ncols + 31) / 32), (unsigned)((nr + 31) / 32));
+            k_gather_block<<<g, 256, 0, stream>>>(Yt.p, ldt, row0 + r, nr, col0, ncols, yt_stage.p, ncols);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaMemcpyAsync(out_host + (size_t)r * ncols, yt_stage.p, (size_t)nr * ncols * sizeof(double),
+                                       cudaMemcpyDeviceToHost, stream));
+            sync();
+        }
+    }
+
     // structure-major copy Yt[j][i] of the resident matrix (the reference's yTildeT cache, made on the device)
     void make_transposed() {
         NvtxRange nvtx("bioen:transpose_ytilde");
@@ -643,13 +727,13 @@ class Context {
         }
     }
     template <int KIND>
-    void launch_fused(const double* bvec, const double* s0, const double* s1, double* xout) {
+    void launch_fused(const double* bvec, const double* s0, const double* s1, double* xout, double theta_arg = -1.0) {
         const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
         {
             TeamArgs a{};
             a.Yt = Yt.p; a.ldt = ldt; a.M = M; a.N = N; a.C = f_C; a.stages = f_stages; a.nslab = f_nslab;
-            a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta; a.xout = xout;
+            a.chunk = f_chunk; a.ab = ab.p; a.b = bvec; a.s0 = s0; a.s1 = s1; a.theta = theta_arg >= 0.0 ? theta_arg : theta; a.xout = xout;
             a.part = fpart.p; a.ldp = Mpad; a.lse = flse.p; a.evict_first = evict_first;
 #define BIOEN_LAUNCH_TEAM(KI_, T_) fused_team_pass<KI_, T_, KIND><<<f_grid, kTThreads, f_smem, stream>>>(a)
             BIOEN_TEAM_DISPATCH(BIOEN_LAUNCH_TEAM);
@@ -781,6 +865,7 @@ class Context {
         a.vN = vN; a.vMb = vMb; a.ab = ab.p;
         a.partial = (MODE == kRowPass) ? partialA.p : partialB.p;
         a.ld = (MODE == kRowPass) ? Mpad : Npad;
+        require_row_major("this evaluation path (tile kernels)");
         if (!has_matrix()) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
@@ -933,7 +1018,11 @@ class Context {
         // (the kernel's own passes and their readers always use the contiguous tile order, whatever the stand-alone
         // kernels of this context are configured for)
         const int npass = method == 0 ? (mode == kPEvalBoth ? 2 : 1) : (mode == kPEvalBoth ? 4 : 2);
-        const bool timed = pass_timing && pass_ev_used + 2 <= pass_ev.size();
+        // per-launch events only on request (BIOEN_B200_PERSISTENT_EVENTS=1): a launch is a whole evaluation, so the
+        // callers that time evaluations (bioen_b200_time_evals) derive the per-pass figure from the step time instead
+        // of paying two timing events per launch inside the timed region
+        static const bool launch_events = getenv("BIOEN_B200_PERSISTENT_EVENTS") != nullptr;
+        const bool timed = launch_events && pass_timing && pass_ev_used + 2 <= pass_ev.size();
         if (timed) CUDA_CHECK(cudaEventRecord(pass_ev[pass_ev_used++], stream));
         // Cooperative launch = the driver's guarantee that all CTAs are resident (the grid barriers need it).
         // BIOEN_B200_PERSISTENT_PLAIN=1 (diagnostics): an ordinary launch, which is resident as well when nothing
@@ -1104,7 +1193,7 @@ class Context {
         if (grad) forces_eval_g(grad, ddir);
     }
     double* forces_x = nullptr;   // the forces vector of the last objective half (persistent gradient half)
-    bool forces_fused_now() const { return fused_ready && allow_fused; }
+    bool forces_fused_now() const { return fused_ready && (allow_fused || yt_only); }
     void forces_eval_f(double* x, const double* xp, const double* d, double stp, const double* stp_dev = nullptr) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         ++eval_gen;
@@ -1172,6 +1261,10 @@ class Context {
     // weights only (the reference's _get_weights_from_forces): leaves normalised w in `w`
     void forces_weights_only(double* x) {
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
+        if (yt_only) {   // the objective half of the fused path leaves the normalised weights in `w`
+            forces_eval_f(x, nullptr, nullptr, 0.0);
+            return;
+        }
         ++eval_gen;
         ForcesUpdateArgs u{M, x, nullptr, nullptr, 0.0, ab.p, sc.p, nullptr};
         k_forces_update<<<1, 1024, 0, stream>>>(u);
@@ -1189,6 +1282,7 @@ class Context {
     // (reference semantics of _bioen_log_posterior_forces / _grad_bioen_log_posterior_forces,
     // c_bioen_kernels_forces.c:227-340)
     void forces_from_weights(double* grad) {
+        require_row_major("the given-weights forces objective");
         ++eval_gen;
         if (!have_forces) throw std::logic_error("bioen_b200: forces data not set");
         {
@@ -1225,6 +1319,20 @@ class Context {
     // avg = Y . v for an arbitrary N-vector v already in `w` (post-processing: yopt = y . wopt)
     void average_of_w(double* avg_out_dev) {
         ++eval_gen;
+        if (yt_only) {
+            // the gradient pass of the fused kernels with r = 0, lr = 0, avg = 0, theta = 1 accumulates
+            // sum_j y_ij * ((1 + 0) * 1 + 0) * w_j = (yTilde . w)_i -- one pass over Yt, summed over the ranks
+            if (!fused_ready) prepare_fused();
+            if (!fused_ready) throw std::logic_error("bioen_b200: structure-major-only mode: fused kernels unavailable");
+            aux_n2.ensure(Npad + 8);
+            CUDA_CHECK(cudaMemsetAsync(ab.p, 0, (size_t)2 * Mpad * sizeof(double), stream));
+            CUDA_CHECK(cudaMemsetAsync(avg.p, 0, (size_t)Mpad * sizeof(double), stream));
+            CUDA_CHECK(cudaMemsetAsync(aux_n2.p, 0, (size_t)(Npad + 8) * sizeof(double), stream));
+            launch_fused<kFusedGradient>(avg.p, w.p, aux_n2.p, nullptr, 1.0);
+            merge_fused_rows(false, 0);
+            d2d(avg_out_dev, msum.p, M);
+            return;
+        }
         launch_pass<kRowPass, false>(w.p, nullptr);
         k_reduce_row_slots<<<vec_blocks_m, kVecThreads, 0, stream>>>(M, partialA.p, Mpad, nCB, row_chunk(), msum.p);
         ++kernels_launched;

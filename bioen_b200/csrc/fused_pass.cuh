@@ -345,4 +345,49 @@ __global__ void __launch_bounds__(256) k_transpose(const double* __restrict__ Y,
     }
 }
 
+// Yt[j][row0 + r] = src[r][j] for a block of `nr` rows that arrived row-major (structure-major-only uploads)
+__global__ void __launch_bounds__(256) k_transpose_block(const double* __restrict__ src, long long lds, int nr, int N,
+                                                         double* __restrict__ Yt, long long ldt, int row0) {
+    __shared__ double tile[32][33];
+    const long long j0 = (long long)blockIdx.x * 32;
+    const int r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int i = r0 + r;
+        const long long j = j0 + tx;
+        tile[r][tx] = (i < nr && j < N) ? src[(size_t)i * lds + j] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const long long j = j0 + r;
+        const int i = r0 + tx;
+        if (j < N && i < nr) Yt[(size_t)j * ldt + row0 + i] = tile[tx][r];
+    }
+}
+
+// out[r][c] = Yt[col0 + c][row0 + r]  (downloads from the structure-major copy)
+__global__ void __launch_bounds__(256) k_gather_block(const double* __restrict__ Yt, long long ldt, int row0, int nr,
+                                                      long long col0, long long nc, double* __restrict__ out,
+                                                      long long ldo) {
+    __shared__ double tile[32][33];
+    const long long c0 = (long long)blockIdx.x * 32;
+    const int r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = ty; q < 32; q += 8) {
+        const long long c = c0 + q;
+        const int r = r0 + tx;
+        tile[q][tx] = (c < nc && r < nr) ? Yt[(size_t)(col0 + c) * ldt + row0 + r] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = ty; q < 32; q += 8) {
+        const int r = r0 + q;
+        const long long c = c0 + tx;
+        if (r < nr && c < nc) out[(size_t)r * ldo + c] = tile[tx][q];
+    }
+}
+
 }  // namespace bioen

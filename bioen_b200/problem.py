@@ -62,7 +62,9 @@ _PROBE_MAX = 1 << 18   # entries of x up to which objective() keeps a copy for g
 class Problem:
     """yTilde (m x n, this rank's columns when sharded) resident on one GPU."""
 
-    def __init__(self, yTilde=None, shape=None, device=0):
+    def __init__(self, yTilde=None, shape=None, device=0, structure_major_only=False):
+        """structure_major_only=True: the device keeps ONLY the structure-major copy of yTilde that the fused forces
+        kernels read (half the memory of the default forces set-up; forces method only, 256 <= M <= ~5500)."""
         self._lib = _lib.load()
         self._h = None
         if yTilde is not None:
@@ -81,6 +83,8 @@ class Problem:
             raise RuntimeError("bioen_b200_create failed: " + msg)
         self.method = None
         self.nranks = 1
+        if structure_major_only:
+            _lib.check(self._lib.bioen_b200_set_option(self._ctx, 11, 1), "set_option")
         if yTilde is not None:
             _lib.check(self._lib.bioen_b200_upload_ytilde(self._ctx, _lib.ptr(yT), self.n), "upload_ytilde")
 

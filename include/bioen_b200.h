@@ -200,11 +200,19 @@ int bioen_b200_set_theta(bioen_b200_ctx *ctx, double theta);
  * variables.
  * BIOEN_B200_OPT_LBFGS_SPECULATIVE (default 1; environment BIOEN_B200_LBFGS_SPECULATIVE=0): the first trial of a line
  * search is enqueued behind the update without fetching the initial slope first (it arrives with the trial's scalars):
- * one host round trip per iteration instead of two.  Results are identical. */
+ * one host round trip per iteration instead of two.  Results are identical.
+ * BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY (default 0; set to 1 before the matrix is uploaded / generated, or afterwards: the
+ * resident matrix is then transposed once and released): the context holds ONLY the structure-major copy that the
+ * fused two-pass forces kernels read -- half the device memory of the default forces set-up (which keeps both
+ * layouts), e.g. 8 GB instead of 16 GB at N = 1e6 x M = 1e3, and 100 GB per GPU instead of 200 GB for N = 1e7 x M = 5e3
+ * on 4 GPUs.  Uploads are transposed chunk by chunk through a 256 MB staging buffer, the generator writes the
+ * structure-major layout directly.  Available: forces evaluations and minimisers (256 <= M <= ~5500), weights,
+ * averages, downloads; the log-weights method, the theta scan, row-affine transforms and the given-weights entry
+ * points need the row-major matrix and fail with a message. */
 enum { BIOEN_B200_OPT_FUSED_FORCES = 1, BIOEN_B200_OPT_P2P = 2, BIOEN_B200_OPT_LAZY_GRADIENT = 3,
        BIOEN_B200_OPT_FUSED_EXCHANGE = 4, BIOEN_B200_OPT_PERSISTENT = 5, BIOEN_B200_OPT_LBFGS_GRAM = 6,
        BIOEN_B200_OPT_FP32_STORAGE = 7, BIOEN_B200_OPT_SLICE = 8, BIOEN_B200_OPT_LBFGS_SMALL = 9,
-       BIOEN_B200_OPT_LBFGS_SPECULATIVE = 10 };
+       BIOEN_B200_OPT_LBFGS_SPECULATIVE = 10, BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY = 11 };
 int bioen_b200_set_option(bioen_b200_ctx *ctx, int option, int value);
 
 /* one evaluation with host vectors.  grad_host may be NULL (objective only: one pass over yTilde instead of
@@ -314,7 +322,8 @@ long long bioen_b200_kernels_launched(bioen_b200_ctx *ctx);
  * 3: 1 if evaluations run as ONE persistent cooperative kernel with yTilde held in L2 (small problems);
  * 4: bytes per element of the resident matrix (8, or 4 with BIOEN_B200_OPT_FP32_STORAGE); 5: one-launch evaluations
  * (persistent or slice kernel) so far; 6: of those, launches of the shared-memory slice kernel; 7: 1 if evaluations
- * run on the slice kernel now.  Returns -1 for an unknown `what`. */
+ * run on the slice kernel now; 8: bytes of device memory held by the context's copies of yTilde (row-major +
+ * structure-major + fp32); 9: 1 in structure-major-only mode.  Returns -1 for an unknown `what`. */
 long long bioen_b200_query(bioen_b200_ctx *ctx, int what);
 int bioen_b200_debug_read(bioen_b200_ctx *ctx, int what, double *out_host, size_t count);
 /* the context's cudaStream_t (for callers that enqueue their own work around the device entry points) */
