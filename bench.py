@@ -74,6 +74,9 @@ def parse():
     ap.add_argument("--no-find-optimum", action="store_true", help="skip the public-API find_optimum timing")
     ap.add_argument("--no-dropin", action="store_true", help="skip the host-matrix drop-in call (needs M*N*8 B of host RAM)")
     ap.add_argument("--unfused-forces", action="store_true", help="forces: four tile passes instead of two fused")
+    ap.add_argument("--only-cfg5", action="store_true",
+                    help="N > 1: run only the BASELINE config-5 record (N=1e7 x M=5000 over 4 or 8 GPUs; a 50 GB shard "
+                         "per GPU otherwise) and print it as the line's extra_workloads")
     ap.add_argument("--theta-scan", type=int, default=0, metavar="K",
                     help="BASELINE config 4: K theta values (log-spaced 1e3..1e-1) minimised together; prints the "
                          "batched-evaluation line instead of the single-theta one")
@@ -479,6 +482,15 @@ def run_b200(args):
         from bioen_b200.dist import bind_to_gpu_numa
         numa_cpus = bind_to_gpu_numa(local)      # before the pinned host vectors of the e2e leg are allocated
 
+    if args.only_cfg5:
+        if world < 2:
+            raise SystemExit("bench.py --only-cfg5 needs N > 1 GPUs (torchrun)")
+        recs = cfg5_records(rank, world, local, dev, min(args.steps, 10), not args.no_optimum)
+        if rank == 0:
+            emit({"metric": METRIC, "n_gpus": world, "only": "config 5", "data": "synthetic", "dtype": "f64",
+                  "extra_workloads": recs})
+        dist.destroy_process_group()
+        return
     M = args.m
     if args.strong:
         from bioen_b200.dist import shard_bounds
@@ -724,10 +736,7 @@ def run_b200(args):
             # (d) strong scaling of config 3 (N = 1e6 in total over the GPUs) and a config-5 shard per GPU
             extra.append(sharded_record("config 3 strong: N=1e6 x M=1e3 in total", 1000, 1000000, True, rank, world,
                                         local, dev, es, ew, not args.no_optimum))
-            free_b, _tot = torch.cuda.mem_get_info(dev)
-            if free_b > 115e9:
-                extra.append(sharded_record("config 5 shard: N=1.25e6 x M=5000 per GPU (50 GB per GPU)", 5000, 1250000,
-                                            False, rank, world, local, dev, min(es, 10), 2, not args.no_optimum))
+            extra.extend(cfg5_records(rank, world, local, dev, es, not args.no_optimum))
         line["extra_workloads"] = extra
     else:
         prob.close()
@@ -735,6 +744,24 @@ def run_b200(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg5_records(rank, world, local, dev, es, want_optimum):
+    """BASELINE config 5 (N = 1e7 x M = 5000, 400 GB): the whole problem on 4 or 8 GPUs (100 / 50 GB per GPU), a 50 GB
+    shard per GPU otherwise.  The forces leg keeps only the structure-major copy, so both legs need ONE copy of the
+    shard per GPU."""
+    import torch
+    n_per = 10000000 // world if world in (4, 8) else 1250000
+    need = 5000.0 * n_per * 8.0 * 1.06 + 4e9
+    free_b, _tot = torch.cuda.mem_get_info(dev)
+    if free_b < need:
+        return []
+    if world in (4, 8):
+        name = "config 5: N=1e7 x M=5000 over %d GPUs (%d GB of yTilde per GPU)" % (world, round(5000 * n_per * 8 / 1e9))
+    else:
+        name = "config 5 shard: N=1.25e6 x M=5000 per GPU (50 GB per GPU)"
+    return [sharded_record(name, 5000, n_per, False, rank, world, local, dev, min(es, 10), 2, want_optimum,
+                           forces_structure_major_only=True)]
 
 
 def sharded_checks(prob, method, x_np, YT, N, n_total, dev, world):
@@ -776,9 +803,12 @@ def sharded_checks(prob, method, x_np, YT, N, n_total, dev, world):
     return out
 
 
-def sharded_record(name, M, n_arg, strong, rank, world, local, dev, steps, warmup, want_optimum):
-    """A second sharded problem of the same job (strong-scaled config 3, or a config-5 shard per GPU): logw and
-    forces f+g rates with the pass roofline, and the log-weights L-BFGS to the optimum."""
+def sharded_record(name, M, n_arg, strong, rank, world, local, dev, steps, warmup, want_optimum,
+                   forces_structure_major_only=False):
+    """A second sharded problem of the same job (strong-scaled config 3, or config 5): logw and forces f+g rates with
+    the pass roofline, and the log-weights L-BFGS to the optimum.  forces_structure_major_only: the forces leg runs on
+    a SECOND problem that holds only the structure-major copy of yTilde (generated directly in that layout, after the
+    row-major problem of the log-weights leg is closed), so the peak is ONE copy of the shard per GPU, not two."""
     import bioen_b200
     import torch
     import torch.distributed as dist
@@ -800,6 +830,12 @@ def sharded_record(name, M, n_arg, strong, rank, world, local, dev, steps, warmu
             if method == LOGW:
                 prob.set_logw(np.zeros(N), YT, THETA)
             else:
+                if forces_structure_major_only:
+                    prob.close()
+                    torch.cuda.empty_cache()
+                    prob = bioen_b200.Problem(shape=(M, N), device=local, structure_major_only=True)
+                    connect_problem(prob, rank, world, n_total, dev)
+                    prob.generate(SEED, col0, a, SIG_SIM / SIG_EXP)
                 prob.set_forces(np.full(N, 1.0 / n_total), YT, THETA)
             nvar = N if method == LOGW else M
             ms, pass_ms, launches = timed_evals(prob, method, nvar, dev, warmup, steps,
@@ -807,7 +843,10 @@ def sharded_record(name, M, n_arg, strong, rank, world, local, dev, steps, warmu
             rec = {"value": units * steps / (ms * 1e-3), "unit": "f+g evals/s (%s, summed over GPUs)"
                    % ("the whole N" if strong else "N-column blocks"), "ms_per_step": ms / steps,
                    "gpu_launches": launches, "exchange": prob.comm_mode(),
-                   "roofline": roofline_hbm(M, N, pass_ms, ms / steps, prob.pass_kernel_name(method))}
+                   "roofline": roofline_hbm(M, N, pass_ms, ms / steps, prob.pass_kernel_name(method)),
+                   "ytilde_bytes_resident_per_gpu": prob.query(8)}
+            if method == FORCES and forces_structure_major_only:
+                rec["layout"] = "structure-major copy only (BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY)"
             if want_optimum and (method == LOGW or M <= 1000):
                 dist.barrier()
                 torch.cuda.synchronize()
