@@ -458,6 +458,7 @@ class Context {
     // on the four tile passes (the same bytes as two fp64 passes).
     void convert_to_fp32() {
         if (storage_fp32) return;
+        require_row_major("the fp32 storage option");
         if (!Y) throw std::logic_error("bioen_b200: yTilde has not been uploaded");
         ++eval_gen;
         ld32 = round_up(N, 32);

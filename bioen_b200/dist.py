@@ -91,7 +91,9 @@ class ShardedProblem:
     Every rank passes the FULL host arrays (or its own slice with `presliced=True`); N-vectors returned by
     the methods are full-length (gathered), so the object can be used like `Problem` on every rank."""
 
-    def __init__(self, yTilde, device, group=None, presliced=False, n_total=None):
+    def __init__(self, yTilde, device, group=None, presliced=False, n_total=None, structure_major_only=False):
+        """structure_major_only: every rank keeps only the structure-major copy of its block (forces method on the
+        fused kernels, half the device memory; see Problem)."""
         import torch
         import torch.distributed as dist
         self.group = group
@@ -102,7 +104,7 @@ class ShardedProblem:
         self.lo, self.hi = shard_bounds(self.n_total, self.rank, self.world)
         local = yT if presliced else np.ascontiguousarray(yT[:, self.lo:self.hi])
         self.m = local.shape[0]
-        self.p = Problem(local, device=device)
+        self.p = Problem(local, device=device, **({"structure_major_only": True} if structure_major_only else {}))
         if self.world > 1:
             connect(self.p, self.n_total, group, self.tdev)
 
