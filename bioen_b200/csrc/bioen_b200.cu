@@ -326,6 +326,7 @@ int bioen_b200_set_option(bioen_b200_ctx* ctx, int option, int value) {
             case BIOEN_B200_OPT_SLICE: ctx->C.slice_mode = value; break;
             case BIOEN_B200_OPT_LBFGS_SMALL: ctx->C.lbfgs_small_opt = value != 0; break;
             case BIOEN_B200_OPT_LBFGS_SPECULATIVE: ctx->C.lbfgs_speculative = value != 0; break;
+            case BIOEN_B200_OPT_FETCH_ZEROCOPY: ctx->C.fetch_zero_copy = value != 0; break;
             case BIOEN_B200_OPT_STRUCTURE_MAJOR_ONLY:
                 CUDA_CHECK(cudaSetDevice(ctx->C.device));
                 if (value) ctx->C.enter_yt_only();

@@ -497,7 +497,9 @@ class Lbfgs {
             }
         }
         // More-Thuente reads the slope of every trial: plain f+g evaluation, one read-back
-        if (!eval(xp, d, stp, d, (prm.linesearch != 0 && C.lazy_gradient) ? &ls : nullptr)) {
+        // (not on the slice kernel: there a combined f+g launch costs ~4 us more than the objective alone, less than the
+        // second launch and host round trip the split costs the ~87 % of trials whose gradient IS read)
+        if (!eval(xp, d, stp, d, (prm.linesearch != 0 && C.lazy_gradient && !C.slice_ok()) ? &ls : nullptr)) {
             C.fetch_scalars();
             take_spec_slope();
         }

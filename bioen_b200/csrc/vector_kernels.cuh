@@ -46,6 +46,19 @@ enum ScalarSlot {
 
 constexpr int kVecThreads = 256;
 
+// the scalar file -> page-locked host memory (mapped), then a sequence number the host spins on (Context::fetch_scalars)
+__global__ void __launch_bounds__(64) k_publish_scalars(const double* __restrict__ sc, double* host_copy, int count,
+                                                        double* host_flag, double seq) {
+    const int i = threadIdx.x;
+    if (i < count) host_copy[i] = sc[i];
+    __threadfence_system();
+    __syncthreads();
+    if (i == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile double*>(host_flag) = seq;
+    }
+}
+
 // merge two (max, sum-of-exp) pairs
 __device__ __forceinline__ void lse_merge(double& m, double& s, double m2, double s2) {
     const double mm = fmax(m, m2);

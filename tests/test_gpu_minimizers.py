@@ -351,6 +351,7 @@ def test_lazy_gradient_is_bit_identical(oracle):
     for (M, N, theta) in ((100, 20000, 10.0), (50, 20000, 1.0), (300, 3001, 3.0)):
         P = oracle.synthetic_problem(M, N, seed=12345)
         with bioen_b200.Problem(P["yTilde"]) as p:
+            p.set_option(8, 0)     # (the L-BFGS driver does not split evaluations on the slice kernel: nothing to gain there)
             for method, setter, x0 in (("logw", lambda: p.set_logw(P["G"], P["YTilde"], theta), P["GInit"]),
                                        ("forces", lambda: p.set_forces(P["w0"], P["YTilde"], theta),
                                         P["forces_init"])):
@@ -422,3 +423,25 @@ def test_small_update_kernel_and_speculative_trial(oracle):
                     assert a[2] == b[2] and a[1] == b[1] and np.array_equal(a[0], b[0]), (name, ls)
                 else:
                     assert a[2] == b[2] and rel(b[1], a[1]) < 1e-8, (name, ls, a[1], b[1], a[2], b[2])
+
+
+def test_zero_copy_scalar_fetch_is_transparent(oracle):
+    """BIOEN_B200_OPT_FETCH_ZEROCOPY (12): the scalar file reaches the host through a one-warp kernel's stores into
+    page-locked memory instead of a copy-engine transfer.  Same values: every minimiser result is bit-identical."""
+    import bioen_b200
+    P = oracle.synthetic_problem(40, 6001, seed=3)
+    with bioen_b200.Problem(P["yTilde"]) as p:
+        for setter, x0 in ((lambda: p.set_logw(P["G"], P["YTilde"], 5.0), P["GInit"]),
+                           (lambda: p.set_forces(P["w0"], P["YTilde"], 5.0), P["forces_init"])):
+            setter()
+            out = []
+            for zc in (1, 0, 1):
+                p.set_option(12, zc)
+                a = p.opt_lbfgs(x0, max_iterations=30)
+                b = p.opt_gsl(x0, max_iterations=10)
+                f, g = p.objective_and_gradient(np.asarray(x0).ravel() + 0.01)
+                out.append((a, b, f, g))
+            for o in out[1:]:
+                assert o[0][1] == out[0][0][1] and o[0][2] == out[0][0][2] and np.array_equal(o[0][0], out[0][0][0])
+                assert o[1][1] == out[0][1][1] and o[1][2] == out[0][1][2] and np.array_equal(o[1][0], out[0][1][0])
+                assert o[2] == out[0][2] and np.array_equal(o[3], out[0][3])

@@ -48,16 +48,18 @@ for (M, N) in shapes:
             if mode == 2 and p.query(7) != 1:
                 continue
             p.set_forces(np.full(N, 1.0 / N), YT, 10.0)
-            for small, spec in ((1, 1), (0, 0)):
+            for small, spec, zc in ((1, 1, 1), (1, 1, 0), (0, 0, 0)):
                 p.set_option(9, small)
                 p.set_option(10, spec)
+                p.set_option(12, zc)
                 best = 1e9
                 for _ in range(3):
                     t0 = time.perf_counter()
                     x, fmin, code, info = p.opt_lbfgs(np.zeros(M))
                     best = min(best, time.perf_counter() - t0)
-                print("M=%d N=%d forces L-BFGS path=%d small-update=%d speculative=%d: %.3f ms (%d it, %d evals, code %d, "
-                      "fmin %.10g)" % (M, N, mode, small, spec, best * 1e3, info["iterations"], info["evaluations"], code,
-                                       fmin), flush=True)
+                print("M=%d N=%d forces L-BFGS path=%d small-update=%d speculative=%d zero-copy-fetch=%d: %.3f ms (%d it, "
+                      "%d evals, code %d, fmin %.10g)" % (M, N, mode, small, spec, zc, best * 1e3, info["iterations"],
+                                                          info["evaluations"], code, fmin), flush=True)
             p.set_option(9, 1)
             p.set_option(10, 1)
+            p.set_option(12, 1)
