@@ -101,6 +101,7 @@ SIGNATURES = {
     "bioen_b200_selftest_tilewalk": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                                    C.c_longlong, _ip, _ip, C.POINTER(C.c_longlong), _ip]),
     "bioen_b200_selftest_num_slots": (C.c_int, [C.c_longlong, C.c_longlong, C.c_longlong]),
+    "bioen_b200_selftest_slice_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_longlong)]),
     "bioen_b200_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "bioen_b200_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_longlong]),
     "bioen_b200_comm_init_local": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_longlong]),

@@ -776,6 +776,12 @@ long long bioen_b200_selftest_tilewalk(int pass_mode, int nRT, int nCB, int grid
     return n;
 }
 int bioen_b200_selftest_num_slots(long long run, long long L, long long chunk) { return pass_num_slots(run, L, chunk); }
+int bioen_b200_selftest_slice_plan(int m, int n, int sms, long long max_dyn_smem, long long out[8]) {
+    const SlicePlan p = slice_plan(m, n, sms, (size_t)max_dyn_smem);
+    out[0] = p.nc; out[1] = p.ncs; out[2] = p.ms; out[3] = p.grid;
+    out[4] = p.cx_log2; out[5] = p.l_log2; out[6] = p.lt_log2; out[7] = (long long)p.smem;
+    return p.ok ? 1 : 0;
+}
 
 int bioen_b200_nccl_unique_id(char id[128]) {
     return guarded("bioen_b200_nccl_unique_id", [&] { Comm::unique_id(id); });

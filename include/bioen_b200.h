@@ -290,6 +290,12 @@ double bioen_b200_selftest_interpolate(double a, double fa, double fpa, double b
 long long bioen_b200_selftest_tilewalk(int pass_mode, int nRT, int nCB, int grid, long long chunk, int interleave,
                                        int cta, long long max_tiles, int *rt, int *cb, long long *slot, int *closes);
 int bioen_b200_selftest_num_slots(long long run, long long L, long long chunk);
+/* host-only test hook: the launch geometry of the shared-memory slice kernel (csrc/slice_eval.cuh, slice_plan) for an
+ * m x n problem on a device with `sms` SMs and `max_dyn_smem` bytes of dynamic shared memory per CTA.  Returns 1 when
+ * the problem is eligible; out = {columns per CTA, row stride of the slice, record stride of the tables, CTAs,
+ * log2 threads along the columns (column sums), log2 lanes per row (row sums), log2 lanes per row (table sums),
+ * dynamic shared memory in bytes}. */
+int bioen_b200_selftest_slice_plan(int m, int n, int sms, long long max_dyn_smem, long long out[8]);
 
 /* multi-GPU: one process per GPU, N sharded.  Rank 0 creates the id, the host layer broadcasts it. */
 int bioen_b200_nccl_unique_id(char id[128]);
