@@ -87,3 +87,32 @@ def test_structure_major_only_generator_and_errors(oracle):
     with bioen_b200.Problem(shape=(100, 500)) as p:               # M < 256: no fused kernels, no such mode
         with pytest.raises(RuntimeError, match="256"):
             p.set_option(OPT_YT_ONLY, 1)
+
+
+@pytest.mark.parametrize("minimizer,algorithm", [("lbfgs", ""), ("gsl", "bfgs2"), ("scipy", "lbfgs")])
+def test_find_optimum_on_a_structure_major_only_problem(oracle, minimizer, algorithm):
+    """The reference API (optimize.forces.find_optimum) on a resident problem that holds only the structure-major
+    copy: every step of it -- initial objective, minimiser, weights, averages -- runs on the fused kernels and returns
+    what the default set-up returns."""
+    import bioen_b200
+    from bioen_b200 import optimize
+    M, N, theta = 300, 2500, 5.0
+    P = oracle.synthetic_problem(M, N, seed=77)
+    cfg = optimize.minimize.Parameters(minimizer)
+    cfg["verbose"] = False
+    if algorithm:
+        cfg["algorithm"] = algorithm
+    if minimizer == "gsl":
+        cfg["params"]["max_iterations"] = 40
+    res = {}
+    for only in (False, True):
+        with bioen_b200.Problem(P["yTilde"], structure_major_only=only) as p:
+            p.set_option(5, 0)       # the default set-up on the fused kernels as well (not the slice kernel)
+            res[only] = optimize.forces.find_optimum(P["forces_init"], P["w0"], P["yTilde"], P["yTilde"], P["YTilde"],
+                                                     theta, cfg, problem=p)
+    a, b = res[False], res[True]
+    assert b[3] == a[3] and b[4] == a[4]                              # fmin_initial, fmin_final
+    assert np.array_equal(b[2], a[2])                                 # forces at the optimum
+    assert np.max(np.abs(b[0] - a[0])) < 1e-15                        # weights
+    assert np.max(np.abs(b[1] - a[1])) < 1e-12 * np.max(np.abs(a[1]))  # y . wopt (fused-kernel average vs row pass)
+    assert abs(b[5] - a[5]) < 1e-11 * abs(a[5]) and abs(b[6] - a[6]) < 1e-11 * max(abs(a[6]), 1e-12)
