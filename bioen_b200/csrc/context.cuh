@@ -346,7 +346,9 @@ class Context {
     // Large pageable source (a NumPy array): a plain cudaMemcpy is limited by the driver's single-threaded staging
     // (~10 GB/s).  Here kUpThreads host threads copy row chunks into their own pinned double buffers and push them
     // with async copies on their own streams, so the host memcpy and the PCIe transfer overlap and scale.
-    static constexpr int kUpThreads = 6;
+    // 8 threads: measured on a 16-core box (8 GB, pageable NumPy source, lanes warm): 4 threads 0.72-0.79 s, 6 0.58 s,
+    // 8 0.48-0.50 s, 12 0.57-0.62 s, 16 0.64-1.05 s
+    static constexpr int kUpThreads = 8;
     // page-locked staging of the upload threads: allocated on first use and kept with the context (cudaHostAlloc of
     // 12 x 32 MB costs more than copying 1 GB; a caller that streams a large host matrix through this context chunk
     // by chunk -- Problem.average_streamed -- would otherwise pay it per chunk)
